@@ -1,0 +1,23 @@
+"""audio-calm_b200: B200-native (sm_100a) log-mel front-end and mel statistics pass for Audio-CALM.
+
+The directory name carries a hyphen (it is mandated by the build contract), so the importable name is
+``audio_calm_b200``: the repository root holds a small ``audio_calm_b200.py`` loader that registers this
+directory as that package.  Layout:
+
+    csrc/acb_kernels.cu      hand-written CUDA kernels + the extern "C" ABI (include/audiocalm_b200.h)
+    _lib.py                  nvcc build + ctypes binding (fails loudly when the .so is missing)
+    tables.py                window / slaney filterbank, bit-identical to the reference's torch tables
+    frontend.py              LogMelFrontend: batched + ragged launches, fused peak-norm / affine / moments
+    stats.py                 per-bin moments, single all-reduce, finalise like compute_mel_stats.py
+    sharding.py              utterance sharding across ranks (length-balanced)
+    preprocess/              drop-in mirrors of the reference's preprocess/{core,compute_mel_stats,process_dataset}.py
+"""
+from . import _lib, tables  # noqa: F401
+from .frontend import (LogMelFrontend, MEL_MEAN_DEFAULT, MEL_STD_DEFAULT, RaggedBatch, frames_for_length,  # noqa: F401
+                       pack_clips, padded_frames)
+from .stats import MelStats, MelStatsAccumulator, finalize_moments  # noqa: F401
+from . import frontend, stats, sharding  # noqa: F401
+
+__all__ = ["LogMelFrontend", "MelStatsAccumulator", "MelStats", "RaggedBatch", "pack_clips", "frames_for_length",
+           "padded_frames", "finalize_moments", "MEL_MEAN_DEFAULT", "MEL_STD_DEFAULT"]
+__version__ = "0.1.0"

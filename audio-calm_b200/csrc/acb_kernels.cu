@@ -1,0 +1,1115 @@
+// B200 (sm_100a) kernels + C ABI of the Audio-CALM log-mel front-end.
+//
+// Hot path: acb_logmel_forward -> logmel_fused_kernel.  One persistent launch replaces, per clip,
+// the ~10 library launches behind MelExtractor.forward (reference preprocess/core.py:50-61:
+// reflection_pad1d, framing*window, cuFFT R2C, abs, pow, SGEMM, clamp, log) plus the optional
+// pad-to-4 (preprocess/process_dataset.py:146-150), the VAE's affine normalisation
+// (models/modeling_vae.py:317-319), the peak normalisation of process_audio_chunk
+// (preprocess/core.py:108-110) and the statistics pass (preprocess/compute_mel_stats.py:26-27).
+// Every input sample is read from HBM once (plus a 3/16 halo served by L2) and every output value is
+// written once.
+//
+// Structure of one CTA (256 threads = 8 warps, 2 CTAs per SM, contiguous range of 16-frame tiles):
+//   1. cp.async the tile's (16+3)*256 samples into shared memory (reflection handled for edge tiles);
+//   2. each warp takes one pair of adjacent frames (A, B) and runs ONE complex 1024-point FFT of
+//      A + iB as 32 x 32: radix-2 DIT FFT-32 in registers (FMA butterflies), twiddle, transpose through
+//      a warp-private padded scratch, second FFT-32; the two real spectra are separated with warp
+//      shuffles ((k, 1024-k) partners live in lane 32-j) and |X|^2 goes to the warp's scratch;
+//   3. the CTA applies the banded mel filterbank (1001 non-zero weights instead of a 513x80 GEMM):
+//      lanes = 4 bands x 8 frame pairs, warp-uniform trip counts from a host-built balanced schedule;
+//      clamp, log, optional affine, optional fp64 moments; results staged in shared memory;
+//   4. coalesced store of the 16 x n_mels tile in either layout, plus the reflected pad-to-4 columns.
+// The next tile's samples are prefetched (cp.async) while step 3/4 run.
+#include "audiocalm_b200.h"
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace acb {
+
+constexpr int kNfft = 1024;
+constexpr int kHop = 256;
+constexpr int kBins = 512;                                   // bins 0..511 are produced; 512 (Nyquist) has zero weight
+constexpr int kTileFrames = 16;
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kTileSamples = (kTileFrames + 3) * kHop;       // 4864 samples staged per tile
+constexpr int kRowStride = 33;                               // complex elements per scratch row (conflict-free transpose)
+constexpr int kScratchFloats = 32 * kRowStride * 2 + 2;      // 2114 floats / warp; == 2 (mod 32) so pair strides spread banks
+constexpr int kMaxMels = 128;
+constexpr int kMaxRounds = 6;                                // mel schedule: rounds of (4 bands) per warp
+constexpr int kMaxWeights = 4096;
+
+thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return ACB_ERR_CUDA;
+}
+#define ACB_CUDA(call)                                  \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// --------------------------------------------------------------------------------------------
+// device helpers
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+__host__ __device__ constexpr int brev5(int x) {
+    return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
+}
+
+// cos/sin of 2*pi*j/32, j = 0..15
+__device__ constexpr float kCos32[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                                         0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f,
+                                         0.f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f,
+                                         -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
+__device__ constexpr float kSin32[16] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
+                                         0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
+                                         1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
+                                         0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
+
+// One radix-2 DIT butterfly with twiddle W = exp(-2*pi*i*TW/32): (u, v) -> (u + W v, u - W v).
+// Generic twiddles use the 6-FMA form (sum by 4 FMAs, difference as 2u - sum).
+template <int TW>
+__device__ __forceinline__ void bfly(float& ur, float& ui, float& vr, float& vi) {
+    if (TW == 0) {
+        const float sr = ur + vr, si = ui + vi;
+        vr = ur - vr; vi = ui - vi;
+        ur = sr; ui = si;
+    } else if (TW == 8) {  // W = -i : W v = (vi, -vr)
+        const float sr = ur + vi, si = ui - vr;
+        const float dr = ur - vi, di = ui + vr;
+        ur = sr; ui = si; vr = dr; vi = di;
+    } else {
+        constexpr float wr = kCos32[TW];
+        constexpr float wi = -kSin32[TW];
+        const float sr = fmaf(wr, vr, fmaf(-wi, vi, ur));
+        const float si = fmaf(wr, vi, fmaf(wi, vr, ui));
+        vr = fmaf(2.f, ur, -sr);
+        vi = fmaf(2.f, ui, -si);
+        ur = sr; ui = si;
+    }
+}
+
+template <int S, int K, int J>
+struct BflyLoop {
+    // stage S (m = 2^S), group base K, index J within the half-group
+    static __device__ __forceinline__ void run(float (&xr)[32], float (&xi)[32]) {
+        constexpr int m = 1 << S, half = m >> 1;
+        bfly<J * (32 / m)>(xr[K + J], xi[K + J], xr[K + J + half], xi[K + J + half]);
+        if constexpr (J + 1 < half) {
+            BflyLoop<S, K, J + 1>::run(xr, xi);
+        } else if constexpr (K + m < 32) {
+            BflyLoop<S, K + m, 0>::run(xr, xi);
+        }
+    }
+};
+
+// In-register complex FFT-32, decimation in time: input in bit-reversed order, output natural order.
+__device__ __forceinline__ void fft32_dit(float (&xr)[32], float (&xi)[32]) {
+    BflyLoop<1, 0, 0>::run(xr, xi);
+    BflyLoop<2, 0, 0>::run(xr, xi);
+    BflyLoop<3, 0, 0>::run(xr, xi);
+    BflyLoop<4, 0, 0>::run(xr, xi);
+    BflyLoop<5, 0, 0>::run(xr, xi);
+}
+
+// --------------------------------------------------------------------------------------------
+// fused log-mel kernel
+// --------------------------------------------------------------------------------------------
+struct LogmelParams {
+    // tables (device)
+    const float* window;       // [1024]
+    const float2* twiddle;     // [32][32]  exp(-2*pi*i*k1*n2/1024) at [k1][n2]
+    const float* weights;      // [n_weights] banded filterbank weights * 0.25
+    const int* band_start;     // [n_mels]
+    const int* band_len;       // [n_mels]
+    const int* band_off;       // [n_mels]
+    const short* sched_band;   // [kWarps][kMaxRounds][4]  band id or -1
+    const short* sched_len;    // [kWarps][kMaxRounds]     max band length of the round (0 = unused)
+    int n_mels;
+    int n_weights;
+    float clamp_min;
+    float log_scale;           // 1 for ln, 1/ln(10) for log10 (applied to ln)
+    float log_floor;           // log(clamp_min) computed on the host: clamped values are exactly the reference's floor
+    // batch
+    const float* wav;
+    const long long* clip_offset;
+    const long long* clip_length;
+    long long clip_stride;
+    long long uniform_length;
+    const int* tile_start;
+    int n_clips;
+    int n_tiles;
+    int uniform_tiles_per_clip;
+    const float* clip_peak;
+    // output
+    void* out;
+    int out_bf16;
+    int time_major;
+    const long long* out_offset;
+    long long out_clip_stride;
+    long long frame_capacity;
+    const long long* frame_capacity_per_clip;
+    int pad_multiple;
+    int fill_tail;
+    float fill_value;
+    int affine;
+    float affine_mean;
+    float affine_inv_std;
+    const float* bin_mean;
+    const float* bin_std;
+    double* moments_partial;   // [gridDim.x][2][n_mels] or nullptr
+};
+
+struct SmemLayout {
+    int samples, scratch, twiddle, window, weights, out, band_start, band_len, band_off, sched_band, sched_len, total_bytes;
+};
+
+__host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_weights) {
+    SmemLayout L;
+    int off = 0;  // in 4-byte words
+    L.samples = off; off += kTileSamples;
+    L.scratch = off; off += kWarps * kScratchFloats;
+    L.twiddle = off; off += 32 * 32 * 2;
+    L.window = off; off += kNfft;
+    L.weights = off; off += (n_weights + 3) & ~3;
+    L.out = off; off += kTileFrames * (n_mels + 1);
+    L.band_start = off; off += n_mels;
+    L.band_len = off; off += n_mels;
+    L.band_off = off; off += n_mels;
+    L.sched_band = off; off += (kWarps * kMaxRounds * 4 + 1) / 2;   // shorts
+    L.sched_len = off; off += (kWarps * kMaxRounds + 1) / 2;        // shorts
+    L.total_bytes = off * 4;
+    return L;
+}
+
+struct TileInfo {
+    long long wav_base;    // element index of the clip's first sample in wav
+    long long length;      // samples in the clip
+    long long out_base;    // element offset of the clip in out
+    long long cap;         // frame capacity (row pitch)
+    int frames;            // T
+    int frames_padded;     // T4
+    int f0;                // first frame of this tile
+    int clip;
+    float gain;            // squared waveform scale (fused peak normalisation), 1 otherwise
+};
+
+__device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const TileInfo& t, float* s_samples) {
+    const long long g0 = (long long)t.f0 * kHop - kNfft / 2;  // sample index (relative to the clip) of smem slot 0
+    const float* src = p.wav + t.wav_base;
+    const bool interior = (g0 >= 0) && (g0 + kTileSamples <= t.length);
+    if (interior) {
+        const float* gp = src + g0;
+        if ((reinterpret_cast<uintptr_t>(gp) & 15) == 0) {
+            for (int i = threadIdx.x; i < kTileSamples / 4; i += kThreads) cp_async16(s_samples + 4 * i, gp + 4 * i);
+        } else {
+            for (int i = threadIdx.x; i < kTileSamples; i += kThreads) cp_async4(s_samples + i, gp + i);
+        }
+    } else {
+        // edge tile: reflect about sample 0 and sample L-1 (torch.stft center=True, pad_mode="reflect");
+        // slots that belong only to frames >= T get zeros.
+        const long long L = t.length;
+        for (int i = threadIdx.x; i < kTileSamples; i += kThreads) {
+            long long idx = g0 + i;
+            if (idx < 0) idx = -idx;
+            if (idx >= L) idx = 2 * (L - 1) - idx;
+            float v = 0.f;
+            if (idx >= 0 && idx < L) v = __ldg(src + idx);
+            s_samples[i] = v;
+        }
+    }
+    cp_async_commit();
+}
+
+template <bool kMoments>
+__global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const SmemLayout L = make_smem_layout(p.n_mels, p.n_weights);
+    float* s_samples = smem + L.samples;
+    float* s_scratch = smem + L.scratch;
+    float2* s_tw = reinterpret_cast<float2*>(smem + L.twiddle);
+    float* s_win = smem + L.window;
+    float* s_w = smem + L.weights;
+    float* s_out = smem + L.out;
+    int* s_band_start = reinterpret_cast<int*>(smem + L.band_start);
+    int* s_band_len = reinterpret_cast<int*>(smem + L.band_len);
+    int* s_band_off = reinterpret_cast<int*>(smem + L.band_off);
+    short* s_sched_band = reinterpret_cast<short*>(smem + L.sched_band);
+    short* s_sched_len = reinterpret_cast<short*>(smem + L.sched_len);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int n_mels = p.n_mels;
+    const int out_stride = n_mels + 1;
+
+    // ---- one-time table staging ----
+    for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = p.twiddle[i];
+    for (int i = tid; i < kNfft; i += kThreads) s_win[i] = p.window[i];
+    for (int i = tid; i < p.n_weights; i += kThreads) s_w[i] = p.weights[i];
+    for (int i = tid; i < n_mels; i += kThreads) {
+        s_band_start[i] = p.band_start[i];
+        s_band_len[i] = p.band_len[i];
+        s_band_off[i] = p.band_off[i];
+    }
+    for (int i = tid; i < kWarps * kMaxRounds * 4; i += kThreads) s_sched_band[i] = p.sched_band[i];
+    for (int i = tid; i < kWarps * kMaxRounds; i += kThreads) s_sched_len[i] = p.sched_len[i];
+
+    // ---- this CTA's contiguous tile range ----
+    const long long t_begin = (long long)p.n_tiles * blockIdx.x / gridDim.x;
+    const long long t_end = (long long)p.n_tiles * (blockIdx.x + 1) / gridDim.x;
+
+    // per-thread moment accumulators (fp64), one slot per schedule round
+    double m_sum[kMaxRounds], m_sq[kMaxRounds];
+#pragma unroll
+    for (int r = 0; r < kMaxRounds; ++r) { m_sum[r] = 0.0; m_sq[r] = 0.0; }
+
+    int clip = 0;
+    if (t_begin < t_end) {
+        if (p.tile_start == nullptr) {
+            clip = (int)(t_begin / p.uniform_tiles_per_clip);
+        } else {  // largest clip with tile_start[clip] <= t_begin
+            int lo = 0, hi = p.n_clips;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if ((long long)__ldg(p.tile_start + mid) <= t_begin) lo = mid; else hi = mid;
+            }
+            clip = lo;
+        }
+    }
+
+    auto describe = [&](long long tile, int& clip_io) -> TileInfo {
+        TileInfo t;
+        int first_tile;
+        if (p.tile_start == nullptr) {
+            clip_io = (int)(tile / p.uniform_tiles_per_clip);
+            first_tile = clip_io * p.uniform_tiles_per_clip;
+        } else {
+            while (clip_io + 1 < p.n_clips && (long long)__ldg(p.tile_start + clip_io + 1) <= tile) ++clip_io;
+            first_tile = __ldg(p.tile_start + clip_io);
+        }
+        t.clip = clip_io;
+        t.wav_base = p.clip_offset ? p.clip_offset[clip_io] : (long long)clip_io * p.clip_stride;
+        t.length = p.clip_length ? p.clip_length[clip_io] : p.uniform_length;
+        t.out_base = p.out_offset ? p.out_offset[clip_io] : (long long)clip_io * p.out_clip_stride;
+        t.cap = p.frame_capacity_per_clip ? p.frame_capacity_per_clip[clip_io] : p.frame_capacity;
+        t.frames = 1 + (int)(t.length / kHop);
+        const int rem = t.frames % p.pad_multiple;
+        t.frames_padded = rem ? t.frames + (p.pad_multiple - rem) : t.frames;
+        t.f0 = (int)(tile - first_tile) * kTileFrames;
+        t.gain = 1.f;
+        if (p.clip_peak) {
+            const float peak = __ldg(p.clip_peak + clip_io);
+            if (peak > 0.f) {
+                const float s = 0.95f / (peak + 1e-8f);
+                t.gain = s * s;
+            }
+        }
+        return t;
+    };
+
+    TileInfo cur;
+    if (t_begin < t_end) {
+        cur = describe(t_begin, clip);
+        if (cur.f0 < cur.frames) load_tile_samples(p, cur, s_samples);
+    }
+
+    for (long long tile = t_begin; tile < t_end; ++tile) {
+        cp_async_wait_all();
+        __syncthreads();  // samples (and tables, first iteration) visible; previous tile's s_out fully stored
+
+        const bool has_frames = cur.f0 < cur.frames;  // false for pure tail-fill tiles
+        float* scr = s_scratch + warp * kScratchFloats;
+        float2* scr2 = reinterpret_cast<float2*>(scr);
+
+        // ================= phase 1: one frame pair per warp =================
+        if (has_frames && cur.f0 + 2 * warp < cur.frames) {
+            float xr[32], xi[32];
+            {
+                const float* sp = s_samples + (2 * warp) * kHop + lane;
+                float v[40];
+#pragma unroll
+                for (int r = 0; r < 40; ++r) v[r] = sp[32 * r];
+#pragma unroll
+                for (int n1 = 0; n1 < 32; ++n1) {
+                    const float w = s_win[32 * n1 + lane];
+                    xr[brev5(n1)] = v[n1] * w;        // frame A
+                    xi[brev5(n1)] = v[n1 + 8] * w;    // frame B = A shifted by one hop (8 rows of 32)
+                }
+            }
+            fft32_dit(xr, xi);  // over n1 -> k1 (natural order)
+            // twiddle W_1024^(k1*lane), store transposed: scr[k1][lane]
+#pragma unroll
+            for (int k1 = 0; k1 < 32; ++k1) {
+                float yr = xr[k1], yi = xi[k1];
+                if (k1 > 0) {
+                    const float2 t = s_tw[k1 * 32 + lane];
+                    const float tr = yr * t.x - yi * t.y;
+                    yi = fmaf(yr, t.y, yi * t.x);
+                    yr = tr;
+                }
+                scr2[k1 * kRowStride + lane] = make_float2(yr, yi);
+            }
+            __syncwarp();
+            // lane j = k1 now owns row j: the 32 values over n2
+#pragma unroll
+            for (int n2 = 0; n2 < 32; ++n2) {
+                const float2 z = scr2[lane * kRowStride + n2];
+                xr[brev5(n2)] = z.x;
+                xi[brev5(n2)] = z.y;
+            }
+            __syncwarp();
+            fft32_dit(xr, xi);  // over n2 -> k2 ; lane j holds Z[j + 32*k2]
+            // separate the two real spectra and take |X|^2 (x4; the 1/4 is folded into the weights):
+            //   Z[k] = a+ib, Z[1024-k] = c+id  =>  4|XA|^2 = (a+c)^2+(b-d)^2 , 4|XB|^2 = (a-c)^2+(b+d)^2
+            // Z[1024-k] for k = j + 32m lives in lane (32-j)&31, register 31-m (register 32-m when j == 0).
+            const int src_lane = (32 - lane) & 31;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const float offer_r = (lane == 0) ? xr[(32 - m) & 31] : xr[31 - m];
+                const float offer_i = (lane == 0) ? xi[(32 - m) & 31] : xi[31 - m];
+                const float c = __shfl_sync(0xffffffffu, offer_r, src_lane);
+                const float d = __shfl_sync(0xffffffffu, offer_i, src_lane);
+                const float a = xr[m], b = xi[m];
+                const float apc = a + c, bmd = b - d, amc = a - c, bpd = b + d;
+                const float pa = fmaf(apc, apc, bmd * bmd);
+                const float pb = fmaf(amc, amc, bpd * bpd);
+                scr2[lane + 32 * m] = make_float2(pa, pb);
+            }
+        }
+        __syncthreads();  // power spectra of all pairs visible; sample tile is free again
+
+        // prefetch the next tile's samples while the mel phase runs
+        TileInfo nxt = cur;
+        if (tile + 1 < t_end) {
+            nxt = describe(tile + 1, clip);
+            if (nxt.f0 < nxt.frames) load_tile_samples(p, nxt, s_samples);
+        }
+
+        // ================= phase 2: banded mel projection, clamp, log, affine, moments =================
+        if (has_frames) {
+            const int q = lane >> 3;     // band slot within the round
+            const int pr = lane & 7;     // frame pair
+            const float2* pp = reinterpret_cast<const float2*>(s_scratch + pr * kScratchFloats);
+            const int fA = cur.f0 + 2 * pr;
+            const int pad = cur.frames_padded - cur.frames;
+#pragma unroll
+            for (int r = 0; r < kMaxRounds; ++r) {
+                const int trip = s_sched_len[warp * kMaxRounds + r];
+                if (trip == 0) continue;  // warp-uniform
+                const int b = s_sched_band[(warp * kMaxRounds + r) * 4 + q];
+                int start = 0, len = 0, off = 0;
+                if (b >= 0) { start = s_band_start[b]; len = s_band_len[b]; off = s_band_off[b]; }
+                float accA = 0.f, accB = 0.f;
+#pragma unroll 4
+                for (int i = 0; i < trip; ++i) {
+                    if (i < len) {
+                        const float w = s_w[off + i];
+                        const float2 pw = pp[start + i];
+                        accA = fmaf(w, pw.x, accA);
+                        accB = fmaf(w, pw.y, accB);
+                    }
+                }
+                if (b >= 0) {
+                    const float mA = accA * cur.gain, mB = accB * cur.gain;
+                    float vA = (mA > p.clamp_min) ? __logf(mA) * p.log_scale : p.log_floor;
+                    float vB = (mB > p.clamp_min) ? __logf(mB) * p.log_scale : p.log_floor;
+                    if (kMoments) {
+                        // frames T-2-j (j < pad) are stored twice (reflected pad-to-4 columns) and counted twice
+                        if (fA < cur.frames) {
+                            const double c = (fA <= cur.frames - 2 && fA > cur.frames - 2 - pad) ? 2.0 : 1.0;
+                            m_sum[r] += c * (double)vA;
+                            m_sq[r] += c * (double)vA * (double)vA;
+                        }
+                        if (fA + 1 < cur.frames) {
+                            const double c = (fA + 1 <= cur.frames - 2 && fA + 1 > cur.frames - 2 - pad) ? 2.0 : 1.0;
+                            m_sum[r] += c * (double)vB;
+                            m_sq[r] += c * (double)vB * (double)vB;
+                        }
+                    }
+                    if (p.affine == 1) {
+                        vA = (vA - p.affine_mean) * p.affine_inv_std;
+                        vB = (vB - p.affine_mean) * p.affine_inv_std;
+                    } else if (p.affine == 2) {
+                        const float mu = __ldg(p.bin_mean + b), is = 1.f / __ldg(p.bin_std + b);
+                        vA = (vA - mu) * is;
+                        vB = (vB - mu) * is;
+                    }
+                    s_out[(2 * pr) * out_stride + b] = vA;
+                    s_out[(2 * pr + 1) * out_stride + b] = vB;
+                }
+            }
+        }
+        __syncthreads();  // output tile staged
+
+        // ================= phase 3: coalesced store =================
+        {
+            const int T = cur.frames, T4 = cur.frames_padded;
+            const int pad = T4 - T;
+            const int n_out = kTileFrames * n_mels;
+            float* out_f = reinterpret_cast<float*>(p.out);
+            __nv_bfloat16* out_h = reinterpret_cast<__nv_bfloat16*>(p.out);
+            for (int idx = tid; idx < n_out; idx += kThreads) {
+                int f, b;
+                if (p.time_major) { f = idx / n_mels; b = idx - f * n_mels; }
+                else { b = idx / kTileFrames; f = idx - b * kTileFrames; }
+                const int fr = cur.f0 + f;
+                if (fr >= cur.cap) continue;
+                float v;
+                bool write = false, dup = false;
+                if (fr < T) {
+                    v = s_out[f * out_stride + b];
+                    write = true;
+                    dup = (fr <= T - 2) && (fr > T - 2 - pad);
+                } else if (fr >= T4 && p.fill_tail) {
+                    v = p.fill_value;
+                    write = true;
+                }
+                if (!write) continue;
+                const long long e0 = p.time_major ? (cur.out_base + (long long)fr * n_mels + b)
+                                                  : (cur.out_base + (long long)b * cur.cap + fr);
+                if (p.out_bf16) out_h[e0] = __float2bfloat16_rn(v); else out_f[e0] = v;
+                if (dup) {
+                    const int fd = 2 * T - 2 - fr;  // column T + j with j = T-2-fr
+                    const long long e1 = p.time_major ? (cur.out_base + (long long)fd * n_mels + b)
+                                                      : (cur.out_base + (long long)b * cur.cap + fd);
+                    if (p.out_bf16) out_h[e1] = __float2bfloat16_rn(v); else out_f[e1] = v;
+                }
+            }
+        }
+        cur = nxt;
+    }
+    cp_async_wait_all();
+
+    // ---- per-CTA moment partials: reduce the 8 pair lanes, one writer per (warp, round, slot) ----
+    if (kMoments) {
+        __syncthreads();
+        double* s_m = reinterpret_cast<double*>(s_scratch);  // [2][n_mels]
+        for (int i = tid; i < 2 * n_mels; i += kThreads) s_m[i] = 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kMaxRounds; ++r) {
+            double s = m_sum[r], s2 = m_sq[r];
+#pragma unroll
+            for (int o = 4; o >= 1; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            }
+            const int trip = s_sched_len[warp * kMaxRounds + r];
+            if (trip != 0 && (lane & 7) == 0) {
+                const int b = s_sched_band[(warp * kMaxRounds + r) * 4 + (lane >> 3)];
+                if (b >= 0) { s_m[b] = s; s_m[n_mels + b] = s2; }  // every band has exactly one owner slot
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 2 * n_mels; i += kThreads) p.moments_partial[(size_t)blockIdx.x * 2 * n_mels + i] = s_m[i];
+    }
+}
+
+// Sum per-CTA partials in a fixed order (deterministic) and add into the running accumulators.
+__global__ void moments_reduce_kernel(const double* __restrict__ partial, int n_parts, int n_vals, double* __restrict__ acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_vals) return;
+    double s = 0.0;
+    for (int k = 0; k < n_parts; ++k) s += partial[(size_t)k * n_vals + i];
+    acc[i] += s;
+}
+
+// --------------------------------------------------------------------------------------------
+// per-clip peak, process_audio_chunk
+// --------------------------------------------------------------------------------------------
+__global__ void peak_abs_kernel(const float* __restrict__ wav, const long long* __restrict__ clip_offset,
+                                const long long* __restrict__ clip_length, long long clip_stride, long long uniform_length,
+                                int blocks_per_clip, float* __restrict__ peak_out) {
+    const int clip = blockIdx.x / blocks_per_clip;
+    const int part = blockIdx.x - clip * blocks_per_clip;
+    const long long base = clip_offset ? clip_offset[clip] : (long long)clip * clip_stride;
+    const long long len = clip_length ? clip_length[clip] : uniform_length;
+    const long long chunk = (len + blocks_per_clip - 1) / blocks_per_clip;
+    const long long lo = (long long)part * chunk;
+    const long long hi = min(len, lo + chunk);
+    const float* src = wav + base;
+    float m = 0.f;
+    // scalar head until 16-byte aligned, then float4 body
+    const long long head_end = min(hi, lo + ((4 - ((base + lo) & 3)) & 3));
+    for (long long k = lo + threadIdx.x; k < head_end; k += blockDim.x) m = fmaxf(m, fabsf(src[k]));
+    const long long body0 = head_end;
+    const long long nvec = (hi > body0 && (reinterpret_cast<uintptr_t>(src + body0) & 15) == 0) ? (hi - body0) / 4 : 0;
+    const float4* v4 = reinterpret_cast<const float4*>(src + body0);
+    for (long long k = threadIdx.x; k < nvec; k += blockDim.x) {
+        const float4 v = __ldg(v4 + k);
+        m = fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+    for (long long k = body0 + nvec * 4 + threadIdx.x; k < hi; k += blockDim.x) m = fmaxf(m, fabsf(src[k]));
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float s_m[32];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < (blockDim.x >> 5)) ? s_m[threadIdx.x] : 0.f;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        // non-negative floats order like their bit patterns
+        if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(peak_out + clip), __float_as_uint(m));
+    }
+}
+
+// channel mean (sequential fp32 sum then divide, as torch.mean over dim 0 does) + peak
+__global__ void mixdown_peak_kernel(const float* __restrict__ wav_cl, int channels, long long length, float* __restrict__ out,
+                                    float* __restrict__ peak) {
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < length; i += (long long)gridDim.x * blockDim.x) {
+        float v = wav_cl[i];
+        if (channels > 1) {
+            for (int c = 1; c < channels; ++c) v += wav_cl[(long long)c * length + i];
+            v = __fdiv_rn(v, (float)channels);
+        }
+        out[i] = v;
+        m = fmaxf(m, fabsf(v));
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(peak), __float_as_uint(m));
+}
+
+// wav / (peak + 1e-8) * 0.95, division first (preprocess/core.py:110)
+__global__ void peak_scale_kernel(float* __restrict__ x, long long length, const float* __restrict__ peak) {
+    const float pk = *peak;
+    if (!(pk > 0.f)) return;
+    const float d = pk + 1e-8f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < length; i += (long long)gridDim.x * blockDim.x)
+        x[i] = __fmul_rn(__fdiv_rn(x[i], d), 0.95f);
+}
+
+// --------------------------------------------------------------------------------------------
+// standalone moments over stored features, per-utterance normalisation
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_feat(const T* p, long long i);
+template <>
+__device__ __forceinline__ float load_feat<float>(const float* p, long long i) { return __ldg(p + i); }
+template <>
+__device__ __forceinline__ float load_feat<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
+
+// one warp per (clip, band) row; rows are dealt round-robin to the grid's warps; per-warp fp64 accumulators in
+// shared memory, combined in a fixed order -> deterministic partial per CTA.
+template <typename T>
+__global__ void __launch_bounds__(256) moments_rows_kernel(const T* __restrict__ feat, int n_clips, int n_mels, long long cap,
+                                                           long long clip_stride, const long long* __restrict__ frames,
+                                                           double* __restrict__ partial) {
+    extern __shared__ double s_acc[];  // [warps][2][n_mels]
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < warps * 2 * n_mels; i += blockDim.x) s_acc[i] = 0.0;
+    __syncthreads();
+    double* my = s_acc + (size_t)warp * 2 * n_mels;
+    const long long n_rows = (long long)n_clips * n_mels;
+    for (long long row = (long long)blockIdx.x * warps + warp; row < n_rows; row += (long long)gridDim.x * warps) {
+        const int clip = (int)(row / n_mels), b = (int)(row - (long long)clip * n_mels);
+        const long long n_fr = frames ? frames[clip] : cap;
+        const T* src = feat + (long long)clip * clip_stride + (long long)b * cap;
+        double s = 0.0, s2 = 0.0;
+        for (long long i = lane; i < n_fr; i += 32) {
+            const double v = (double)load_feat<T>(src, i);
+            s += v;
+            s2 += v * v;
+        }
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0) { my[b] += s; my[n_mels + b] += s2; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * n_mels; i += blockDim.x) {
+        double s = 0.0;
+        for (int w = 0; w < warps; ++w) s += s_acc[(size_t)w * 2 * n_mels + i];
+        partial[(size_t)blockIdx.x * 2 * n_mels + i] = s;
+    }
+}
+
+// (x - mean_t) / max(std_t, min_std) per (clip, band) row, unbiased std (eval/eval_vae.py:80-82)
+__global__ void __launch_bounds__(128) normalize_rows_kernel(const float* __restrict__ feat, float* __restrict__ out, int n_mels,
+                                                             long long cap, const long long* __restrict__ frames, float min_std) {
+    const int clip = blockIdx.x / n_mels;
+    const long long T = frames ? frames[clip] : cap;
+    const float* src = feat + (long long)blockIdx.x * cap;
+    float* dst = out + (long long)blockIdx.x * cap;
+    __shared__ double s_red[4];
+    __shared__ float s_stat[2];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < T; i += blockDim.x) s += (double)src[i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) s_stat[0] = (float)((s_red[0] + s_red[1] + s_red[2] + s_red[3]) / (double)T);
+    __syncthreads();
+    const float mean = s_stat[0];
+    double s2 = 0.0;
+    for (long long i = threadIdx.x; i < T; i += blockDim.x) {
+        const double d = (double)src[i] - (double)mean;
+        s2 += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double var = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) / (double)(T > 1 ? T - 1 : 1);
+        s_stat[1] = fmaxf((float)sqrt(var), min_std);
+    }
+    __syncthreads();
+    const float sd = s_stat[1];
+    for (long long i = threadIdx.x; i < T; i += blockDim.x) dst[i] = __fdiv_rn(src[i] - mean, sd);
+}
+
+}  // namespace acb
+
+// ==============================================================================================
+// host side: handle, planning, launches
+// ==============================================================================================
+struct acb_frontend {
+    int device = 0;
+    int n_fft = 0, hop = 0, n_mels = 0, n_weights = 0, log_kind = 0;
+    float clamp_min = 0.f;
+    int num_sms = 0;
+    int grid = 0;          // persistent grid (CTAs)
+    int smem_bytes = 0;
+    // one device allocation holding every table
+    void* d_blob = nullptr;
+    const float* d_window = nullptr;
+    const float2* d_twiddle = nullptr;
+    const float* d_weights = nullptr;
+    const int* d_band_start = nullptr;
+    const int* d_band_len = nullptr;
+    const int* d_band_off = nullptr;
+    const short* d_sched_band = nullptr;
+    const short* d_sched_len = nullptr;
+    // host-path streams/events (created lazily)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev;
+    std::mutex mu;
+};
+
+using namespace acb;
+
+extern "C" {
+
+int acb_abi_version(void) { return ACB_ABI_VERSION; }
+const char* acb_last_error(void) { return g_last_error.c_str(); }
+int acb_frames_per_tile(void) { return kTileFrames; }
+
+int64_t acb_frames_for_length(int64_t length, int n_fft, int hop) {
+    if (n_fft <= 0 || hop <= 0) return -1;
+    if (length <= n_fft / 2) return -1;
+    return 1 + length / hop;
+}
+
+int64_t acb_padded_frames(int64_t frames, int multiple) {
+    if (multiple <= 1) return frames;
+    const int64_t r = frames % multiple;
+    return r ? frames + (multiple - r) : frames;
+}
+
+int64_t acb_plan_tiles(const int64_t* lengths_host, int32_t n_clips, int n_fft, int hop, int64_t frame_capacity,
+                       int32_t* tile_start_host) {
+    if (!lengths_host || !tile_start_host || n_clips < 0) return fail(ACB_ERR_INVALID, "acb_plan_tiles: null argument");
+    int64_t total = 0;
+    for (int32_t i = 0; i < n_clips; ++i) {
+        const int64_t T = acb_frames_for_length(lengths_host[i], n_fft, hop);
+        if (T < 0) {
+            return fail(ACB_ERR_INVALID, "acb_plan_tiles: clip " + std::to_string(i) + " has " + std::to_string(lengths_host[i]) +
+                                             " samples; reflect padding needs more than " + std::to_string(n_fft / 2));
+        }
+        const int64_t cover = frame_capacity > 0 ? frame_capacity : T;
+        tile_start_host[i] = (int32_t)total;
+        total += (cover + kTileFrames - 1) / kTileFrames;
+        if (total > INT32_MAX) return fail(ACB_ERR_INVALID, "acb_plan_tiles: more than 2^31 tiles in one call");
+    }
+    tile_start_host[n_clips] = (int32_t)total;
+    return total;
+}
+
+int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int n_mels, const float* window_host,
+                        const float* fb_host, float clamp_min, int log_kind) {
+    if (!out || !window_host || !fb_host) return fail(ACB_ERR_INVALID, "acb_frontend_create: null argument");
+    if (n_fft != kNfft || hop != kHop)
+        return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: this build has kernels for n_fft=1024, hop=256 only (got n_fft=" +
+                                             std::to_string(n_fft) + ", hop=" + std::to_string(hop) + ")");
+    if (n_mels < 1 || n_mels > kMaxMels) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: n_mels must be in [1, 128]");
+    if (log_kind != ACB_LOG_NATURAL && log_kind != ACB_LOG_10) return fail(ACB_ERR_INVALID, "acb_frontend_create: bad log_kind");
+    const int n_freq = n_fft / 2 + 1;
+
+    // banded form of the filterbank; the 1/4 of the packed-pair power spectrum is folded in (exact scaling)
+    std::vector<int> start(n_mels, 0), len(n_mels, 0), off(n_mels, 0);
+    std::vector<float> weights;
+    for (int m = 0; m < n_mels; ++m) {
+        int lo = -1, hi = -1;
+        for (int f = 0; f < n_freq; ++f)
+            if (fb_host[(size_t)f * n_mels + m] != 0.f) { if (lo < 0) lo = f; hi = f; }
+        off[m] = (int)weights.size();
+        if (lo >= 0) {
+            if (hi >= kBins) {
+                // the Nyquist bin is not produced by the packed FFT; the slaney bank (f_max = sr/2) has zero weight there
+                if (fb_host[(size_t)(n_freq - 1) * n_mels + m] != 0.f)
+                    return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: filterbank has weight on the Nyquist bin");
+            }
+            start[m] = lo;
+            len[m] = hi - lo + 1;
+            for (int f = lo; f <= hi; ++f) weights.push_back(fb_host[(size_t)f * n_mels + m] * 0.25f);
+        }
+    }
+    if ((int)weights.size() > kMaxWeights) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: filterbank too dense");
+
+    // mel schedule: bands sorted by run length, groups of 4 (one per lane slot), groups dealt to the 8 warps
+    // longest-processing-time first so every warp sums about the same number of bins.
+    std::vector<int> order(n_mels);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
+    const int n_groups = (n_mels + 3) / 4;
+    std::vector<short> sched_band(kWarps * kMaxRounds * 4, (short)-1), sched_len(kWarps * kMaxRounds, (short)0);
+    std::vector<int> load(kWarps, 0), rounds(kWarps, 0);
+    for (int g = 0; g < n_groups; ++g) {
+        int best = -1;
+        for (int w = 0; w < kWarps; ++w)
+            if (rounds[w] < kMaxRounds && (best < 0 || load[w] < load[best])) best = w;
+        if (best < 0) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel schedule overflow");
+        int gl = 0;
+        for (int q = 0; q < 4; ++q) {
+            const int idx = 4 * g + q;
+            if (idx < n_mels) {
+                sched_band[(best * kMaxRounds + rounds[best]) * 4 + q] = (short)order[idx];
+                gl = std::max(gl, len[order[idx]]);
+            }
+        }
+        sched_len[best * kMaxRounds + rounds[best]] = (short)std::max(gl, 1);
+        load[best] += gl + 8;  // + fixed per-round epilogue cost
+        rounds[best]++;
+    }
+
+    // twiddles exp(-2*pi*i*k1*n2/1024) in double, rounded once
+    std::vector<float2> tw(32 * 32);
+    for (int k1 = 0; k1 < 32; ++k1)
+        for (int n2 = 0; n2 < 32; ++n2) {
+            const double a = -2.0 * M_PI * (double)(k1 * n2) / 1024.0;
+            tw[k1 * 32 + n2] = make_float2((float)cos(a), (float)sin(a));
+        }
+
+    int prev = 0;
+    ACB_CUDA(cudaGetDevice(&prev));
+    ACB_CUDA(cudaSetDevice(device));
+    auto* fe = new acb_frontend();
+    fe->device = device; fe->n_fft = n_fft; fe->hop = hop; fe->n_mels = n_mels; fe->n_weights = (int)weights.size();
+    fe->log_kind = log_kind; fe->clamp_min = clamp_min;
+
+    // pack the blob
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
+    const size_t o_win = take(sizeof(float) * kNfft), o_tw = take(sizeof(float2) * 1024), o_w = take(sizeof(float) * std::max<size_t>(weights.size(), 1)),
+                 o_bs = take(sizeof(int) * n_mels), o_bl = take(sizeof(int) * n_mels), o_bo = take(sizeof(int) * n_mels),
+                 o_sb = take(sizeof(short) * sched_band.size()), o_sl = take(sizeof(short) * sched_len.size());
+    std::vector<unsigned char> host(o, 0);
+    memcpy(host.data() + o_win, window_host, sizeof(float) * kNfft);
+    memcpy(host.data() + o_tw, tw.data(), sizeof(float2) * 1024);
+    if (!weights.empty()) memcpy(host.data() + o_w, weights.data(), sizeof(float) * weights.size());
+    memcpy(host.data() + o_bs, start.data(), sizeof(int) * n_mels);
+    memcpy(host.data() + o_bl, len.data(), sizeof(int) * n_mels);
+    memcpy(host.data() + o_bo, off.data(), sizeof(int) * n_mels);
+    memcpy(host.data() + o_sb, sched_band.data(), sizeof(short) * sched_band.size());
+    memcpy(host.data() + o_sl, sched_len.data(), sizeof(short) * sched_len.size());
+    cudaError_t e = cudaMalloc(&fe->d_blob, o);
+    if (e == cudaSuccess) e = cudaMemcpy(fe->d_blob, host.data(), o, cudaMemcpyHostToDevice);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
+    const SmemLayout L = make_smem_layout(n_mels, fe->n_weights);
+    fe->smem_bytes = L.total_bytes;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
+    int occ = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, logmel_fused_kernel<false>, kThreads, L.total_bytes);
+    if (e != cudaSuccess) {
+        if (fe->d_blob) cudaFree(fe->d_blob);
+        delete fe;
+        cudaSetDevice(prev);
+        return cuda_fail(e, "acb_frontend_create");
+    }
+    fe->num_sms = prop.multiProcessorCount;
+    fe->grid = fe->num_sms * std::max(occ, 1);
+    auto* base = static_cast<unsigned char*>(fe->d_blob);
+    fe->d_window = reinterpret_cast<const float*>(base + o_win);
+    fe->d_twiddle = reinterpret_cast<const float2*>(base + o_tw);
+    fe->d_weights = reinterpret_cast<const float*>(base + o_w);
+    fe->d_band_start = reinterpret_cast<const int*>(base + o_bs);
+    fe->d_band_len = reinterpret_cast<const int*>(base + o_bl);
+    fe->d_band_off = reinterpret_cast<const int*>(base + o_bo);
+    fe->d_sched_band = reinterpret_cast<const short*>(base + o_sb);
+    fe->d_sched_len = reinterpret_cast<const short*>(base + o_sl);
+    cudaSetDevice(prev);
+    *out = fe;
+    return ACB_OK;
+}
+
+int acb_frontend_destroy(acb_frontend* fe) {
+    if (!fe) return ACB_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(fe->device);
+    for (auto ev : fe->ev) cudaEventDestroy(ev);
+    if (fe->s_in) cudaStreamDestroy(fe->s_in);
+    if (fe->s_out) cudaStreamDestroy(fe->s_out);
+    if (fe->d_blob) cudaFree(fe->d_blob);
+    cudaSetDevice(prev);
+    delete fe;
+    return ACB_OK;
+}
+
+int64_t acb_moments_workspace_bytes(const acb_frontend* fe) {
+    if (!fe) return fail(ACB_ERR_INVALID, "acb_moments_workspace_bytes: null handle");
+    return (int64_t)fe->grid * 2 * fe->n_mels * (int64_t)sizeof(double);
+}
+
+int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* stream) {
+    if (!fe || !a) return fail(ACB_ERR_INVALID, "acb_logmel_forward: null argument");
+    if (a->n_clips <= 0 || a->n_tiles <= 0) return ACB_OK;  // empty batch
+    if (!a->wav || !a->out) return fail(ACB_ERR_INVALID, "acb_logmel_forward: null wav/out");
+    if (a->out_dtype != ACB_F32 && a->out_dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_logmel_forward: bad out_dtype");
+    if (a->out_layout != ACB_MEL_MAJOR && a->out_layout != ACB_TIME_MAJOR) return fail(ACB_ERR_INVALID, "acb_logmel_forward: bad out_layout");
+    if (a->pad_multiple < 1) return fail(ACB_ERR_INVALID, "acb_logmel_forward: pad_multiple must be >= 1");
+    if (a->affine < 0 || a->affine > 2) return fail(ACB_ERR_INVALID, "acb_logmel_forward: bad affine mode");
+    if (a->affine == 2 && (!a->bin_mean || !a->bin_std)) return fail(ACB_ERR_INVALID, "acb_logmel_forward: per-bin affine needs bin_mean/bin_std");
+    if (a->affine == 1 && !(a->affine_std > 0.f)) return fail(ACB_ERR_INVALID, "acb_logmel_forward: affine_std must be > 0");
+    if (a->moments && !a->moments_workspace) return fail(ACB_ERR_INVALID, "acb_logmel_forward: moments need a workspace");
+    if (!a->frame_capacity_per_clip && a->frame_capacity <= 0) return fail(ACB_ERR_INVALID, "acb_logmel_forward: frame_capacity must be > 0");
+
+    LogmelParams p{};
+    p.window = fe->d_window; p.twiddle = fe->d_twiddle; p.weights = fe->d_weights;
+    p.band_start = fe->d_band_start; p.band_len = fe->d_band_len; p.band_off = fe->d_band_off;
+    p.sched_band = fe->d_sched_band; p.sched_len = fe->d_sched_len;
+    p.n_mels = fe->n_mels; p.n_weights = fe->n_weights; p.clamp_min = fe->clamp_min;
+    p.log_scale = fe->log_kind == ACB_LOG_10 ? 0.43429448190325176f : 1.f;
+    p.log_floor = fe->log_kind == ACB_LOG_10 ? log10f(fe->clamp_min) : logf(fe->clamp_min);
+    p.wav = a->wav;
+    p.clip_offset = reinterpret_cast<const long long*>(a->clip_offset);
+    p.clip_length = reinterpret_cast<const long long*>(a->clip_length);
+    p.clip_stride = a->clip_stride; p.uniform_length = a->uniform_length;
+    p.tile_start = a->tile_start; p.n_clips = a->n_clips; p.n_tiles = a->n_tiles;
+    p.uniform_tiles_per_clip = 1;
+    if (!a->tile_start) {
+        if (a->clip_length) return fail(ACB_ERR_INVALID, "acb_logmel_forward: ragged clips need tile_start (acb_plan_tiles)");
+        const int64_t T = acb_frames_for_length(a->uniform_length, fe->n_fft, fe->hop);
+        if (T < 0) return fail(ACB_ERR_INVALID, "acb_logmel_forward: clips of " + std::to_string(a->uniform_length) +
+                                                    " samples are too short for reflect padding of " + std::to_string(fe->n_fft / 2));
+        const int64_t cover = a->fill_tail ? a->frame_capacity : T;
+        p.uniform_tiles_per_clip = (int)((cover + kTileFrames - 1) / kTileFrames);
+        if ((int64_t)p.uniform_tiles_per_clip * a->n_clips != a->n_tiles)
+            return fail(ACB_ERR_INVALID, "acb_logmel_forward: n_tiles does not match n_clips * tiles per clip");
+        if (acb_padded_frames(T, a->pad_multiple) > a->frame_capacity)
+            return fail(ACB_ERR_INVALID, "acb_logmel_forward: frame_capacity smaller than the padded frame count");
+    }
+    p.clip_peak = a->clip_peak;
+    p.out = a->out; p.out_bf16 = a->out_dtype == ACB_BF16; p.time_major = a->out_layout == ACB_TIME_MAJOR;
+    p.out_offset = reinterpret_cast<const long long*>(a->out_offset);
+    p.out_clip_stride = a->out_clip_stride; p.frame_capacity = a->frame_capacity;
+    p.frame_capacity_per_clip = reinterpret_cast<const long long*>(a->frame_capacity_per_clip);
+    p.pad_multiple = a->pad_multiple; p.fill_tail = a->fill_tail; p.fill_value = a->fill_value;
+    p.affine = a->affine; p.affine_mean = a->affine_mean;
+    p.affine_inv_std = a->affine == 1 ? (float)(1.0 / (double)a->affine_std) : 1.f;
+    p.bin_mean = a->bin_mean; p.bin_std = a->bin_std;
+    p.moments_partial = a->moments ? static_cast<double*>(a->moments_workspace) : nullptr;
+
+    int prev = 0;
+    ACB_CUDA(cudaGetDevice(&prev));
+    if (prev != fe->device) ACB_CUDA(cudaSetDevice(fe->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = fe->grid;  // persistent: every CTA takes a contiguous share of the tiles (possibly empty)
+    if (a->moments) {
+        logmel_fused_kernel<true><<<grid, kThreads, fe->smem_bytes, st>>>(p);
+        const int n_vals = 2 * fe->n_mels;
+        moments_reduce_kernel<<<(n_vals + 127) / 128, 128, 0, st>>>(p.moments_partial, grid, n_vals, a->moments);
+    } else {
+        logmel_fused_kernel<false><<<grid, kThreads, fe->smem_bytes, st>>>(p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (prev != fe->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "acb_logmel_forward launch");
+    return ACB_OK;
+}
+
+int acb_peak_abs(const float* wav, const int64_t* clip_offset, const int64_t* clip_length, int64_t clip_stride,
+                 int64_t uniform_length, int32_t n_clips, float* peak_out, void* stream) {
+    if (n_clips <= 0) return ACB_OK;
+    if (!wav || !peak_out) return fail(ACB_ERR_INVALID, "acb_peak_abs: null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ACB_CUDA(cudaMemsetAsync(peak_out, 0, sizeof(float) * n_clips, st));
+    // enough CTAs to fill the chip even for a single clip
+    int blocks_per_clip = std::max(1, std::min(64, (148 * 8 + n_clips - 1) / n_clips));
+    peak_abs_kernel<<<n_clips * blocks_per_clip, 256, 0, st>>>(wav, reinterpret_cast<const long long*>(clip_offset),
+                                                               reinterpret_cast<const long long*>(clip_length), clip_stride,
+                                                               uniform_length, blocks_per_clip, peak_out);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
+int acb_process_audio_chunk(const float* wav_cl, int32_t channels, int64_t length, float* out, float* scratch_peak, void* stream) {
+    if (!wav_cl || !out || !scratch_peak || channels < 1 || length < 0) return fail(ACB_ERR_INVALID, "acb_process_audio_chunk: bad argument");
+    if (length == 0) return ACB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ACB_CUDA(cudaMemsetAsync(scratch_peak, 0, sizeof(float), st));
+    const int blocks = (int)std::min<int64_t>(148 * 8, (length + 255) / 256);
+    mixdown_peak_kernel<<<blocks, 256, 0, st>>>(wav_cl, channels, length, out, scratch_peak);
+    peak_scale_kernel<<<blocks, 256, 0, st>>>(out, length, scratch_peak);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
+int acb_moments_accumulate(const void* feat, int32_t dtype, int32_t n_clips, int32_t n_mels, int64_t frame_capacity,
+                           int64_t clip_stride, const int64_t* frames, double* moments, void* stream) {
+    if (n_clips <= 0) return ACB_OK;
+    if (!feat || !moments || n_mels < 1 || frame_capacity < 1) return fail(ACB_ERR_INVALID, "acb_moments_accumulate: bad argument");
+    if (dtype != ACB_F32 && dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_moments_accumulate: bad dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int warps = 8;
+    const long long n_rows = (long long)n_clips * n_mels;
+    const int grid = (int)std::min<long long>(148 * 4, (n_rows + warps - 1) / warps);
+    double* partial = nullptr;
+    ACB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(double) * (size_t)grid * 2 * n_mels, st));
+    const size_t smem = sizeof(double) * warps * 2 * n_mels;
+    if (dtype == ACB_F32)
+        moments_rows_kernel<float><<<grid, warps * 32, smem, st>>>(static_cast<const float*>(feat), n_clips, n_mels, frame_capacity,
+                                                                    clip_stride, reinterpret_cast<const long long*>(frames), partial);
+    else
+        moments_rows_kernel<__nv_bfloat16><<<grid, warps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(feat), n_clips, n_mels,
+                                                                            frame_capacity, clip_stride,
+                                                                            reinterpret_cast<const long long*>(frames), partial);
+    moments_reduce_kernel<<<(2 * n_mels + 127) / 128, 128, 0, st>>>(partial, grid, 2 * n_mels, moments);
+    cudaError_t e = cudaGetLastError();
+    cudaFreeAsync(partial, st);
+    if (e != cudaSuccess) return cuda_fail(e, "acb_moments_accumulate launch");
+    return ACB_OK;
+}
+
+int acb_moments_finalize(const double* m, int32_t n_mels, int64_t frames, double var_floor, double* bin_mean, double* bin_std,
+                         double* global_mean, double* global_std) {
+    if (!m || n_mels < 1 || frames < 1) return fail(ACB_ERR_INVALID, "acb_moments_finalize: bad argument");
+    double S = 0.0, S2 = 0.0;
+    for (int b = 0; b < n_mels; ++b) {
+        const double mean = m[b] / (double)frames;
+        const double var = std::max(m[n_mels + b] / (double)frames - mean * mean, var_floor);
+        if (bin_mean) bin_mean[b] = mean;
+        if (bin_std) bin_std[b] = std::sqrt(var);
+        S += m[b];
+        S2 += m[n_mels + b];
+    }
+    const double N = (double)frames * (double)n_mels;  // mel.numel() summed over files (compute_mel_stats.py:28)
+    const double mean = S / N;
+    const double var = std::max(S2 / N - mean * mean, var_floor);
+    if (global_mean) *global_mean = mean;
+    if (global_std) *global_std = std::sqrt(var);
+    return ACB_OK;
+}
+
+int acb_normalize_per_utterance(const float* feat, float* out, int32_t n_clips, int32_t n_mels, int64_t frame_capacity,
+                                const int64_t* frames, float min_std, void* stream) {
+    if (n_clips <= 0) return ACB_OK;
+    if (!feat || !out || n_mels < 1 || frame_capacity < 1) return fail(ACB_ERR_INVALID, "acb_normalize_per_utterance: bad argument");
+    normalize_rows_kernel<<<n_clips * n_mels, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        feat, out, n_mels, frame_capacity, reinterpret_cast<const long long*>(frames), min_std);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
+int acb_logmel_forward_host(const acb_frontend* fe_c, const float* wav_host, int32_t n_clips, int64_t length, void* out_host,
+                            acb_logmel_args* tmpl, float* dev_in, void* dev_out, int32_t n_chunks, void* stream) {
+    if (!fe_c || !wav_host || !out_host || !tmpl || !dev_in || !dev_out) return fail(ACB_ERR_INVALID, "acb_logmel_forward_host: null argument");
+    if (n_clips <= 0) return ACB_OK;
+    auto* fe = const_cast<acb_frontend*>(fe_c);
+    const int64_t T = acb_frames_for_length(length, fe->n_fft, fe->hop);
+    if (T < 0) return fail(ACB_ERR_INVALID, "acb_logmel_forward_host: clips too short");
+    n_chunks = std::max(1, std::min(n_chunks, n_clips));
+    const int64_t cap = tmpl->frame_capacity;
+    const size_t esz = tmpl->out_dtype == ACB_BF16 ? 2 : 4;
+    const int64_t out_clip = (int64_t)fe->n_mels * cap;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    std::lock_guard<std::mutex> lock(fe->mu);
+    int prev = 0;
+    ACB_CUDA(cudaGetDevice(&prev));
+    if (prev != fe->device) ACB_CUDA(cudaSetDevice(fe->device));
+    if (!fe->s_in) {
+        ACB_CUDA(cudaStreamCreateWithFlags(&fe->s_in, cudaStreamNonBlocking));
+        ACB_CUDA(cudaStreamCreateWithFlags(&fe->s_out, cudaStreamNonBlocking));
+    }
+    while ((int)fe->ev.size() < 2 * n_chunks + 1) {
+        cudaEvent_t e;
+        ACB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        fe->ev.push_back(e);
+    }
+    // order the side streams after work already queued on the caller's stream
+    ACB_CUDA(cudaEventRecord(fe->ev[2 * n_chunks], st));
+    ACB_CUDA(cudaStreamWaitEvent(fe->s_in, fe->ev[2 * n_chunks], 0));
+    const int cover_tiles = (int)(((tmpl->fill_tail ? cap : T) + kTileFrames - 1) / kTileFrames);
+    int rc = ACB_OK;
+    for (int c = 0; c < n_chunks && rc == ACB_OK; ++c) {
+        const int c0 = (int)((int64_t)n_clips * c / n_chunks), c1 = (int)((int64_t)n_clips * (c + 1) / n_chunks);
+        if (c1 == c0) continue;
+        ACB_CUDA(cudaMemcpyAsync(dev_in + (int64_t)c0 * length, wav_host + (int64_t)c0 * length, sizeof(float) * (size_t)(c1 - c0) * length,
+                                 cudaMemcpyHostToDevice, fe->s_in));
+        ACB_CUDA(cudaEventRecord(fe->ev[2 * c], fe->s_in));
+        ACB_CUDA(cudaStreamWaitEvent(st, fe->ev[2 * c], 0));
+        acb_logmel_args a = *tmpl;
+        a.wav = dev_in + (int64_t)c0 * length;
+        a.clip_offset = nullptr; a.clip_length = nullptr; a.tile_start = nullptr;
+        a.clip_stride = length; a.uniform_length = length;
+        a.n_clips = c1 - c0; a.n_tiles = (c1 - c0) * cover_tiles;
+        a.out = static_cast<unsigned char*>(dev_out) + (size_t)c0 * out_clip * esz;
+        a.out_offset = nullptr; a.out_clip_stride = out_clip; a.frame_capacity_per_clip = nullptr;
+        if (a.clip_peak) a.clip_peak = tmpl->clip_peak + c0;
+        rc = acb_logmel_forward(fe, &a, st);
+        if (rc != ACB_OK) break;
+        ACB_CUDA(cudaEventRecord(fe->ev[2 * c + 1], st));
+        ACB_CUDA(cudaStreamWaitEvent(fe->s_out, fe->ev[2 * c + 1], 0));
+        ACB_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(out_host) + (size_t)c0 * out_clip * esz,
+                                 static_cast<unsigned char*>(dev_out) + (size_t)c0 * out_clip * esz, (size_t)(c1 - c0) * out_clip * esz,
+                                 cudaMemcpyDeviceToHost, fe->s_out));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(fe->s_out);
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    cudaError_t e3 = cudaStreamSynchronize(fe->s_in);
+    if (prev != fe->device) cudaSetDevice(prev);
+    if (rc != ACB_OK) return rc;
+    if (e1 != cudaSuccess) return cuda_fail(e1, "acb_logmel_forward_host sync");
+    if (e2 != cudaSuccess) return cuda_fail(e2, "acb_logmel_forward_host sync");
+    if (e3 != cudaSuccess) return cuda_fail(e3, "acb_logmel_forward_host sync");
+    return ACB_OK;
+}
+
+}  // extern "C"

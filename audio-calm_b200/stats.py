@@ -1,0 +1,125 @@
+"""Dataset-wide mel statistics: per-bin moments on the device, one all-reduce, finalise like the reference.
+
+The reference's pass (``preprocess/compute_mel_stats.py:19-36``) is a single-process loop that keeps one
+global ``sum``, ``sum of squares`` and ``count``.  Here every GPU keeps ``sum[b]`` and ``sumsq[b]`` per mel
+bin in fp64 plus an exact integer frame count for its shard of utterances; the shards are combined with ONE
+``all_reduce(SUM)`` of ``2 * n_mels + 1`` fp64 values and finalised identically on every rank.  The
+reference's two scalars follow exactly from the per-bin moments
+(``S = sum_b sum[b]``, ``N = n_mels * frames``).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+VAR_FLOOR = 1e-8  # compute_mel_stats.py:32
+
+
+@dataclass
+class MelStats:
+    bin_mean: np.ndarray     # [n_mels] fp64
+    bin_std: np.ndarray      # [n_mels] fp64
+    mel_mean: float          # the reference's "Global mel_mean"
+    mel_std: float           # the reference's "Global mel_std"
+    frames: int
+    count: int               # n_mels * frames == sum of mel.numel() (compute_mel_stats.py:28)
+
+    def lines(self):
+        """Exactly what the reference prints (compute_mel_stats.py:35-36; two spaces after ``mel_std:``)."""
+        return [f"Global mel_mean: {self.mel_mean:.6f}", f"Global mel_std:  {self.mel_std:.6f}"]
+
+    def state(self) -> Dict[str, object]:
+        """Stats-file payload: the only on-disk stats layout of the reference is ``{"mean": [D], "std": [D]}``
+        (preprocess/compute_latent_stats.py:44-47); the scalar ``mel_mean`` / ``mel_std`` (pasted by hand into
+        config/calm_config.yaml:62-63 in the reference) ride along."""
+        return {"mean": torch.from_numpy(self.bin_mean.astype(np.float32)),
+                "std": torch.from_numpy(self.bin_std.astype(np.float32)),
+                "mel_mean": self.mel_mean, "mel_std": self.mel_std, "frames": self.frames, "count": self.count}
+
+    def save(self, path: str) -> None:
+        torch.save(self.state(), path)
+
+
+def finalize_moments(moments: np.ndarray, frames: int, var_floor: float = VAR_FLOOR) -> MelStats:
+    """Host-side finalise (compute_mel_stats.py:30-33 per bin and globally).  Pure numpy: also used on CPU by the
+    multi-process tests; the C-ABI twin is ``acb_moments_finalize``."""
+    m = np.asarray(moments, dtype=np.float64)
+    n_mels = m.shape[0] // 2
+    if frames <= 0:
+        raise ValueError("no frames accumulated")
+    s, s2 = m[:n_mels], m[n_mels:]
+    bin_mean = s / frames
+    bin_var = np.maximum(s2 / frames - bin_mean * bin_mean, var_floor)
+    count = n_mels * frames
+    mean = float(s.sum() / count)
+    var = max(float(s2.sum() / count) - mean * mean, var_floor)
+    return MelStats(bin_mean, np.sqrt(bin_var), mean, math.sqrt(var), int(frames), int(count))
+
+
+class MelStatsAccumulator:
+    """Running per-bin moments on one device (fp64) + exact frame count on the host."""
+
+    def __init__(self, n_mels: int = 80, device="cuda"):
+        self.n_mels = int(n_mels)
+        self.device = torch.device(device)
+        self.moments = torch.zeros(2 * self.n_mels, dtype=torch.float64, device=self.device)
+        self.frames = 0
+
+    # -- S1: moments of features that already exist (files written by the dataset driver) --
+    def update(self, feat: torch.Tensor, frames: Optional[torch.Tensor] = None) -> None:
+        """``feat[B, n_mels, cap]`` (or ``[n_mels, T]``) fp32/bf16 on the device; ``frames[B]`` int64 valid frames."""
+        from . import _lib
+        lib = _lib.load()
+        if feat.dim() == 2:
+            feat = feat.unsqueeze(0)
+        if not feat.is_cuda:
+            raise RuntimeError("MelStatsAccumulator.update expects device features (no CPU fallback)")
+        if feat.dtype not in (torch.float32, torch.bfloat16):
+            feat = feat.float()
+        feat = feat.contiguous()
+        B, M, cap = (int(x) for x in feat.shape)
+        if M != self.n_mels:
+            raise ValueError(f"expected {self.n_mels} mel bins, got {M}")
+        fr_ptr = None
+        if frames is not None:
+            frames = frames.to(feat.device, torch.int64).contiguous()
+            fr_ptr = frames.data_ptr()
+        dtype = _lib.ACB_F32 if feat.dtype == torch.float32 else _lib.ACB_BF16
+        _lib.check(lib.acb_moments_accumulate(feat.data_ptr(), dtype, B, M, cap, M * cap, fr_ptr, self.moments.data_ptr(),
+                                              torch.cuda.current_stream(feat.device).cuda_stream), "acb_moments_accumulate")
+        self.frames += int(frames.sum().item()) if frames is not None else B * cap
+
+    # -- combine shards: one collective --
+    def all_reduce(self, group=None) -> None:
+        """SUM the per-rank moments and frame counts across the process group with a single ``all_reduce`` of
+        ``2 * n_mels + 1`` fp64 values (the count is exact in fp64 below 2^53 frames)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        buf = torch.cat([self.moments, torch.tensor([float(self.frames)], dtype=torch.float64, device=self.moments.device)])
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        self.moments = buf[:-1].clone()
+        self.frames = int(round(buf[-1].item()))
+
+    def finalize(self, var_floor: float = VAR_FLOOR) -> MelStats:
+        return finalize_moments(self.moments.detach().cpu().numpy(), self.frames, var_floor)
+
+
+def finalize_moments_c(moments: np.ndarray, frames: int, var_floor: float = VAR_FLOOR) -> MelStats:
+    """Same as :func:`finalize_moments` through ``acb_moments_finalize`` (host function of the C ABI)."""
+    from . import _lib
+    lib = _lib.load()
+    m = np.ascontiguousarray(moments, dtype=np.float64)
+    n_mels = m.shape[0] // 2
+    bm = np.zeros(n_mels)
+    bs = np.zeros(n_mels)
+    gm, gs = ctypes.c_double(), ctypes.c_double()
+    _lib.check(lib.acb_moments_finalize(m.ctypes.data, n_mels, int(frames), float(var_floor), bm.ctypes.data, bs.ctypes.data,
+                                        ctypes.cast(ctypes.byref(gm), ctypes.c_void_p), ctypes.cast(ctypes.byref(gs), ctypes.c_void_p)),
+               "acb_moments_finalize")
+    return MelStats(bm, bs, gm.value, gs.value, int(frames), int(n_mels * frames))

@@ -1,0 +1,153 @@
+/*
+ * audiocalm_b200.h -- C ABI of the B200-native (sm_100a) log-mel front-end for Audio-CALM.
+ *
+ * Drop-in boundary.  The reference has no FFI: its boundary is the Python symbols of
+ * preprocess/core.py and preprocess/compute_mel_stats.py.  Every entry point below names the reference
+ * lines it replaces; the Python shims in audio-calm_b200/preprocess/ keep the reference's call
+ * signatures and bind these functions with ctypes (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device pointer owned by the caller
+ *     (the Python side allocates with torch); nothing is allocated or freed across the ABI except the
+ *     opaque front-end handle (constant tables) created/destroyed explicitly.
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no call
+ *     synchronises the device unless stated.
+ *   - return value: 0 = ACB_OK, negative = error; acb_last_error() returns a thread-local message.
+ *     No exception ever crosses the ABI.
+ */
+#ifndef AUDIOCALM_B200_H_
+#define AUDIOCALM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACB_OK 0
+#define ACB_ERR_INVALID (-1)      /* bad argument (null pointer, unsupported preset, clip too short ...) */
+#define ACB_ERR_CUDA (-2)         /* a CUDA runtime call failed; message carries cudaGetErrorString */
+#define ACB_ERR_UNSUPPORTED (-3)  /* valid request this build has no kernel for */
+
+#define ACB_ABI_VERSION 1
+
+/* output element type */
+#define ACB_F32 0
+#define ACB_BF16 1
+/* output layout of one clip: MEL_MAJOR = [n_mels][frame_capacity] (what the saved {"mel"} payload and the
+ * VAE consume, preprocess/process_dataset.py:155); TIME_MAJOR = [frame_capacity][n_mels], the physical
+ * layout torchaudio's MelScale returns as a transposed view. */
+#define ACB_MEL_MAJOR 0
+#define ACB_TIME_MAJOR 1
+/* log kind */
+#define ACB_LOG_NATURAL 0         /* preprocess/core.py:60 */
+#define ACB_LOG_10 1
+
+typedef struct acb_frontend acb_frontend; /* opaque: device-resident tables for one (device, preset) */
+
+int acb_abi_version(void);
+const char* acb_last_error(void);
+
+/* Frames tile: the hot kernel processes clips in tiles of this many frames. */
+int acb_frames_per_tile(void);
+
+/* T = 1 + L / hop of torch.stft(center=True) as called through preprocess/core.py:55; returns -1 when
+ * L <= n_fft/2 (the reference raises RuntimeError: reflect padding needs a longer input). */
+int64_t acb_frames_for_length(int64_t length, int n_fft, int hop);
+/* Frame count after the reflect pad to a multiple (preprocess/process_dataset.py:146-150). */
+int64_t acb_padded_frames(int64_t frames, int multiple);
+
+/* Host-side planning: exclusive prefix of per-clip tile counts for acb_logmel_forward.
+ * lengths_host[n_clips] in samples; frame_capacity > 0 asks for tiles covering the whole row (used with
+ * fill_tail), 0 covers only the frames that exist.  Writes tile_start_host[n_clips + 1]; returns the
+ * total tile count or a negative error (a clip shorter than n_fft/2 + 1 samples). */
+int64_t acb_plan_tiles(const int64_t* lengths_host, int32_t n_clips, int n_fft, int hop,
+                       int64_t frame_capacity, int32_t* tile_start_host);
+
+/* Build the device tables (replaces MelExtractor.__init__, preprocess/core.py:33-48).
+ * window_host[n_fft] and fb_host[(n_fft/2+1) * n_mels] (row-major [freq][mel]) are the fp32 tables the
+ * host derived with the reference's torch calls.  This build has kernels for n_fft = 1024, hop = 256,
+ * n_mels <= 128; anything else returns ACB_ERR_UNSUPPORTED. */
+int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int n_mels,
+                        const float* window_host, const float* fb_host, float clamp_min, int log_kind);
+int acb_frontend_destroy(acb_frontend* fe);
+/* bytes of device workspace acb_logmel_forward needs when moments are requested */
+int64_t acb_moments_workspace_bytes(const acb_frontend* fe);
+
+typedef struct acb_logmel_args {
+    /* ---- input: a flat device buffer of fp32 samples holding n_clips clips ---- */
+    const float* wav;            /* device */
+    const int64_t* clip_offset;  /* device [n_clips]: first sample of clip i in wav; NULL => i * clip_stride */
+    const int64_t* clip_length;  /* device [n_clips]: samples in clip i;            NULL => uniform_length */
+    int64_t clip_stride;         /* used when clip_offset is NULL */
+    int64_t uniform_length;      /* used when clip_length is NULL */
+    const int32_t* tile_start;   /* device [n_clips + 1] from acb_plan_tiles;        NULL => uniform clips */
+    int32_t n_clips;
+    int32_t n_tiles;             /* total tiles (last entry of tile_start) */
+    /* ---- optional fused peak normalisation (preprocess/core.py:108-110) ---- */
+    const float* clip_peak;      /* device [n_clips] max|x| per clip from acb_peak_abs, or NULL */
+    /* ---- output ---- */
+    void* out;                   /* device */
+    int32_t out_dtype;           /* ACB_F32 | ACB_BF16 */
+    int32_t out_layout;          /* ACB_MEL_MAJOR | ACB_TIME_MAJOR */
+    const int64_t* out_offset;   /* device [n_clips] element offset of clip i in out; NULL => i * out_clip_stride */
+    int64_t out_clip_stride;     /* elements */
+    int64_t frame_capacity;      /* frames per clip row in `out` (row pitch of MEL_MAJOR; >= padded frames) */
+    const int64_t* frame_capacity_per_clip; /* device [n_clips] overrides frame_capacity (packed outputs) or NULL */
+    int32_t pad_multiple;        /* 1 = none, 4 = reflect-pad the time axis (process_dataset.py:146-150) */
+    int32_t fill_tail;           /* !=0: frames [padded, frame_capacity) are set to fill_value (ragged batches) */
+    float fill_value;
+    /* ---- optional fused affine normalisation (models/modeling_vae.py:317-319) ---- */
+    int32_t affine;              /* 0 none, 1 scalar (affine_mean/affine_std), 2 per-bin arrays */
+    float affine_mean;
+    float affine_std;
+    const float* bin_mean;       /* device [n_mels] when affine == 2 */
+    const float* bin_std;        /* device [n_mels] when affine == 2 */
+    /* ---- optional fused per-bin moments of the un-normalised log-mel (compute_mel_stats.py:26-27) ---- */
+    double* moments;             /* device [2 * n_mels]: sum then sum of squares, ACCUMULATED into; or NULL */
+    void* moments_workspace;     /* device, acb_moments_workspace_bytes() bytes, when moments != NULL */
+} acb_logmel_args;
+
+/* Fused reflect-pad + framing + Hann window + STFT + power + mel projection + clamp + log
+ * (+ pad-to-4, + affine normalisation, + per-bin moments): replaces MelExtractor.forward
+ * (preprocess/core.py:50-61) and the torchaudio/torch.stft calls below it. */
+int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* args, void* stream);
+
+/* Per-clip max|x| (preprocess/core.py:108). peak_out: device [n_clips] fp32. */
+int acb_peak_abs(const float* wav, const int64_t* clip_offset, const int64_t* clip_length, int64_t clip_stride,
+                 int64_t uniform_length, int32_t n_clips, float* peak_out, void* stream);
+
+/* process_audio_chunk (preprocess/core.py:93-112): wav_cl device [channels][length] -> out device [length]:
+ * channel mean when channels > 1, then x / (peak + 1e-8) * 0.95 when peak > 0 (division first).
+ * scratch_peak: device [1] fp32 workspace. */
+int acb_process_audio_chunk(const float* wav_cl, int32_t channels, int64_t length, float* out,
+                            float* scratch_peak, void* stream);
+
+/* Per-bin moments of already-extracted features (compute_mel_stats.py:19-28 over saved files):
+ * feat device, MEL_MAJOR [n_clips][n_mels][frame_capacity] fp32 or bf16, frames[i] valid frames of clip i
+ * (device [n_clips]; NULL => all frame_capacity).  Accumulates into moments[2 * n_mels] (device, fp64). */
+int acb_moments_accumulate(const void* feat, int32_t dtype, int32_t n_clips, int32_t n_mels, int64_t frame_capacity,
+                           int64_t clip_stride, const int64_t* frames, double* moments, void* stream);
+
+/* Finalise on the host (compute_mel_stats.py:30-33): per-bin mean/std and the reference's global scalars.
+ * moments_host[2 * n_mels], frames = total frame count (all clips).  var floor as in the reference (1e-8). */
+int acb_moments_finalize(const double* moments_host, int32_t n_mels, int64_t frames, double var_floor,
+                         double* bin_mean, double* bin_std, double* global_mean, double* global_std);
+
+/* Per-utterance, per-bin normalisation used by eval (eval/eval_vae.py:80-82): (x - mean_t) / max(std_t, 1e-5)
+ * with the unbiased std over time.  feat/out device MEL_MAJOR fp32 [n_clips][n_mels][frame_capacity]. */
+int acb_normalize_per_utterance(const float* feat, float* out, int32_t n_clips, int32_t n_mels,
+                                int64_t frame_capacity, const int64_t* frames, float min_std, void* stream);
+
+/* Host-buffer convenience path (pinned or pageable host memory): H2D copy, acb_logmel_forward on uniform
+ * clips [n_clips][length], D2H copy, chunked over `n_chunks` so copies overlap compute.  dev_in/dev_out
+ * are caller-provided device staging buffers (n_clips*length floats / n_clips*n_mels*frame_capacity
+ * elements).  Synchronises `stream` before returning. */
+int acb_logmel_forward_host(const acb_frontend* fe, const float* wav_host, int32_t n_clips, int64_t length,
+                            void* out_host, acb_logmel_args* args_template, float* dev_in, void* dev_out,
+                            int32_t n_chunks, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOCALM_B200_H_ */
