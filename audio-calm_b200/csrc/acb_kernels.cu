@@ -44,7 +44,7 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTileSamples = (kTileFrames + 3) * kHop;       // 4864 samples staged per tile
 constexpr int kRowStride = 33;                               // complex elements per scratch row (conflict-free transpose)
-constexpr int kScratchFloats = 32 * kRowStride * 2 + 2;      // 2114 floats / warp; == 2 (mod 32) so pair strides spread banks
+constexpr int kScratchFloats = 32 * kRowStride * 2 + 4;      // 2116 floats / warp; == 4 (mod 32): 16-byte loads of 8 pairs hit 32 distinct banks
 constexpr int kMaxMels = 128;
 constexpr int kMaxRounds = 6;                                // mel schedule: rounds of (4 bands) per warp
 constexpr int kMaxWeights = 4096;
@@ -139,6 +139,14 @@ __device__ __forceinline__ void fft32_dit(float (&xr)[32], float (&xi)[32]) {
     BflyLoop<5, 0, 0>::run(xr, xi);
 }
 
+// Same, when stage 1 (span-1 butterflies, twiddle 1) has already been applied by the caller.
+__device__ __forceinline__ void fft32_dit_from_stage2(float (&xr)[32], float (&xi)[32]) {
+    BflyLoop<2, 0, 0>::run(xr, xi);
+    BflyLoop<3, 0, 0>::run(xr, xi);
+    BflyLoop<4, 0, 0>::run(xr, xi);
+    BflyLoop<5, 0, 0>::run(xr, xi);
+}
+
 // --------------------------------------------------------------------------------------------
 // fused log-mel kernel
 // --------------------------------------------------------------------------------------------
@@ -146,14 +154,15 @@ struct LogmelParams {
     // tables (device)
     const float* window;       // [1024]
     const float2* twiddle;     // [32][32]  exp(-2*pi*i*k1*n2/1024) at [k1][n2]
-    const float* weights;      // [n_weights] banded filterbank weights * 0.25
-    const int* band_start;     // [n_mels]
-    const int* band_len;       // [n_mels]
-    const int* band_off;       // [n_mels]
-    const short* sched_band;   // [kWarps][kMaxRounds][4]  band id or -1
-    const short* sched_len;    // [kWarps][kMaxRounds]     max band length of the round (0 = unused)
+    // mel plan: per (warp, round) four band slots with a common even trip count; weights zero-padded to the trip
+    // and interleaved as [i/2][slot][2] so that a lane fetches two consecutive weights with one 8-byte load
+    const float* plan_w;       // [n_plan_w]
+    const int* plan_woff;      // [kWarps][kMaxRounds] offset (floats) of the round's weights in plan_w
+    const short* plan_trip;    // [kWarps][kMaxRounds] bins per round (even, 0 = no more rounds)
+    const short* plan_band;    // [kWarps][kMaxRounds][4] band id or -1
+    const short* plan_astart;  // [kWarps][kMaxRounds][4] first bin (even) of the slot's run
+    int n_plan_w;
     int n_mels;
-    int n_weights;
     float clamp_min;
     float log_scale;           // 1 for ln, 1/ln(10) for log10 (applied to ln)
     float log_floor;           // log(clamp_min) computed on the host: clamped values are exactly the reference's floor
@@ -188,41 +197,88 @@ struct LogmelParams {
 };
 
 struct SmemLayout {
-    int samples, scratch, twiddle, window, weights, out, band_start, band_len, band_off, sched_band, sched_len, total_bytes;
+    int samples, scratch, twiddle, window, plan_w, out, plan_woff, plan_trip, plan_band, plan_astart, total_bytes;
 };
 
-__host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_weights) {
+__host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }   // odd: conflict-free both ways
+
+__host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w) {
     SmemLayout L;
     int off = 0;  // in 4-byte words
     L.samples = off; off += kTileSamples;
     L.scratch = off; off += kWarps * kScratchFloats;
     L.twiddle = off; off += 32 * 32 * 2;
     L.window = off; off += kNfft;
-    L.weights = off; off += (n_weights + 3) & ~3;
-    L.out = off; off += kTileFrames * (n_mels + 1);
-    L.band_start = off; off += n_mels;
-    L.band_len = off; off += n_mels;
-    L.band_off = off; off += n_mels;
-    L.sched_band = off; off += (kWarps * kMaxRounds * 4 + 1) / 2;   // shorts
-    L.sched_len = off; off += (kWarps * kMaxRounds + 1) / 2;        // shorts
+    L.plan_w = off; off += (n_plan_w + 3) & ~3;
+    L.out = off; off += (kTileFrames * out_row_stride(n_mels) + 3) & ~3;
+    L.plan_woff = off; off += kWarps * kMaxRounds;
+    L.plan_trip = off; off += kWarps * kMaxRounds / 2;            // shorts
+    L.plan_band = off; off += kWarps * kMaxRounds * 4 / 2;        // shorts
+    L.plan_astart = off; off += kWarps * kMaxRounds * 4 / 2;      // shorts
     L.total_bytes = off * 4;
     return L;
 }
 
-struct TileInfo {
+// Position of a CTA in its contiguous tile range: which clip, which tile of the clip, and the clip's geometry.
+struct ClipCursor {
     long long wav_base;    // element index of the clip's first sample in wav
     long long length;      // samples in the clip
     long long out_base;    // element offset of the clip in out
-    long long cap;         // frame capacity (row pitch)
+    int cap;               // frame capacity (row pitch of the mel-major layout)
     int frames;            // T
     int frames_padded;     // T4
-    int f0;                // first frame of this tile
     int clip;
+    int tile_in_clip;
+    int tiles_in_clip;
     float gain;            // squared waveform scale (fused peak normalisation), 1 otherwise
 };
 
-__device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const TileInfo& t, float* s_samples) {
-    const long long g0 = (long long)t.f0 * kHop - kNfft / 2;  // sample index (relative to the clip) of smem slot 0
+__device__ __forceinline__ void cursor_load_clip(const LogmelParams& p, ClipCursor& c) {
+    const int i = c.clip;
+    c.wav_base = p.clip_offset ? p.clip_offset[i] : (long long)i * p.clip_stride;
+    c.length = p.clip_length ? p.clip_length[i] : p.uniform_length;
+    c.out_base = p.out_offset ? p.out_offset[i] : (long long)i * p.out_clip_stride;
+    c.cap = (int)(p.frame_capacity_per_clip ? p.frame_capacity_per_clip[i] : p.frame_capacity);
+    c.frames = 1 + (int)(c.length / kHop);
+    const int rem = c.frames % p.pad_multiple;
+    c.frames_padded = rem ? c.frames + (p.pad_multiple - rem) : c.frames;
+    c.tiles_in_clip = p.tile_start ? (__ldg(p.tile_start + i + 1) - __ldg(p.tile_start + i)) : p.uniform_tiles_per_clip;
+    c.gain = 1.f;
+    if (p.clip_peak) {
+        const float peak = __ldg(p.clip_peak + i);
+        if (peak > 0.f) {
+            const float s = 0.95f / (peak + 1e-8f);
+            c.gain = s * s;
+        }
+    }
+}
+
+__device__ __forceinline__ void cursor_init(const LogmelParams& p, ClipCursor& c, long long tile) {
+    if (p.tile_start == nullptr) {
+        c.clip = (int)(tile / p.uniform_tiles_per_clip);
+        c.tile_in_clip = (int)(tile - (long long)c.clip * p.uniform_tiles_per_clip);
+    } else {  // largest clip with tile_start[clip] <= tile
+        int lo = 0, hi = p.n_clips;
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((long long)__ldg(p.tile_start + mid) <= tile) lo = mid; else hi = mid;
+        }
+        c.clip = lo;
+        c.tile_in_clip = (int)(tile - __ldg(p.tile_start + lo));
+    }
+    cursor_load_clip(p, c);
+}
+
+__device__ __forceinline__ void cursor_advance(const LogmelParams& p, ClipCursor& c) {
+    if (++c.tile_in_clip >= c.tiles_in_clip) {
+        c.tile_in_clip = 0;
+        do { ++c.clip; cursor_load_clip(p, c); } while (c.tiles_in_clip == 0 && c.clip + 1 < p.n_clips);
+    }
+}
+
+__device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const ClipCursor& t, float* s_samples) {
+    const int f0 = t.tile_in_clip * kTileFrames;
+    const long long g0 = (long long)f0 * kHop - kNfft / 2;  // sample index (relative to the clip) of smem slot 0
     const float* src = p.wav + t.wav_base;
     const bool interior = (g0 >= 0) && (g0 + kTileSamples <= t.length);
     if (interior) {
@@ -248,123 +304,140 @@ __device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const T
     cp_async_commit();
 }
 
+template <typename OutT>
+__device__ __forceinline__ OutT to_out(float v);
+template <>
+__device__ __forceinline__ float to_out<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Store one staged tile.  Interior tiles (every frame exists and none is a pad-to-4 source) take loops without
+// per-element conditions; the last tiles of a clip take the general path (masking, reflected columns, tail fill).
+template <typename OutT>
+__device__ __forceinline__ void store_tile(const LogmelParams& p, const ClipCursor& c, const float* s_out, int n_mels, int S) {
+    OutT* out = reinterpret_cast<OutT*>(p.out) + c.out_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f0 = c.tile_in_clip * kTileFrames;
+    const int T = c.frames, T4 = c.frames_padded, pad = T4 - T;
+    const bool interior = (f0 + kTileFrames - 1 <= T - 2 - pad);
+    if (interior) {
+        if (p.time_major) {
+            OutT* row0 = out + (size_t)f0 * n_mels;
+            for (int f = warp; f < kTileFrames; f += kWarps) {
+                OutT* row = row0 + f * n_mels;
+                const float* srow = s_out + f * S;
+                for (int b = lane; b < n_mels; b += 32) row[b] = to_out<OutT>(srow[b]);
+            }
+        } else {
+            OutT* col0 = out + f0;
+            const int f = tid & (kTileFrames - 1);
+            for (int b = tid >> 4; b < n_mels; b += kThreads / kTileFrames)
+                col0[(unsigned)b * (unsigned)c.cap + f] = to_out<OutT>(s_out[f * S + b]);
+        }
+        return;
+    }
+    const int n_out = kTileFrames * n_mels;
+    for (int idx = tid; idx < n_out; idx += kThreads) {
+        int f, b;
+        if (p.time_major) { f = idx / n_mels; b = idx - f * n_mels; }
+        else { b = idx / kTileFrames; f = idx - b * kTileFrames; }
+        const int fr = f0 + f;
+        if (fr >= c.cap) continue;
+        float v;
+        bool dup = false;
+        if (fr < T) {
+            v = s_out[f * S + b];
+            dup = (fr <= T - 2) && (fr > T - 2 - pad);
+        } else if (fr >= T4 && p.fill_tail) {
+            v = p.fill_value;
+        } else {
+            continue;
+        }
+        const size_t e0 = p.time_major ? ((size_t)fr * n_mels + b) : ((size_t)b * c.cap + fr);
+        out[e0] = to_out<OutT>(v);
+        if (dup) {
+            const int fd = 2 * T - 2 - fr;  // column T + j with j = T-2-fr  (out[T+j] = mel[T-2-j])
+            const size_t e1 = p.time_major ? ((size_t)fd * n_mels + b) : ((size_t)b * c.cap + fd);
+            out[e1] = to_out<OutT>(v);
+        }
+    }
+}
+
 template <bool kMoments>
 __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelParams p) {
     extern __shared__ __align__(16) float smem[];
-    const SmemLayout L = make_smem_layout(p.n_mels, p.n_weights);
+    const SmemLayout L = make_smem_layout(p.n_mels, p.n_plan_w);
     float* s_samples = smem + L.samples;
     float* s_scratch = smem + L.scratch;
     float2* s_tw = reinterpret_cast<float2*>(smem + L.twiddle);
     float* s_win = smem + L.window;
-    float* s_w = smem + L.weights;
+    float* s_pw = smem + L.plan_w;
     float* s_out = smem + L.out;
-    int* s_band_start = reinterpret_cast<int*>(smem + L.band_start);
-    int* s_band_len = reinterpret_cast<int*>(smem + L.band_len);
-    int* s_band_off = reinterpret_cast<int*>(smem + L.band_off);
-    short* s_sched_band = reinterpret_cast<short*>(smem + L.sched_band);
-    short* s_sched_len = reinterpret_cast<short*>(smem + L.sched_len);
+    int* s_woff = reinterpret_cast<int*>(smem + L.plan_woff);
+    short* s_trip = reinterpret_cast<short*>(smem + L.plan_trip);
+    short* s_band = reinterpret_cast<short*>(smem + L.plan_band);
+    short* s_astart = reinterpret_cast<short*>(smem + L.plan_astart);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
     const int n_mels = p.n_mels;
-    const int out_stride = n_mels + 1;
+    const int S = out_row_stride(n_mels);
 
     // ---- one-time table staging ----
     for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = p.twiddle[i];
     for (int i = tid; i < kNfft; i += kThreads) s_win[i] = p.window[i];
-    for (int i = tid; i < p.n_weights; i += kThreads) s_w[i] = p.weights[i];
-    for (int i = tid; i < n_mels; i += kThreads) {
-        s_band_start[i] = p.band_start[i];
-        s_band_len[i] = p.band_len[i];
-        s_band_off[i] = p.band_off[i];
-    }
-    for (int i = tid; i < kWarps * kMaxRounds * 4; i += kThreads) s_sched_band[i] = p.sched_band[i];
-    for (int i = tid; i < kWarps * kMaxRounds; i += kThreads) s_sched_len[i] = p.sched_len[i];
+    for (int i = tid; i < p.n_plan_w; i += kThreads) s_pw[i] = p.plan_w[i];
+    for (int i = tid; i < kWarps * kMaxRounds; i += kThreads) { s_woff[i] = p.plan_woff[i]; s_trip[i] = p.plan_trip[i]; }
+    for (int i = tid; i < kWarps * kMaxRounds * 4; i += kThreads) { s_band[i] = p.plan_band[i]; s_astart[i] = p.plan_astart[i]; }
 
     // ---- this CTA's contiguous tile range ----
     const long long t_begin = (long long)p.n_tiles * blockIdx.x / gridDim.x;
     const long long t_end = (long long)p.n_tiles * (blockIdx.x + 1) / gridDim.x;
 
-    // per-thread moment accumulators (fp64), one slot per schedule round
+    // per-thread moment accumulators (fp64), one slot per plan round
     double m_sum[kMaxRounds], m_sq[kMaxRounds];
 #pragma unroll
     for (int r = 0; r < kMaxRounds; ++r) { m_sum[r] = 0.0; m_sq[r] = 0.0; }
 
-    int clip = 0;
+    ClipCursor cur;
     if (t_begin < t_end) {
-        if (p.tile_start == nullptr) {
-            clip = (int)(t_begin / p.uniform_tiles_per_clip);
-        } else {  // largest clip with tile_start[clip] <= t_begin
-            int lo = 0, hi = p.n_clips;
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if ((long long)__ldg(p.tile_start + mid) <= t_begin) lo = mid; else hi = mid;
-            }
-            clip = lo;
-        }
-    }
-
-    auto describe = [&](long long tile, int& clip_io) -> TileInfo {
-        TileInfo t;
-        int first_tile;
-        if (p.tile_start == nullptr) {
-            clip_io = (int)(tile / p.uniform_tiles_per_clip);
-            first_tile = clip_io * p.uniform_tiles_per_clip;
-        } else {
-            while (clip_io + 1 < p.n_clips && (long long)__ldg(p.tile_start + clip_io + 1) <= tile) ++clip_io;
-            first_tile = __ldg(p.tile_start + clip_io);
-        }
-        t.clip = clip_io;
-        t.wav_base = p.clip_offset ? p.clip_offset[clip_io] : (long long)clip_io * p.clip_stride;
-        t.length = p.clip_length ? p.clip_length[clip_io] : p.uniform_length;
-        t.out_base = p.out_offset ? p.out_offset[clip_io] : (long long)clip_io * p.out_clip_stride;
-        t.cap = p.frame_capacity_per_clip ? p.frame_capacity_per_clip[clip_io] : p.frame_capacity;
-        t.frames = 1 + (int)(t.length / kHop);
-        const int rem = t.frames % p.pad_multiple;
-        t.frames_padded = rem ? t.frames + (p.pad_multiple - rem) : t.frames;
-        t.f0 = (int)(tile - first_tile) * kTileFrames;
-        t.gain = 1.f;
-        if (p.clip_peak) {
-            const float peak = __ldg(p.clip_peak + clip_io);
-            if (peak > 0.f) {
-                const float s = 0.95f / (peak + 1e-8f);
-                t.gain = s * s;
-            }
-        }
-        return t;
-    };
-
-    TileInfo cur;
-    if (t_begin < t_end) {
-        cur = describe(t_begin, clip);
-        if (cur.f0 < cur.frames) load_tile_samples(p, cur, s_samples);
+        cursor_init(p, cur, t_begin);
+        if (cur.tile_in_clip * kTileFrames < cur.frames) load_tile_samples(p, cur, s_samples);
     }
 
     for (long long tile = t_begin; tile < t_end; ++tile) {
         cp_async_wait_all();
         __syncthreads();  // samples (and tables, first iteration) visible; previous tile's s_out fully stored
 
-        const bool has_frames = cur.f0 < cur.frames;  // false for pure tail-fill tiles
+        const int f0 = cur.tile_in_clip * kTileFrames;
+        const bool has_frames = f0 < cur.frames;  // false for pure tail-fill tiles
         float* scr = s_scratch + warp * kScratchFloats;
         float2* scr2 = reinterpret_cast<float2*>(scr);
 
         // ================= phase 1: one frame pair per warp =================
-        if (has_frames && cur.f0 + 2 * warp < cur.frames) {
+        if (has_frames && f0 + 2 * warp < cur.frames) {
             float xr[32], xi[32];
             {
+                // Hann window folded into the first radix-2 stage: positions (2j, 2j+1) of the bit-reversed order hold
+                // samples n1 and n1 + 16, so  x[2j] = a*wa + b*wb ,  x[2j+1] = a*wa - b*wb  (3 ops instead of 4).
                 const float* sp = s_samples + (2 * warp) * kHop + lane;
                 float v[40];
 #pragma unroll
                 for (int r = 0; r < 40; ++r) v[r] = sp[32 * r];
 #pragma unroll
-                for (int n1 = 0; n1 < 32; ++n1) {
-                    const float w = s_win[32 * n1 + lane];
-                    xr[brev5(n1)] = v[n1] * w;        // frame A
-                    xi[brev5(n1)] = v[n1 + 8] * w;    // frame B = A shifted by one hop (8 rows of 32)
+                for (int j = 0; j < 16; ++j) {
+                    const int n1 = brev5(2 * j);          // < 16
+                    const float wa = s_win[32 * n1 + lane];
+                    const float wb = s_win[32 * (n1 + 16) + lane];
+                    const float ar = v[n1] * wa, ai = v[n1 + 8] * wa;           // frame A (re) and frame B (im): B = A + one hop
+                    xr[2 * j] = fmaf(v[n1 + 16], wb, ar);
+                    xr[2 * j + 1] = fmaf(-v[n1 + 16], wb, ar);
+                    xi[2 * j] = fmaf(v[n1 + 24], wb, ai);
+                    xi[2 * j + 1] = fmaf(-v[n1 + 24], wb, ai);
                 }
             }
-            fft32_dit(xr, xi);  // over n1 -> k1 (natural order)
+            fft32_dit_from_stage2(xr, xi);  // over n1 -> k1 (natural order)
             // twiddle W_1024^(k1*lane), store transposed: scr[k1][lane]
 #pragma unroll
             for (int k1 = 0; k1 < 32; ++k1) {
@@ -407,35 +480,37 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         __syncthreads();  // power spectra of all pairs visible; sample tile is free again
 
         // prefetch the next tile's samples while the mel phase runs
-        TileInfo nxt = cur;
+        ClipCursor nxt = cur;
         if (tile + 1 < t_end) {
-            nxt = describe(tile + 1, clip);
-            if (nxt.f0 < nxt.frames) load_tile_samples(p, nxt, s_samples);
+            cursor_advance(p, nxt);
+            if (nxt.tile_in_clip * kTileFrames < nxt.frames) load_tile_samples(p, nxt, s_samples);
         }
 
         // ================= phase 2: banded mel projection, clamp, log, affine, moments =================
         if (has_frames) {
             const int q = lane >> 3;     // band slot within the round
             const int pr = lane & 7;     // frame pair
-            const float2* pp = reinterpret_cast<const float2*>(s_scratch + pr * kScratchFloats);
-            const int fA = cur.f0 + 2 * pr;
+            const float* pair_scratch = s_scratch + pr * kScratchFloats;
+            const int fA = f0 + 2 * pr;
             const int pad = cur.frames_padded - cur.frames;
 #pragma unroll
             for (int r = 0; r < kMaxRounds; ++r) {
-                const int trip = s_sched_len[warp * kMaxRounds + r];
-                if (trip == 0) continue;  // warp-uniform
-                const int b = s_sched_band[(warp * kMaxRounds + r) * 4 + q];
-                int start = 0, len = 0, off = 0;
-                if (b >= 0) { start = s_band_start[b]; len = s_band_len[b]; off = s_band_off[b]; }
+                const int trip = s_trip[warp * kMaxRounds + r];
+                if (trip == 0) break;  // warp-uniform; rounds are filled in order
+                const int b = s_band[(warp * kMaxRounds + r) * 4 + q];
+                const int ast = s_astart[(warp * kMaxRounds + r) * 4 + q];
+                const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + (ast >> 1);   // two bins x (A, B)
+                const float2* w2 = reinterpret_cast<const float2*>(s_pw + s_woff[warp * kMaxRounds + r]) + q;
                 float accA = 0.f, accB = 0.f;
+                const int half_trip = trip >> 1;
 #pragma unroll 4
-                for (int i = 0; i < trip; ++i) {
-                    if (i < len) {
-                        const float w = s_w[off + i];
-                        const float2 pw = pp[start + i];
-                        accA = fmaf(w, pw.x, accA);
-                        accB = fmaf(w, pw.y, accB);
-                    }
+                for (int i = 0; i < half_trip; ++i) {
+                    const float4 pw = p4[i];
+                    const float2 w = w2[4 * i];
+                    accA = fmaf(w.x, pw.x, accA);
+                    accB = fmaf(w.x, pw.y, accB);
+                    accA = fmaf(w.y, pw.z, accA);
+                    accB = fmaf(w.y, pw.w, accB);
                 }
                 if (b >= 0) {
                     const float mA = accA * cur.gain, mB = accB * cur.gain;
@@ -462,48 +537,16 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                         vA = (vA - mu) * is;
                         vB = (vB - mu) * is;
                     }
-                    s_out[(2 * pr) * out_stride + b] = vA;
-                    s_out[(2 * pr + 1) * out_stride + b] = vB;
+                    s_out[(2 * pr) * S + b] = vA;
+                    s_out[(2 * pr + 1) * S + b] = vB;
                 }
             }
         }
         __syncthreads();  // output tile staged
 
         // ================= phase 3: coalesced store =================
-        {
-            const int T = cur.frames, T4 = cur.frames_padded;
-            const int pad = T4 - T;
-            const int n_out = kTileFrames * n_mels;
-            float* out_f = reinterpret_cast<float*>(p.out);
-            __nv_bfloat16* out_h = reinterpret_cast<__nv_bfloat16*>(p.out);
-            for (int idx = tid; idx < n_out; idx += kThreads) {
-                int f, b;
-                if (p.time_major) { f = idx / n_mels; b = idx - f * n_mels; }
-                else { b = idx / kTileFrames; f = idx - b * kTileFrames; }
-                const int fr = cur.f0 + f;
-                if (fr >= cur.cap) continue;
-                float v;
-                bool write = false, dup = false;
-                if (fr < T) {
-                    v = s_out[f * out_stride + b];
-                    write = true;
-                    dup = (fr <= T - 2) && (fr > T - 2 - pad);
-                } else if (fr >= T4 && p.fill_tail) {
-                    v = p.fill_value;
-                    write = true;
-                }
-                if (!write) continue;
-                const long long e0 = p.time_major ? (cur.out_base + (long long)fr * n_mels + b)
-                                                  : (cur.out_base + (long long)b * cur.cap + fr);
-                if (p.out_bf16) out_h[e0] = __float2bfloat16_rn(v); else out_f[e0] = v;
-                if (dup) {
-                    const int fd = 2 * T - 2 - fr;  // column T + j with j = T-2-fr
-                    const long long e1 = p.time_major ? (cur.out_base + (long long)fd * n_mels + b)
-                                                      : (cur.out_base + (long long)b * cur.cap + fd);
-                    if (p.out_bf16) out_h[e1] = __float2bfloat16_rn(v); else out_f[e1] = v;
-                }
-            }
-        }
+        if (p.out_bf16) store_tile<__nv_bfloat16>(p, cur, s_out, n_mels, S);
+        else store_tile<float>(p, cur, s_out, n_mels, S);
         cur = nxt;
     }
     cp_async_wait_all();
@@ -522,9 +565,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 s += __shfl_xor_sync(0xffffffffu, s, o);
                 s2 += __shfl_xor_sync(0xffffffffu, s2, o);
             }
-            const int trip = s_sched_len[warp * kMaxRounds + r];
+            const int trip = s_trip[warp * kMaxRounds + r];
             if (trip != 0 && (lane & 7) == 0) {
-                const int b = s_sched_band[(warp * kMaxRounds + r) * 4 + (lane >> 3)];
+                const int b = s_band[(warp * kMaxRounds + r) * 4 + (lane >> 3)];
                 if (b >= 0) { s_m[b] = s; s_m[n_mels + b] = s2; }  // every band has exactly one owner slot
             }
         }
@@ -709,12 +752,12 @@ struct acb_frontend {
     void* d_blob = nullptr;
     const float* d_window = nullptr;
     const float2* d_twiddle = nullptr;
-    const float* d_weights = nullptr;
-    const int* d_band_start = nullptr;
-    const int* d_band_len = nullptr;
-    const int* d_band_off = nullptr;
-    const short* d_sched_band = nullptr;
-    const short* d_sched_len = nullptr;
+    const float* d_plan_w = nullptr;
+    const int* d_plan_woff = nullptr;
+    const short* d_plan_trip = nullptr;
+    const short* d_plan_band = nullptr;
+    const short* d_plan_astart = nullptr;
+    int n_plan_w = 0;
     // host-path streams/events (created lazily)
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev;
@@ -791,31 +834,56 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     }
     if ((int)weights.size() > kMaxWeights) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: filterbank too dense");
 
-    // mel schedule: bands sorted by run length, groups of 4 (one per lane slot), groups dealt to the 8 warps
-    // longest-processing-time first so every warp sums about the same number of bins.
+    // mel plan: bands sorted by (even-aligned) run length, groups of 4 (one per lane slot), groups dealt to the 8
+    // warps longest-processing-time first.  Within a group every slot is zero-padded to the group's trip count, so the
+    // kernel's inner loop is predicate-free; runs start on an even bin so two bins are fetched with one 16-byte load.
+    std::vector<int> astart(n_mels), alen(n_mels);
+    for (int m = 0; m < n_mels; ++m) {
+        astart[m] = start[m] & ~1;
+        const int end = start[m] + len[m];
+        alen[m] = ((end + 1) & ~1) - astart[m];
+        if (len[m] == 0) { astart[m] = 0; alen[m] = 2; }
+    }
     std::vector<int> order(n_mels);
     std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return len[a] > len[b]; });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return alen[a] > alen[b]; });
     const int n_groups = (n_mels + 3) / 4;
-    std::vector<short> sched_band(kWarps * kMaxRounds * 4, (short)-1), sched_len(kWarps * kMaxRounds, (short)0);
+    std::vector<short> plan_band(kWarps * kMaxRounds * 4, (short)-1), plan_astart(kWarps * kMaxRounds * 4, (short)0),
+        plan_trip(kWarps * kMaxRounds, (short)0);
+    std::vector<int> plan_woff(kWarps * kMaxRounds, 0);
+    std::vector<float> plan_w;
     std::vector<int> load(kWarps, 0), rounds(kWarps, 0);
     for (int g = 0; g < n_groups; ++g) {
         int best = -1;
         for (int w = 0; w < kWarps; ++w)
             if (rounds[w] < kMaxRounds && (best < 0 || load[w] < load[best])) best = w;
-        if (best < 0) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel schedule overflow");
-        int gl = 0;
+        if (best < 0) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel plan overflow");
+        int trip = 2;
+        for (int q = 0; q < 4; ++q)
+            if (4 * g + q < n_mels) trip = std::max(trip, alen[order[4 * g + q]]);
+        const int slot = best * kMaxRounds + rounds[best];
+        plan_trip[slot] = (short)trip;
+        plan_woff[slot] = (int)plan_w.size();
+        plan_w.resize(plan_w.size() + (size_t)trip * 4, 0.f);
+        float* wbase = plan_w.data() + plan_woff[slot];
         for (int q = 0; q < 4; ++q) {
-            const int idx = 4 * g + q;
-            if (idx < n_mels) {
-                sched_band[(best * kMaxRounds + rounds[best]) * 4 + q] = (short)order[idx];
-                gl = std::max(gl, len[order[idx]]);
+            if (4 * g + q >= n_mels) continue;
+            const int m = order[4 * g + q];
+            plan_band[slot * 4 + q] = (short)m;
+            // keep every 16-byte read of the slot inside the 512-bin power array
+            int as = astart[m];
+            if (as + trip > kBins) as = std::max(0, (kBins - trip) & ~1);
+            plan_astart[slot * 4 + q] = (short)as;
+            for (int i = 0; i < len[m]; ++i) {
+                const int rel = start[m] + i - as;                 // bin offset inside the slot's window
+                if (rel < 0 || rel >= trip) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel plan window error");
+                wbase[(rel >> 1) * 8 + q * 2 + (rel & 1)] = weights[off[m] + i];
             }
         }
-        sched_len[best * kMaxRounds + rounds[best]] = (short)std::max(gl, 1);
-        load[best] += gl + 8;  // + fixed per-round epilogue cost
+        load[best] += trip + 16;  // + fixed per-round epilogue cost
         rounds[best]++;
     }
+    if ((int)plan_w.size() > kMaxWeights * 2) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel plan too large");
 
     // twiddles exp(-2*pi*i*k1*n2/1024) in double, rounded once
     std::vector<float2> tw(32 * 32);
@@ -830,28 +898,29 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     ACB_CUDA(cudaSetDevice(device));
     auto* fe = new acb_frontend();
     fe->device = device; fe->n_fft = n_fft; fe->hop = hop; fe->n_mels = n_mels; fe->n_weights = (int)weights.size();
+    fe->n_plan_w = (int)plan_w.size();
     fe->log_kind = log_kind; fe->clamp_min = clamp_min;
 
     // pack the blob
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
-    const size_t o_win = take(sizeof(float) * kNfft), o_tw = take(sizeof(float2) * 1024), o_w = take(sizeof(float) * std::max<size_t>(weights.size(), 1)),
-                 o_bs = take(sizeof(int) * n_mels), o_bl = take(sizeof(int) * n_mels), o_bo = take(sizeof(int) * n_mels),
-                 o_sb = take(sizeof(short) * sched_band.size()), o_sl = take(sizeof(short) * sched_len.size());
+    const size_t o_win = take(sizeof(float) * kNfft), o_tw = take(sizeof(float2) * 1024),
+                 o_pw = take(sizeof(float) * std::max<size_t>(plan_w.size(), 1)), o_po = take(sizeof(int) * plan_woff.size()),
+                 o_pt = take(sizeof(short) * plan_trip.size()), o_pb = take(sizeof(short) * plan_band.size()),
+                 o_pa = take(sizeof(short) * plan_astart.size());
     std::vector<unsigned char> host(o, 0);
     memcpy(host.data() + o_win, window_host, sizeof(float) * kNfft);
     memcpy(host.data() + o_tw, tw.data(), sizeof(float2) * 1024);
-    if (!weights.empty()) memcpy(host.data() + o_w, weights.data(), sizeof(float) * weights.size());
-    memcpy(host.data() + o_bs, start.data(), sizeof(int) * n_mels);
-    memcpy(host.data() + o_bl, len.data(), sizeof(int) * n_mels);
-    memcpy(host.data() + o_bo, off.data(), sizeof(int) * n_mels);
-    memcpy(host.data() + o_sb, sched_band.data(), sizeof(short) * sched_band.size());
-    memcpy(host.data() + o_sl, sched_len.data(), sizeof(short) * sched_len.size());
+    if (!plan_w.empty()) memcpy(host.data() + o_pw, plan_w.data(), sizeof(float) * plan_w.size());
+    memcpy(host.data() + o_po, plan_woff.data(), sizeof(int) * plan_woff.size());
+    memcpy(host.data() + o_pt, plan_trip.data(), sizeof(short) * plan_trip.size());
+    memcpy(host.data() + o_pb, plan_band.data(), sizeof(short) * plan_band.size());
+    memcpy(host.data() + o_pa, plan_astart.data(), sizeof(short) * plan_astart.size());
     cudaError_t e = cudaMalloc(&fe->d_blob, o);
     if (e == cudaSuccess) e = cudaMemcpy(fe->d_blob, host.data(), o, cudaMemcpyHostToDevice);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
-    const SmemLayout L = make_smem_layout(n_mels, fe->n_weights);
+    const SmemLayout L = make_smem_layout(n_mels, fe->n_plan_w);
     fe->smem_bytes = L.total_bytes;
     if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
@@ -868,12 +937,11 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     auto* base = static_cast<unsigned char*>(fe->d_blob);
     fe->d_window = reinterpret_cast<const float*>(base + o_win);
     fe->d_twiddle = reinterpret_cast<const float2*>(base + o_tw);
-    fe->d_weights = reinterpret_cast<const float*>(base + o_w);
-    fe->d_band_start = reinterpret_cast<const int*>(base + o_bs);
-    fe->d_band_len = reinterpret_cast<const int*>(base + o_bl);
-    fe->d_band_off = reinterpret_cast<const int*>(base + o_bo);
-    fe->d_sched_band = reinterpret_cast<const short*>(base + o_sb);
-    fe->d_sched_len = reinterpret_cast<const short*>(base + o_sl);
+    fe->d_plan_w = reinterpret_cast<const float*>(base + o_pw);
+    fe->d_plan_woff = reinterpret_cast<const int*>(base + o_po);
+    fe->d_plan_trip = reinterpret_cast<const short*>(base + o_pt);
+    fe->d_plan_band = reinterpret_cast<const short*>(base + o_pb);
+    fe->d_plan_astart = reinterpret_cast<const short*>(base + o_pa);
     cudaSetDevice(prev);
     *out = fe;
     return ACB_OK;
@@ -912,10 +980,10 @@ int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* s
     if (!a->frame_capacity_per_clip && a->frame_capacity <= 0) return fail(ACB_ERR_INVALID, "acb_logmel_forward: frame_capacity must be > 0");
 
     LogmelParams p{};
-    p.window = fe->d_window; p.twiddle = fe->d_twiddle; p.weights = fe->d_weights;
-    p.band_start = fe->d_band_start; p.band_len = fe->d_band_len; p.band_off = fe->d_band_off;
-    p.sched_band = fe->d_sched_band; p.sched_len = fe->d_sched_len;
-    p.n_mels = fe->n_mels; p.n_weights = fe->n_weights; p.clamp_min = fe->clamp_min;
+    p.window = fe->d_window; p.twiddle = fe->d_twiddle;
+    p.plan_w = fe->d_plan_w; p.plan_woff = fe->d_plan_woff; p.plan_trip = fe->d_plan_trip;
+    p.plan_band = fe->d_plan_band; p.plan_astart = fe->d_plan_astart; p.n_plan_w = fe->n_plan_w;
+    p.n_mels = fe->n_mels; p.clamp_min = fe->clamp_min;
     p.log_scale = fe->log_kind == ACB_LOG_10 ? 0.43429448190325176f : 1.f;
     p.log_floor = fe->log_kind == ACB_LOG_10 ? log10f(fe->clamp_min) : logf(fe->clamp_min);
     p.wav = a->wav;
