@@ -46,7 +46,7 @@ constexpr int kTileSamples = (kTileFrames + 3) * kHop;       // 4864 samples sta
 constexpr int kRowStride = 33;                               // complex elements per scratch row (conflict-free transpose)
 constexpr int kScratchFloats = 32 * kRowStride * 2 + 4;      // 2116 floats / warp; == 4 (mod 32): 16-byte loads of 8 pairs hit 32 distinct banks
 constexpr int kMaxMels = 128;
-constexpr int kMaxRounds = 6;                                // mel schedule: rounds of (4 bands) per warp
+constexpr int kMaxRounds = 4;                                // mel plan: rounds of (4 bands) per warp
 constexpr int kMaxWeights = 4096;
 
 thread_local std::string g_last_error;
@@ -197,12 +197,12 @@ struct LogmelParams {
 };
 
 struct SmemLayout {
-    int samples, scratch, twiddle, window, plan_w, out, plan_woff, plan_trip, plan_band, plan_astart, total_bytes;
+    int samples, scratch, twiddle, window, plan_w, out, plan_woff, plan_trip, plan_band, plan_astart, moments, total_bytes;
 };
 
 __host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }   // odd: conflict-free both ways
 
-__host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w) {
+__host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w, bool with_moments = false) {
     SmemLayout L;
     int off = 0;  // in 4-byte words
     L.samples = off; off += kTileSamples;
@@ -215,6 +215,8 @@ __host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w)
     L.plan_trip = off; off += kWarps * kMaxRounds / 2;            // shorts
     L.plan_band = off; off += kWarps * kMaxRounds * 4 / 2;        // shorts
     L.plan_astart = off; off += kWarps * kMaxRounds * 4 / 2;      // shorts
+    off = (off + 1) & ~1;
+    L.moments = off; if (with_moments) off += 4 * n_mels;       // doubles [2][n_mels]
     L.total_bytes = off * 4;
     return L;
 }
@@ -363,10 +365,10 @@ __device__ __forceinline__ void store_tile(const LogmelParams& p, const ClipCurs
     }
 }
 
-template <bool kMoments>
+template <bool kMoments, typename OutT>
 __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelParams p) {
     extern __shared__ __align__(16) float smem[];
-    const SmemLayout L = make_smem_layout(p.n_mels, p.n_plan_w);
+    const SmemLayout L = make_smem_layout(p.n_mels, p.n_plan_w, kMoments);
     float* s_samples = smem + L.samples;
     float* s_scratch = smem + L.scratch;
     float2* s_tw = reinterpret_cast<float2*>(smem + L.twiddle);
@@ -377,6 +379,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     short* s_trip = reinterpret_cast<short*>(smem + L.plan_trip);
     short* s_band = reinterpret_cast<short*>(smem + L.plan_band);
     short* s_astart = reinterpret_cast<short*>(smem + L.plan_astart);
+    double* s_mom = reinterpret_cast<double*>(smem + L.moments);   // [2][n_mels], only when kMoments
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -390,15 +393,12 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     for (int i = tid; i < p.n_plan_w; i += kThreads) s_pw[i] = p.plan_w[i];
     for (int i = tid; i < kWarps * kMaxRounds; i += kThreads) { s_woff[i] = p.plan_woff[i]; s_trip[i] = p.plan_trip[i]; }
     for (int i = tid; i < kWarps * kMaxRounds * 4; i += kThreads) { s_band[i] = p.plan_band[i]; s_astart[i] = p.plan_astart[i]; }
+    if (kMoments)
+        for (int i = tid; i < 2 * n_mels; i += kThreads) s_mom[i] = 0.0;
 
     // ---- this CTA's contiguous tile range ----
     const long long t_begin = (long long)p.n_tiles * blockIdx.x / gridDim.x;
     const long long t_end = (long long)p.n_tiles * (blockIdx.x + 1) / gridDim.x;
-
-    // per-thread moment accumulators (fp64), one slot per plan round
-    double m_sum[kMaxRounds], m_sq[kMaxRounds];
-#pragma unroll
-    for (int r = 0; r < kMaxRounds; ++r) { m_sum[r] = 0.0; m_sq[r] = 0.0; }
 
     ClipCursor cur;
     if (t_begin < t_end) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
 
     for (long long tile = t_begin; tile < t_end; ++tile) {
         cp_async_wait_all();
-        __syncthreads();  // samples (and tables, first iteration) visible; previous tile's s_out fully stored
+        __syncthreads();  // samples (and tables, first iteration) visible; previous tile's mel phase done with the scratch
 
         const int f0 = cur.tile_in_clip * kTileFrames;
         const bool has_frames = f0 < cur.frames;  // false for pure tail-fill tiles
@@ -486,49 +486,63 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
             if (nxt.tile_in_clip * kTileFrames < nxt.frames) load_tile_samples(p, nxt, s_samples);
         }
 
+        // interior tile: every frame exists and none is a pad-to-4 source -> mel-major results go straight to global
+        // memory from the mel phase (8 lanes x 2 frames = 64 contiguous bytes per band); other tiles and the
+        // time-major layout are staged in shared memory and stored by store_tile().
+        const int pad = cur.frames_padded - cur.frames;
+        const bool direct = !p.time_major && (f0 + kTileFrames - 1 <= cur.frames - 2 - pad);
+
         // ================= phase 2: banded mel projection, clamp, log, affine, moments =================
         if (has_frames) {
             const int q = lane >> 3;     // band slot within the round
             const int pr = lane & 7;     // frame pair
             const float* pair_scratch = s_scratch + pr * kScratchFloats;
             const int fA = f0 + 2 * pr;
-            const int pad = cur.frames_padded - cur.frames;
-#pragma unroll
+            OutT* out_clip = reinterpret_cast<OutT*>(p.out) + cur.out_base;
             for (int r = 0; r < kMaxRounds; ++r) {
-                const int trip = s_trip[warp * kMaxRounds + r];
+                const int slot = warp * kMaxRounds + r;
+                const int trip = s_trip[slot];
                 if (trip == 0) break;  // warp-uniform; rounds are filled in order
-                const int b = s_band[(warp * kMaxRounds + r) * 4 + q];
-                const int ast = s_astart[(warp * kMaxRounds + r) * 4 + q];
+                const int b = s_band[slot * 4 + q];
+                const int ast = s_astart[slot * 4 + q];
                 const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + (ast >> 1);   // two bins x (A, B)
-                const float2* w2 = reinterpret_cast<const float2*>(s_pw + s_woff[warp * kMaxRounds + r]) + q;
-                float accA = 0.f, accB = 0.f;
+                const float2* w2 = reinterpret_cast<const float2*>(s_pw + s_woff[slot]) + q;
+                float accA0 = 0.f, accB0 = 0.f, accA1 = 0.f, accB1 = 0.f;
                 const int half_trip = trip >> 1;
 #pragma unroll 4
                 for (int i = 0; i < half_trip; ++i) {
                     const float4 pw = p4[i];
                     const float2 w = w2[4 * i];
-                    accA = fmaf(w.x, pw.x, accA);
-                    accB = fmaf(w.x, pw.y, accB);
-                    accA = fmaf(w.y, pw.z, accA);
-                    accB = fmaf(w.y, pw.w, accB);
+                    accA0 = fmaf(w.x, pw.x, accA0);
+                    accB0 = fmaf(w.x, pw.y, accB0);
+                    accA1 = fmaf(w.y, pw.z, accA1);
+                    accB1 = fmaf(w.y, pw.w, accB1);
+                }
+                const float mA = (accA0 + accA1) * cur.gain, mB = (accB0 + accB1) * cur.gain;
+                float vA = (mA > p.clamp_min) ? __logf(mA) * p.log_scale : p.log_floor;
+                float vB = (mB > p.clamp_min) ? __logf(mB) * p.log_scale : p.log_floor;
+                if (kMoments) {
+                    // frames T-2-j (j < pad) are stored twice (reflected pad-to-4 columns) and counted twice
+                    double s = 0.0, s2 = 0.0;
+                    if (b >= 0 && fA < cur.frames) {
+                        const double c = (fA <= cur.frames - 2 && fA > cur.frames - 2 - pad) ? 2.0 : 1.0;
+                        s += c * (double)vA;
+                        s2 += c * (double)vA * (double)vA;
+                    }
+                    if (b >= 0 && fA + 1 < cur.frames) {
+                        const double c = (fA + 1 <= cur.frames - 2 && fA + 1 > cur.frames - 2 - pad) ? 2.0 : 1.0;
+                        s += c * (double)vB;
+                        s2 += c * (double)vB * (double)vB;
+                    }
+                    // the 8 pair lanes of a slot are a contiguous, aligned lane group (all 32 lanes take part)
+#pragma unroll
+                    for (int o = 4; o >= 1; o >>= 1) {
+                        s += __shfl_xor_sync(0xffffffffu, s, o);
+                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                    }
+                    if (pr == 0 && b >= 0) { s_mom[b] += s; s_mom[n_mels + b] += s2; }   // each band has exactly one owner slot
                 }
                 if (b >= 0) {
-                    const float mA = accA * cur.gain, mB = accB * cur.gain;
-                    float vA = (mA > p.clamp_min) ? __logf(mA) * p.log_scale : p.log_floor;
-                    float vB = (mB > p.clamp_min) ? __logf(mB) * p.log_scale : p.log_floor;
-                    if (kMoments) {
-                        // frames T-2-j (j < pad) are stored twice (reflected pad-to-4 columns) and counted twice
-                        if (fA < cur.frames) {
-                            const double c = (fA <= cur.frames - 2 && fA > cur.frames - 2 - pad) ? 2.0 : 1.0;
-                            m_sum[r] += c * (double)vA;
-                            m_sq[r] += c * (double)vA * (double)vA;
-                        }
-                        if (fA + 1 < cur.frames) {
-                            const double c = (fA + 1 <= cur.frames - 2 && fA + 1 > cur.frames - 2 - pad) ? 2.0 : 1.0;
-                            m_sum[r] += c * (double)vB;
-                            m_sq[r] += c * (double)vB * (double)vB;
-                        }
-                    }
                     if (p.affine == 1) {
                         vA = (vA - p.affine_mean) * p.affine_inv_std;
                         vB = (vB - p.affine_mean) * p.affine_inv_std;
@@ -537,42 +551,28 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                         vA = (vA - mu) * is;
                         vB = (vB - mu) * is;
                     }
-                    s_out[(2 * pr) * S + b] = vA;
-                    s_out[(2 * pr + 1) * S + b] = vB;
+                    if (direct) {
+                        OutT* dst = out_clip + (size_t)b * cur.cap + fA;
+                        dst[0] = to_out<OutT>(vA);
+                        dst[1] = to_out<OutT>(vB);
+                    } else {
+                        s_out[(2 * pr) * S + b] = vA;
+                        s_out[(2 * pr + 1) * S + b] = vB;
+                    }
                 }
             }
         }
-        __syncthreads();  // output tile staged
-
-        // ================= phase 3: coalesced store =================
-        if (p.out_bf16) store_tile<__nv_bfloat16>(p, cur, s_out, n_mels, S);
-        else store_tile<float>(p, cur, s_out, n_mels, S);
+        if (!direct) {   // CTA-uniform
+            __syncthreads();  // output tile staged
+            store_tile<OutT>(p, cur, s_out, n_mels, S);
+        }
         cur = nxt;
     }
     cp_async_wait_all();
 
-    // ---- per-CTA moment partials: reduce the 8 pair lanes, one writer per (warp, round, slot) ----
     if (kMoments) {
         __syncthreads();
-        double* s_m = reinterpret_cast<double*>(s_scratch);  // [2][n_mels]
-        for (int i = tid; i < 2 * n_mels; i += kThreads) s_m[i] = 0.0;
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < kMaxRounds; ++r) {
-            double s = m_sum[r], s2 = m_sq[r];
-#pragma unroll
-            for (int o = 4; o >= 1; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-            }
-            const int trip = s_trip[warp * kMaxRounds + r];
-            if (trip != 0 && (lane & 7) == 0) {
-                const int b = s_band[(warp * kMaxRounds + r) * 4 + (lane >> 3)];
-                if (b >= 0) { s_m[b] = s; s_m[n_mels + b] = s2; }  // every band has exactly one owner slot
-            }
-        }
-        __syncthreads();
-        for (int i = tid; i < 2 * n_mels; i += kThreads) p.moments_partial[(size_t)blockIdx.x * 2 * n_mels + i] = s_m[i];
+        for (int i = tid; i < 2 * n_mels; i += kThreads) p.moments_partial[(size_t)blockIdx.x * 2 * n_mels + i] = s_mom[i];
     }
 }
 
@@ -748,6 +748,7 @@ struct acb_frontend {
     int num_sms = 0;
     int grid = 0;          // persistent grid (CTAs)
     int smem_bytes = 0;
+    int smem_bytes_moments = 0;
     // one device allocation holding every table
     void* d_blob = nullptr;
     const float* d_window = nullptr;
@@ -920,12 +921,16 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     if (e == cudaSuccess) e = cudaMemcpy(fe->d_blob, host.data(), o, cudaMemcpyHostToDevice);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
-    const SmemLayout L = make_smem_layout(n_mels, fe->n_plan_w);
+    const SmemLayout L = make_smem_layout(n_mels, fe->n_plan_w, false);
+    const SmemLayout Lm = make_smem_layout(n_mels, fe->n_plan_w, true);
     fe->smem_bytes = L.total_bytes;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
+    fe->smem_bytes_moments = Lm.total_bytes;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lm.total_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lm.total_bytes);
     int occ = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, logmel_fused_kernel<false>, kThreads, L.total_bytes);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, logmel_fused_kernel<false, float>, kThreads, L.total_bytes);
     if (e != cudaSuccess) {
         if (fe->d_blob) cudaFree(fe->d_blob);
         delete fe;
@@ -1021,11 +1026,13 @@ int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* s
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = fe->grid;  // persistent: every CTA takes a contiguous share of the tiles (possibly empty)
     if (a->moments) {
-        logmel_fused_kernel<true><<<grid, kThreads, fe->smem_bytes, st>>>(p);
+        if (p.out_bf16) logmel_fused_kernel<true, __nv_bfloat16><<<grid, kThreads, fe->smem_bytes_moments, st>>>(p);
+        else logmel_fused_kernel<true, float><<<grid, kThreads, fe->smem_bytes_moments, st>>>(p);
         const int n_vals = 2 * fe->n_mels;
         moments_reduce_kernel<<<(n_vals + 127) / 128, 128, 0, st>>>(p.moments_partial, grid, n_vals, a->moments);
     } else {
-        logmel_fused_kernel<false><<<grid, kThreads, fe->smem_bytes, st>>>(p);
+        if (p.out_bf16) logmel_fused_kernel<false, __nv_bfloat16><<<grid, kThreads, fe->smem_bytes, st>>>(p);
+        else logmel_fused_kernel<false, float><<<grid, kThreads, fe->smem_bytes, st>>>(p);
     }
     cudaError_t e = cudaGetLastError();
     if (prev != fe->device) cudaSetDevice(prev);
