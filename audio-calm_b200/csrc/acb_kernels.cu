@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 for (int j = 0; j < 16; ++j) {
                     const int n1 = brev5(2 * j);          // < 16
                     const float wa = s_win[32 * n1 + lane];
-                    const float wb = s_win[32 * (n1 + 16) + lane];
+                    const float wb = 1.f - wa;   // periodic Hann: w[n + N/2] = 1 - w[n] (saves half the window loads; <= 1 ulp of 1.0)
                     const float ar = v[n1] * wa, ai = v[n1 + 8] * wa;           // frame A (re) and frame B (im): B = A + one hop
                     xr[2 * j] = fmaf(v[n1 + 16], wb, ar);
                     xr[2 * j + 1] = fmaf(-v[n1 + 16], wb, ar);
