@@ -34,6 +34,12 @@
 #include <string>
 #include <vector>
 
+// Development-only ablation switch (tools/ablate.py builds variants with -DACB_ABLATE=n to price each part of the
+// kernel in situ; results are wrong for n != 0).  The shipped library is always built with ACB_ABLATE == 0.
+#ifndef ACB_ABLATE
+#define ACB_ABLATE 0
+#endif
+
 namespace acb {
 
 constexpr int kNfft = 1024;
@@ -134,16 +140,20 @@ struct BflyLoop {
 __device__ __forceinline__ void fft32_dit(float (&xr)[32], float (&xi)[32]) {
     BflyLoop<1, 0, 0>::run(xr, xi);
     BflyLoop<2, 0, 0>::run(xr, xi);
+#if ACB_ABLATE != 1
     BflyLoop<3, 0, 0>::run(xr, xi);
     BflyLoop<4, 0, 0>::run(xr, xi);
+#endif
     BflyLoop<5, 0, 0>::run(xr, xi);
 }
 
 // Same, when stage 1 (span-1 butterflies, twiddle 1) has already been applied by the caller.
 __device__ __forceinline__ void fft32_dit_from_stage2(float (&xr)[32], float (&xi)[32]) {
     BflyLoop<2, 0, 0>::run(xr, xi);
+#if ACB_ABLATE != 1
     BflyLoop<3, 0, 0>::run(xr, xi);
     BflyLoop<4, 0, 0>::run(xr, xi);
+#endif
     BflyLoop<5, 0, 0>::run(xr, xi);
 }
 
@@ -416,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         float2* scr2 = reinterpret_cast<float2*>(scr);
 
         // ================= phase 1: one frame pair per warp =================
-        if (has_frames && f0 + 2 * warp < cur.frames) {
+        if (has_frames && f0 + 2 * warp < cur.frames && ACB_ABLATE != 7) {
             float xr[32], xi[32];
             {
                 // Hann window folded into the first radix-2 stage: positions (2j, 2j+1) of the bit-reversed order hold
@@ -424,7 +434,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 const float* sp = s_samples + (2 * warp) * kHop + lane;
                 float v[40];
 #pragma unroll
+#if ACB_ABLATE == 6
+                for (int r = 0; r < 40; ++r) v[r] = (float)(lane + r);
+#else
                 for (int r = 0; r < 40; ++r) v[r] = sp[32 * r];
+#endif
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const int n1 = brev5(2 * j);          // < 16
@@ -442,22 +456,28 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
 #pragma unroll
             for (int k1 = 0; k1 < 32; ++k1) {
                 float yr = xr[k1], yi = xi[k1];
-                if (k1 > 0) {
+                if (k1 > 0 && ACB_ABLATE != 2) {
                     const float2 t = s_tw[k1 * 32 + lane];
                     const float tr = yr * t.x - yi * t.y;
                     yi = fmaf(yr, t.y, yi * t.x);
                     yr = tr;
                 }
+#if ACB_ABLATE == 3
+                xr[k1] = yr; xi[k1] = yi;
+#else
                 scr2[k1 * kRowStride + lane] = make_float2(yr, yi);
+#endif
             }
             __syncwarp();
             // lane j = k1 now owns row j: the 32 values over n2
 #pragma unroll
+#if ACB_ABLATE != 3
             for (int n2 = 0; n2 < 32; ++n2) {
                 const float2 z = scr2[lane * kRowStride + n2];
                 xr[brev5(n2)] = z.x;
                 xi[brev5(n2)] = z.y;
             }
+#endif
             __syncwarp();
             fft32_dit(xr, xi);  // over n2 -> k2 ; lane j holds Z[j + 32*k2]
             // separate the two real spectra and take |X|^2 (x4; the 1/4 is folded into the weights):
@@ -468,8 +488,12 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
             for (int m = 0; m < 16; ++m) {
                 const float offer_r = (lane == 0) ? xr[(32 - m) & 31] : xr[31 - m];
                 const float offer_i = (lane == 0) ? xi[(32 - m) & 31] : xi[31 - m];
+#if ACB_ABLATE == 5
+                const float c = offer_r, d = offer_i;
+#else
                 const float c = __shfl_sync(0xffffffffu, offer_r, src_lane);
                 const float d = __shfl_sync(0xffffffffu, offer_i, src_lane);
+#endif
                 const float a = xr[m], b = xi[m];
                 const float apc = a + c, bmd = b - d, amc = a - c, bpd = b + d;
                 const float pa = fmaf(apc, apc, bmd * bmd);
@@ -493,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         const bool direct = !p.time_major && (f0 + kTileFrames - 1 <= cur.frames - 2 - pad);
 
         // ================= phase 2: banded mel projection, clamp, log, affine, moments =================
-        if (has_frames) {
+        if (has_frames && ACB_ABLATE != 8) {
             const int q = lane >> 3;     // band slot within the round
             const int pr = lane & 7;     // frame pair
             const float* pair_scratch = s_scratch + pr * kScratchFloats;
@@ -508,7 +532,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + (ast >> 1);   // two bins x (A, B)
                 const float2* w2 = reinterpret_cast<const float2*>(s_pw + s_woff[slot]) + q;
                 float accA0 = 0.f, accB0 = 0.f, accA1 = 0.f, accB1 = 0.f;
-                const int half_trip = trip >> 1;
+                const int half_trip = ACB_ABLATE == 4 ? 0 : (trip >> 1);
 #pragma unroll 4
                 for (int i = 0; i < half_trip; ++i) {
                     const float4 pw = p4[i];
