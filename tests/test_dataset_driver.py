@@ -1,0 +1,122 @@
+"""The dataset driver mirror (preprocess/process_dataset.py) and the statistics CLIs around the hot path.
+
+CPU tests cover the host-side bookkeeping (paths, resume, transcripts, sharding, CLI flags); the GPU tests run the driver end to end on
+synthetic .wav files and compare every saved payload with the oracle's restatement of process_dataset.py:140-156."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import audio_calm_b200 as acb
+from audio_calm_b200.preprocess import compute_latent_stats, compute_mel_stats, process_dataset as pd
+from oracle import logmel_oracle as o
+
+
+def _args(**kw):
+    base = dict(dataset_name="librispeech", in_dir="", out_dir="", vae_ckpt=None, mel_only=True, cv_tsv=None, num_gpus=1,
+                workers_per_gpu=2, force=False)
+    base.update(kw)
+    return types.SimpleNamespace(**base)
+
+
+def _write_wav(path, x):
+    from scipy.io import wavfile
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    wavfile.write(path, 16000, x.astype(np.float32))
+
+
+def test_cli_flags_match_the_reference():
+    a = pd.build_parser().parse_args(["--dataset_name", "libritts", "--in_dir", "i", "--out_dir", "o", "--mel_only", "--force",
+                                      "--num_gpus", "2", "--workers_per_gpu", "3", "--cv_tsv", "x.tsv", "--vae_ckpt", "c"])
+    assert (a.dataset_name, a.in_dir, a.out_dir, a.mel_only, a.force, a.num_gpus, a.workers_per_gpu, a.cv_tsv, a.vae_ckpt) == \
+           ("libritts", "i", "o", True, True, 2, 3, "x.tsv", "c")
+
+
+def test_scan_and_output_paths(tmp_path):
+    root = tmp_path / "in"
+    for rel in ("a/b/u1.wav", "a/b/u2.flac", "a/c/u3.mp3", "a/c/notes.txt"):
+        p = root / rel
+        p.parent.mkdir(parents=True, exist_ok=True)
+        p.write_bytes(b"")
+    files = pd.scan_files(str(root))
+    assert sorted(os.path.basename(f) for f in files) == ["u1.wav", "u2.flac", "u3.mp3"]
+    args = _args(in_dir=str(root), out_dir=str(tmp_path / "out"))
+    save_dir, file_id, save_path = pd.output_path(str(root / "a/b/u1.wav"), args)
+    assert save_dir == str(tmp_path / "out" / "a" / "b") and file_id == "u1" and save_path.endswith("a/b/u1.pt")
+    args.dataset_name = "commonvoice"                       # flat output (process_dataset.py:113-116)
+    assert pd.output_path(str(root / "a/b/u1.wav"), args)[0] == str(tmp_path / "out")
+
+
+def test_transcripts(tmp_path):
+    d = tmp_path / "spk" / "chap"
+    d.mkdir(parents=True)
+    (d / "spk-chap.trans.txt").write_text("spk-chap-0001 HELLO WORLD\nspk-chap-0002 SECOND LINE\n")
+    (d / "utt.normalized.txt").write_text(" normalised text \n")
+    assert pd.transcript_for(str(d / "spk-chap-0002.flac"), _args(dataset_name="librispeech"), {}) == "SECOND LINE"
+    assert pd.transcript_for(str(d / "utt.wav"), _args(dataset_name="libritts"), {}) == "normalised text"
+    assert pd.transcript_for(str(d / "x.mp3"), _args(dataset_name="commonvoice"), {"x.mp3": "bonjour"}) == "bonjour"
+    tsv = tmp_path / "cv.tsv"
+    tsv.write_text("path\tsentence\nx.mp3\tbonjour\n")
+    assert pd.get_common_voice_map(str(tsv)) == {"x.mp3": "bonjour"}
+
+
+def test_load_audio_pcm_wav(tmp_path):
+    from scipy.io import wavfile
+    x = (o.hash_noise(4000, 3) * 30000).astype(np.int16)
+    wavfile.write(str(tmp_path / "a.wav"), 16000, x)
+    w = pd.load_audio(str(tmp_path / "a.wav"))
+    assert w.dtype == torch.float32 and tuple(w.shape) == (1, 4000)
+    assert np.allclose(w.numpy()[0], x.astype(np.float32) / 32768.0, atol=1e-7)
+
+
+def test_iter_files_generators(tmp_path):
+    for rel in ("x/a.pt", "x/y/b.pt", "x/c.txt"):
+        p = tmp_path / rel
+        p.parent.mkdir(parents=True, exist_ok=True)
+        p.write_bytes(b"")
+    assert sorted(os.path.basename(p) for p in compute_mel_stats.iter_mel_files(str(tmp_path))) == ["a.pt", "b.pt"]
+
+
+# ------------------------------------------------------------------------------------------------ GPU: end to end
+@pytest.mark.gpu
+def test_driver_mel_only_matches_reference_pipeline(tmp_path):
+    fe_tables = acb.tables.calm_tables()
+    window, fb = fe_tables[0].numpy(), fe_tables[1].numpy()
+    root, out = tmp_path / "in", tmp_path / "out"
+    clips = {"s1/c1/u1.wav": o.synth_clip(16000, 21), "s1/c1/u2.wav": o.synth_clip(40001, 22), "s1/c2/u3.wav": o.hash_noise(24000, 23),
+             "s2/c3/u4.wav": np.stack([o.synth_clip(20000, 24), o.hash_noise(20000, 25)], axis=1)}   # u4 is stereo
+    for rel, x in clips.items():
+        _write_wav(str(root / rel), x)
+    _write_wav(str(root / "s2/c3/short.wav"), o.hash_noise(300, 26))                                  # too short: reported, not fatal
+    args = _args(in_dir=str(root), out_dir=str(out))
+    runner = pd.ShardRunner(args, 0, batch_samples=70000, decode_threads=2)                           # forces several ragged launches
+    runner.run(pd.scan_files(str(root)))
+    assert len(runner.errors) == 1 and "short.wav" in runner.errors[0][0]
+    for rel, x in clips.items():
+        payload = torch.load(str(out / rel.replace(".wav", ".pt")))
+        mel = payload["mel"]
+        mono = x if x.ndim == 1 else x.T                                                              # [C, L] for the oracle
+        ref = o.dataset_mel(np.atleast_2d(mono), window, fb)
+        assert mel.dtype == torch.float32 and tuple(mel.shape) == ref.shape and mel.shape[1] % 4 == 0
+        assert float(np.max(np.abs(mel.numpy() - ref))) < 1e-4
+    # resume: nothing is rewritten unless --force (process_dataset.py:125-130)
+    stamp = {rel: os.path.getmtime(str(out / rel.replace(".wav", ".pt"))) for rel in clips}
+    pd.ShardRunner(args, 0).run(pd.scan_files(str(root)))
+    assert stamp == {rel: os.path.getmtime(str(out / rel.replace(".wav", ".pt"))) for rel in clips}
+
+
+@pytest.mark.gpu
+def test_stats_cli_over_saved_features(tmp_path, capsys, manifest):
+    fe_tables = acb.tables.calm_tables()
+    window, fb = fe_tables[0].numpy(), fe_tables[1].numpy()
+    mels = [o.dataset_mel(o.hash_noise(n, s)[None], window, fb).astype(np.float32) for n, s in ((16000, 1), (40000, 2), (100001, 3))]
+    for i, m in enumerate(mels):
+        torch.save({"mel": torch.from_numpy(m)}, str(tmp_path / f"m{i}.pt"))
+    stats = compute_mel_stats.main(["--root", str(tmp_path)])
+    lines = capsys.readouterr().out.strip().splitlines()
+    want = manifest["stats_three_files"]                       # what the reference's compute_mel_stats.py printed for these files
+    assert lines[-2:] == want["printed"]
+    assert stats.count == want["total_count"]
+    assert abs(stats.mel_mean - want["mean"]) < 1e-6 and abs(stats.mel_std - want["std"]) < 1e-6
