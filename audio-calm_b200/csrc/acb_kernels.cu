@@ -49,8 +49,8 @@ constexpr int kTileFrames = 16;
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kTileSamples = (kTileFrames + 3) * kHop;       // 4864 samples staged per tile
-constexpr int kRowStride = 33;                               // complex elements per scratch row (conflict-free transpose)
-constexpr int kScratchFloats = 32 * kRowStride * 2 + 4;      // 2116 floats / warp; == 4 (mod 32): 16-byte loads of 8 pairs hit 32 distinct banks
+constexpr int kRowStride = 34;                               // complex elements per scratch row: 8-byte column stores and 16-byte row loads are both conflict-free
+constexpr int kScratchFloats = 32 * kRowStride * 2 + 4;      // 2180 floats / warp; == 4 (mod 32): 16-byte loads of 8 pairs hit 32 distinct banks
 constexpr int kMaxMels = 128;
 constexpr int kMaxRounds = 4;                                // mel plan: rounds of (4 bands) per warp
 constexpr int kMaxWeights = 4096;
@@ -163,7 +163,7 @@ __device__ __forceinline__ void fft32_dit_from_stage2(float (&xr)[32], float (&x
 struct LogmelParams {
     // tables (device)
     const float* window;       // [1024]
-    const float2* twiddle;     // [32][32]  exp(-2*pi*i*k1*n2/1024) at [k1][n2]
+    const float4* twiddle;     // [16][32]  (W^(2h*l), W^((2h+1)*l)) at [h][l], W = exp(-2*pi*i/1024): symmetric in (k1, n2)
     // mel plan: per (warp, round) four band slots with a common even trip count; weights zero-padded to the trip
     // and interleaved as [i/2][slot][2] so that a lane fetches two consecutive weights with one 8-byte load
     const float* plan_w;       // [n_plan_w]
@@ -174,7 +174,7 @@ struct LogmelParams {
     int n_plan_w;
     int n_mels;
     float clamp_min;
-    float log_scale;           // 1 for ln, 1/ln(10) for log10 (applied to ln)
+    float log_scale;           // ln(2) for ln, log10(2) for log10 (applied to log2)
     float log_floor;           // log(clamp_min) computed on the host: clamped values are exactly the reference's floor
     // batch
     const float* wav;
@@ -207,7 +207,7 @@ struct LogmelParams {
 };
 
 struct SmemLayout {
-    int samples, scratch, twiddle, window, plan_w, out, plan_woff, plan_trip, plan_band, plan_astart, moments, total_bytes;
+    int samples, scratch, twiddle, window, plan_w, out, affine, plan_woff, plan_trip, plan_band, plan_astart, moments, total_bytes;
 };
 
 __host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }   // odd: conflict-free both ways
@@ -218,9 +218,10 @@ __host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w,
     L.samples = off; off += kTileSamples;
     L.scratch = off; off += kWarps * kScratchFloats;
     L.twiddle = off; off += 32 * 32 * 2;
-    L.window = off; off += kNfft;
+    L.window = off; off += kNfft / 2;                             // first half only: w[n + N/2] = 1 - w[n]
     L.plan_w = off; off += (n_plan_w + 3) & ~3;
     L.out = off; off += (kTileFrames * out_row_stride(n_mels) + 3) & ~3;
+    L.affine = off; off += 2 * ((n_mels + 1) & ~1);
     L.plan_woff = off; off += kWarps * kMaxRounds;
     L.plan_trip = off; off += kWarps * kMaxRounds / 2;            // shorts
     L.plan_band = off; off += kWarps * kMaxRounds * 4 / 2;        // shorts
@@ -381,12 +382,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     const SmemLayout L = make_smem_layout(p.n_mels, p.n_plan_w, kMoments);
     float* s_samples = smem + L.samples;
     float* s_scratch = smem + L.scratch;
-    float2* s_tw = reinterpret_cast<float2*>(smem + L.twiddle);
+    float4* s_tw4 = reinterpret_cast<float4*>(smem + L.twiddle);
     float* s_win = smem + L.window;
     float* s_pw = smem + L.plan_w;
     float* s_out = smem + L.out;
+    float2* s_aff = reinterpret_cast<float2*>(smem + L.affine);   // per band (scale, shift): out = v * scale + shift
     int* s_woff = reinterpret_cast<int*>(smem + L.plan_woff);
-    short* s_trip = reinterpret_cast<short*>(smem + L.plan_trip);
+    short* s_nblk = reinterpret_cast<short*>(smem + L.plan_trip);
     short* s_band = reinterpret_cast<short*>(smem + L.plan_band);
     short* s_astart = reinterpret_cast<short*>(smem + L.plan_astart);
     double* s_mom = reinterpret_cast<double*>(smem + L.moments);   // [2][n_mels], only when kMoments
@@ -396,13 +398,20 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     const int warp = tid >> 5;
     const int n_mels = p.n_mels;
     const int S = out_row_stride(n_mels);
+    const bool write_out = p.out != nullptr;   // statistics-only launches have no feature output
 
     // ---- one-time table staging ----
-    for (int i = tid; i < 32 * 32; i += kThreads) s_tw[i] = p.twiddle[i];
-    for (int i = tid; i < kNfft; i += kThreads) s_win[i] = p.window[i];
+    for (int i = tid; i < 16 * 32; i += kThreads) s_tw4[i] = p.twiddle[i];
+    for (int i = tid; i < kNfft / 2; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < p.n_plan_w; i += kThreads) s_pw[i] = p.plan_w[i];
-    for (int i = tid; i < kWarps * kMaxRounds; i += kThreads) { s_woff[i] = p.plan_woff[i]; s_trip[i] = p.plan_trip[i]; }
+    for (int i = tid; i < kWarps * kMaxRounds; i += kThreads) { s_woff[i] = p.plan_woff[i]; s_nblk[i] = p.plan_trip[i]; }
     for (int i = tid; i < kWarps * kMaxRounds * 4; i += kThreads) { s_band[i] = p.plan_band[i]; s_astart[i] = p.plan_astart[i]; }
+    for (int i = tid; i < n_mels; i += kThreads) {
+        float sc = 1.f, sh = 0.f;   // affine == 0: v * 1 + 0 is exact
+        if (p.affine == 1) { sc = p.affine_inv_std; sh = -p.affine_mean * p.affine_inv_std; }
+        else if (p.affine == 2) { sc = 1.f / __ldg(p.bin_std + i); sh = -__ldg(p.bin_mean + i) * sc; }
+        s_aff[i] = make_float2(sc, sh);
+    }
     if (kMoments)
         for (int i = tid; i < 2 * n_mels; i += kThreads) s_mom[i] = 0.0;
 
@@ -415,6 +424,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         cursor_init(p, cur, t_begin);
         if (cur.tile_in_clip * kTileFrames < cur.frames) load_tile_samples(p, cur, s_samples);
     }
+
+    // ---- per-thread constants of the mel phase: lanes = 4 band slots x 8 frame pairs, up to kMaxRounds rounds per warp ----
+    const int q = lane >> 3;     // band slot within a round
+    const int pr = lane & 7;     // frame pair
+    const float* pair_scratch = s_scratch + pr * kScratchFloats;
 
     for (long long tile = t_begin; tile < t_end; ++tile) {
         cp_async_wait_all();
@@ -443,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 for (int j = 0; j < 16; ++j) {
                     const int n1 = brev5(2 * j);          // < 16
                     const float wa = s_win[32 * n1 + lane];
-                    const float wb = 1.f - wa;   // periodic Hann: w[n + N/2] = 1 - w[n] (saves half the window loads; <= 1 ulp of 1.0)
+                    const float wb = 1.f - wa;   // periodic Hann: w[n + N/2] = 1 - w[n] (only the first half of the window is staged)
                     const float ar = v[n1] * wa, ai = v[n1 + 8] * wa;           // frame A (re) and frame B (im): B = A + one hop
                     xr[2 * j] = fmaf(v[n1 + 16], wb, ar);
                     xr[2 * j + 1] = fmaf(-v[n1 + 16], wb, ar);
@@ -452,33 +466,37 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 }
             }
             fft32_dit_from_stage2(xr, xi);  // over n1 -> k1 (natural order)
-            // twiddle W_1024^(k1*lane), store transposed: scr[k1][lane]
-#pragma unroll
-            for (int k1 = 0; k1 < 32; ++k1) {
-                float yr = xr[k1], yi = xi[k1];
-                if (k1 > 0 && ACB_ABLATE != 2) {
-                    const float2 t = s_tw[k1 * 32 + lane];
-                    const float tr = yr * t.x - yi * t.y;
-                    yi = fmaf(yr, t.y, yi * t.x);
-                    yr = tr;
-                }
-#if ACB_ABLATE == 3
-                xr[k1] = yr; xi[k1] = yi;
-#else
-                scr2[k1 * kRowStride + lane] = make_float2(yr, yi);
-#endif
-            }
-            __syncwarp();
-            // lane j = k1 now owns row j: the 32 values over n2
-#pragma unroll
 #if ACB_ABLATE != 3
-            for (int n2 = 0; n2 < 32; ++n2) {
-                const float2 z = scr2[lane * kRowStride + n2];
-                xr[brev5(n2)] = z.x;
-                xi[brev5(n2)] = z.y;
-            }
+            // twiddle W_1024^(k1*lane) (two k1 per 16-byte table load), then transposed store scr[k1][lane]
+#pragma unroll
+            for (int h = 0; h < 16; ++h) {
+#if ACB_ABLATE == 2
+                scr2[(2 * h) * kRowStride + lane] = make_float2(xr[2 * h], xi[2 * h]);
+                scr2[(2 * h + 1) * kRowStride + lane] = make_float2(xr[2 * h + 1], xi[2 * h + 1]);
+#else
+                const float4 t = s_tw4[h * 32 + lane];
+                if (h == 0) {   // W^0 = 1
+                    scr2[lane] = make_float2(xr[0], xi[0]);
+                } else {
+                    scr2[(2 * h) * kRowStride + lane] = make_float2(fmaf(xr[2 * h], t.x, -xi[2 * h] * t.y), fmaf(xr[2 * h], t.y, xi[2 * h] * t.x));
+                }
+                scr2[(2 * h + 1) * kRowStride + lane] =
+                    make_float2(fmaf(xr[2 * h + 1], t.z, -xi[2 * h + 1] * t.w), fmaf(xr[2 * h + 1], t.w, xi[2 * h + 1] * t.z));
 #endif
+            }
             __syncwarp();
+            // lane j = k1 now owns row j: the 32 values over n2, read 16 bytes (two values) at a time
+            {
+                const float4* row4 = reinterpret_cast<const float4*>(scr2 + lane * kRowStride);
+#pragma unroll
+                for (int h = 0; h < 16; ++h) {
+                    const float4 z = row4[h];
+                    xr[brev5(2 * h)] = z.x; xi[brev5(2 * h)] = z.y;
+                    xr[brev5(2 * h + 1)] = z.z; xi[brev5(2 * h + 1)] = z.w;
+                }
+            }
+            __syncwarp();
+#endif
             fft32_dit(xr, xi);  // over n2 -> k2 ; lane j holds Z[j + 32*k2]
             // separate the two real spectra and take |X|^2 (x4; the 1/4 is folded into the weights):
             //   Z[k] = a+ib, Z[1024-k] = c+id  =>  4|XA|^2 = (a+c)^2+(b-d)^2 , 4|XB|^2 = (a-c)^2+(b+d)^2
@@ -518,33 +536,29 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
 
         // ================= phase 2: banded mel projection, clamp, log, affine, moments =================
         if (has_frames && ACB_ABLATE != 8) {
-            const int q = lane >> 3;     // band slot within the round
-            const int pr = lane & 7;     // frame pair
-            const float* pair_scratch = s_scratch + pr * kScratchFloats;
             const int fA = f0 + 2 * pr;
             OutT* out_clip = reinterpret_cast<OutT*>(p.out) + cur.out_base;
             for (int r = 0; r < kMaxRounds; ++r) {
                 const int slot = warp * kMaxRounds + r;
-                const int trip = s_trip[slot];
+                const int trip = s_nblk[slot];
                 if (trip == 0) break;  // warp-uniform; rounds are filled in order
                 const int b = s_band[slot * 4 + q];
-                const int ast = s_astart[slot * 4 + q];
-                const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + (ast >> 1);   // two bins x (A, B)
+                const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + (s_astart[slot * 4 + q] >> 1);   // two bins x (A, B)
                 const float2* w2 = reinterpret_cast<const float2*>(s_pw + s_woff[slot]) + q;
-                float accA0 = 0.f, accB0 = 0.f, accA1 = 0.f, accB1 = 0.f;
+                float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
                 const int half_trip = ACB_ABLATE == 4 ? 0 : (trip >> 1);
 #pragma unroll 4
                 for (int i = 0; i < half_trip; ++i) {
                     const float4 pw = p4[i];
                     const float2 w = w2[4 * i];
-                    accA0 = fmaf(w.x, pw.x, accA0);
-                    accB0 = fmaf(w.x, pw.y, accB0);
-                    accA1 = fmaf(w.y, pw.z, accA1);
-                    accB1 = fmaf(w.y, pw.w, accB1);
+                    acc0 = fmaf(w.x, pw.x, acc0);
+                    acc1 = fmaf(w.x, pw.y, acc1);
+                    acc2 = fmaf(w.y, pw.z, acc2);
+                    acc3 = fmaf(w.y, pw.w, acc3);
                 }
-                const float mA = (accA0 + accA1) * cur.gain, mB = (accB0 + accB1) * cur.gain;
-                float vA = (mA > p.clamp_min) ? __logf(mA) * p.log_scale : p.log_floor;
-                float vB = (mB > p.clamp_min) ? __logf(mB) * p.log_scale : p.log_floor;
+                const float mA = (acc0 + acc2) * cur.gain, mB = (acc1 + acc3) * cur.gain;
+                float vA = (mA > p.clamp_min) ? __log2f(mA) * p.log_scale : p.log_floor;
+                float vB = (mB > p.clamp_min) ? __log2f(mB) * p.log_scale : p.log_floor;
                 if (kMoments) {
                     // frames T-2-j (j < pad) are stored twice (reflected pad-to-4 columns) and counted twice
                     double s = 0.0, s2 = 0.0;
@@ -567,18 +581,15 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                     if (pr == 0 && b >= 0) { s_mom[b] += s; s_mom[n_mels + b] += s2; }   // each band has exactly one owner slot
                 }
                 if (b >= 0) {
-                    if (p.affine == 1) {
-                        vA = (vA - p.affine_mean) * p.affine_inv_std;
-                        vB = (vB - p.affine_mean) * p.affine_inv_std;
-                    } else if (p.affine == 2) {
-                        const float mu = __ldg(p.bin_mean + b), is = 1.f / __ldg(p.bin_std + b);
-                        vA = (vA - mu) * is;
-                        vB = (vB - mu) * is;
-                    }
+                    const float2 af = s_aff[b];
+                    vA = fmaf(vA, af.x, af.y);
+                    vB = fmaf(vB, af.x, af.y);
                     if (direct) {
-                        OutT* dst = out_clip + (size_t)b * cur.cap + fA;
-                        dst[0] = to_out<OutT>(vA);
-                        dst[1] = to_out<OutT>(vB);
+                        if (write_out) {
+                            OutT* dst = out_clip + (size_t)((unsigned)b * (unsigned)cur.cap) + fA;
+                            dst[0] = to_out<OutT>(vA);
+                            dst[1] = to_out<OutT>(vB);
+                        }
                     } else {
                         s_out[(2 * pr) * S + b] = vA;
                         s_out[(2 * pr + 1) * S + b] = vB;
@@ -588,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         }
         if (!direct) {   // CTA-uniform
             __syncthreads();  // output tile staged
-            store_tile<OutT>(p, cur, s_out, n_mels, S);
+            if (write_out) store_tile<OutT>(p, cur, s_out, n_mels, S);
         }
         cur = nxt;
     }
@@ -776,7 +787,7 @@ struct acb_frontend {
     // one device allocation holding every table
     void* d_blob = nullptr;
     const float* d_window = nullptr;
-    const float2* d_twiddle = nullptr;
+    const float4* d_twiddle = nullptr;
     const float* d_plan_w = nullptr;
     const int* d_plan_woff = nullptr;
     const short* d_plan_trip = nullptr;
@@ -910,12 +921,12 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     }
     if ((int)plan_w.size() > kMaxWeights * 2) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel plan too large");
 
-    // twiddles exp(-2*pi*i*k1*n2/1024) in double, rounded once
-    std::vector<float2> tw(32 * 32);
-    for (int k1 = 0; k1 < 32; ++k1)
-        for (int n2 = 0; n2 < 32; ++n2) {
-            const double a = -2.0 * M_PI * (double)(k1 * n2) / 1024.0;
-            tw[k1 * 32 + n2] = make_float2((float)cos(a), (float)sin(a));
+    // twiddles W^(n2*l) = exp(-2*pi*i*n2*l/1024) in double, rounded once; entry [h][l] holds n2 = 2h and 2h + 1
+    std::vector<float4> tw(16 * 32);
+    for (int h = 0; h < 16; ++h)
+        for (int l = 0; l < 32; ++l) {
+            const double a0 = -2.0 * M_PI * (double)((2 * h) * l) / 1024.0, a1 = -2.0 * M_PI * (double)((2 * h + 1) * l) / 1024.0;
+            tw[h * 32 + l] = make_float4((float)cos(a0), (float)sin(a0), (float)cos(a1), (float)sin(a1));
         }
 
     int prev = 0;
@@ -929,13 +940,13 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     // pack the blob
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
-    const size_t o_win = take(sizeof(float) * kNfft), o_tw = take(sizeof(float2) * 1024),
+    const size_t o_win = take(sizeof(float) * kNfft), o_tw = take(sizeof(float4) * 512),
                  o_pw = take(sizeof(float) * std::max<size_t>(plan_w.size(), 1)), o_po = take(sizeof(int) * plan_woff.size()),
                  o_pt = take(sizeof(short) * plan_trip.size()), o_pb = take(sizeof(short) * plan_band.size()),
                  o_pa = take(sizeof(short) * plan_astart.size());
     std::vector<unsigned char> host(o, 0);
     memcpy(host.data() + o_win, window_host, sizeof(float) * kNfft);
-    memcpy(host.data() + o_tw, tw.data(), sizeof(float2) * 1024);
+    memcpy(host.data() + o_tw, tw.data(), sizeof(float4) * 512);
     if (!plan_w.empty()) memcpy(host.data() + o_pw, plan_w.data(), sizeof(float) * plan_w.size());
     memcpy(host.data() + o_po, plan_woff.data(), sizeof(int) * plan_woff.size());
     memcpy(host.data() + o_pt, plan_trip.data(), sizeof(short) * plan_trip.size());
@@ -965,7 +976,7 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     fe->grid = fe->num_sms * std::max(occ, 1);
     auto* base = static_cast<unsigned char*>(fe->d_blob);
     fe->d_window = reinterpret_cast<const float*>(base + o_win);
-    fe->d_twiddle = reinterpret_cast<const float2*>(base + o_tw);
+    fe->d_twiddle = reinterpret_cast<const float4*>(base + o_tw);
     fe->d_plan_w = reinterpret_cast<const float*>(base + o_pw);
     fe->d_plan_woff = reinterpret_cast<const int*>(base + o_po);
     fe->d_plan_trip = reinterpret_cast<const short*>(base + o_pt);
@@ -998,7 +1009,8 @@ int64_t acb_moments_workspace_bytes(const acb_frontend* fe) {
 int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* stream) {
     if (!fe || !a) return fail(ACB_ERR_INVALID, "acb_logmel_forward: null argument");
     if (a->n_clips <= 0 || a->n_tiles <= 0) return ACB_OK;  // empty batch
-    if (!a->wav || !a->out) return fail(ACB_ERR_INVALID, "acb_logmel_forward: null wav/out");
+    if (!a->wav) return fail(ACB_ERR_INVALID, "acb_logmel_forward: null wav");
+    if (!a->out && !a->moments) return fail(ACB_ERR_INVALID, "acb_logmel_forward: out may be NULL only for a statistics-only launch (moments set)");
     if (a->out_dtype != ACB_F32 && a->out_dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_logmel_forward: bad out_dtype");
     if (a->out_layout != ACB_MEL_MAJOR && a->out_layout != ACB_TIME_MAJOR) return fail(ACB_ERR_INVALID, "acb_logmel_forward: bad out_layout");
     if (a->pad_multiple < 1) return fail(ACB_ERR_INVALID, "acb_logmel_forward: pad_multiple must be >= 1");
@@ -1007,13 +1019,14 @@ int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* s
     if (a->affine == 1 && !(a->affine_std > 0.f)) return fail(ACB_ERR_INVALID, "acb_logmel_forward: affine_std must be > 0");
     if (a->moments && !a->moments_workspace) return fail(ACB_ERR_INVALID, "acb_logmel_forward: moments need a workspace");
     if (!a->frame_capacity_per_clip && a->frame_capacity <= 0) return fail(ACB_ERR_INVALID, "acb_logmel_forward: frame_capacity must be > 0");
+    if (a->frame_capacity * (int64_t)fe->n_mels >= (int64_t)1 << 32) return fail(ACB_ERR_INVALID, "acb_logmel_forward: n_mels * frame_capacity must be < 2^32");
 
     LogmelParams p{};
     p.window = fe->d_window; p.twiddle = fe->d_twiddle;
     p.plan_w = fe->d_plan_w; p.plan_woff = fe->d_plan_woff; p.plan_trip = fe->d_plan_trip;
     p.plan_band = fe->d_plan_band; p.plan_astart = fe->d_plan_astart; p.n_plan_w = fe->n_plan_w;
     p.n_mels = fe->n_mels; p.clamp_min = fe->clamp_min;
-    p.log_scale = fe->log_kind == ACB_LOG_10 ? 0.43429448190325176f : 1.f;
+    p.log_scale = fe->log_kind == ACB_LOG_10 ? 0.30102999566398120f : 0.69314718055994531f;   // log10(2) : ln(2)
     p.log_floor = fe->log_kind == ACB_LOG_10 ? log10f(fe->clamp_min) : logf(fe->clamp_min);
     p.wav = a->wav;
     p.clip_offset = reinterpret_cast<const long long*>(a->clip_offset);

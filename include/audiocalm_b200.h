@@ -87,7 +87,7 @@ typedef struct acb_logmel_args {
     /* ---- optional fused peak normalisation (preprocess/core.py:108-110) ---- */
     const float* clip_peak;      /* device [n_clips] max|x| per clip from acb_peak_abs, or NULL */
     /* ---- output ---- */
-    void* out;                   /* device */
+    void* out;                   /* device; NULL = statistics-only launch (needs moments != NULL): nothing is stored */
     int32_t out_dtype;           /* ACB_F32 | ACB_BF16 */
     int32_t out_layout;          /* ACB_MEL_MAJOR | ACB_TIME_MAJOR */
     const int64_t* out_offset;   /* device [n_clips] element offset of clip i in out; NULL => i * out_clip_stride */
