@@ -9,16 +9,18 @@
 // Every input sample is read from HBM once (plus a 3/16 halo served by L2) and every output value is
 // written once.
 //
-// Structure of one CTA (256 threads = 8 warps, 2 CTAs per SM, contiguous range of 16-frame tiles):
-//   1. cp.async the tile's (16+3)*256 samples into shared memory (reflection handled for edge tiles);
+// Structure: a CTA (256 threads, 2 CTAs per SM) holds TWO independent groups of 4 warps; a group owns a contiguous range
+// of 8-frame tiles, its own sample buffer, scratch and named barrier, so four groups per SM run out of phase and the
+// FMA-heavy and the shared-memory-heavy parts of different groups overlap.  Per tile a group does:
+//   1. cp.async the tile's (8+3)*256 samples into shared memory (reflection handled for edge tiles);
 //   2. each warp takes one pair of adjacent frames (A, B) and runs ONE complex 1024-point FFT of
 //      A + iB as 32 x 32: radix-2 DIT FFT-32 in registers (FMA butterflies), twiddle, transpose through
 //      a warp-private padded scratch, second FFT-32; the two real spectra are separated with warp
 //      shuffles ((k, 1024-k) partners live in lane 32-j) and |X|^2 goes to the warp's scratch;
-//   3. the CTA applies the banded mel filterbank (1001 non-zero weights instead of a 513x80 GEMM):
-//      lanes = 4 bands x 8 frame pairs, warp-uniform trip counts from a host-built balanced schedule;
-//      clamp, log, optional affine, optional fp64 moments; results staged in shared memory;
-//   4. coalesced store of the 16 x n_mels tile in either layout, plus the reflected pad-to-4 columns.
+//   3. the group applies the banded mel filterbank (1001 non-zero weights instead of a 513x80 GEMM):
+//      lanes = 8 bands x 4 frame pairs, warp-uniform trip counts from a host-built balanced schedule;
+//      clamp, log, optional affine, optional fp64 moments; interior tiles store straight from registers;
+//   4. edge tiles are staged in shared memory and stored with masking, reflected pad-to-4 columns and tail fill.
 // The next tile's samples are prefetched (cp.async) while step 3/4 run.
 #include "audiocalm_b200.h"
 
@@ -45,15 +47,21 @@ namespace acb {
 constexpr int kNfft = 1024;
 constexpr int kHop = 256;
 constexpr int kBins = 512;                                   // bins 0..511 are produced; 512 (Nyquist) has zero weight
-constexpr int kTileFrames = 16;
-constexpr int kWarps = 8;
-constexpr int kThreads = kWarps * 32;
-constexpr int kTileSamples = (kTileFrames + 3) * kHop;       // 4864 samples staged per tile
+constexpr int kTileFrames = 8;                               // one tile = 4 frame pairs = one pair per warp of a group
+constexpr int kGroupWarps = 4;
+constexpr int kGroupThreads = kGroupWarps * 32;
+constexpr int kGroups = 2;                                   // independent groups per CTA
+constexpr int kThreads = kGroups * kGroupThreads;
+constexpr int kTileSamples = (kTileFrames + 3) * kHop;       // 2816 samples staged per tile
 constexpr int kRowStride = 34;                               // complex elements per scratch row: 8-byte column stores and 16-byte row loads are both conflict-free
-constexpr int kScratchFloats = 32 * kRowStride * 2 + 4;      // 2180 floats / warp; == 4 (mod 32): 16-byte loads of 8 pairs hit 32 distinct banks
+constexpr int kScratchFloats = 32 * kRowStride * 2 + 8;      // 2184 floats / warp; == 8 (mod 32): see the mel phase
+constexpr int kSlots = 8;                                    // band slots per mel round: lanes = 8 slots x 4 frame pairs
 constexpr int kMaxMels = 128;
-constexpr int kMaxRounds = 4;                                // mel plan: rounds of (4 bands) per warp
+constexpr int kMaxRounds = 4;                                // mel plan: rounds of (8 bands) per warp
 constexpr int kMaxWeights = 4096;
+constexpr int kOutStageOffset = 2 * kBins;                   // the staged output tile lives above pair 0's power spectrum
+static_assert(kScratchFloats % 32 == 8 && kScratchFloats % 4 == 0, "pair stride must be 8 (mod 32) words and 16-byte aligned");
+static_assert(kOutStageOffset + kTileFrames * (kMaxMels | 1) <= kScratchFloats, "staged tile must fit above the power spectrum");
 
 thread_local std::string g_last_error;
 
@@ -164,13 +172,13 @@ struct LogmelParams {
     // tables (device)
     const float* window;       // [1024]
     const float4* twiddle;     // [16][32]  (W^(2h*l), W^((2h+1)*l)) at [h][l], W = exp(-2*pi*i/1024): symmetric in (k1, n2)
-    // mel plan: per (warp, round) four band slots with a common even trip count; weights zero-padded to the trip
+    // mel plan: per (group warp, round) eight band slots with a common even trip count; weights zero-padded to the trip
     // and interleaved as [i/2][slot][2] so that a lane fetches two consecutive weights with one 8-byte load
     const float* plan_w;       // [n_plan_w]
-    const int* plan_woff;      // [kWarps][kMaxRounds] offset (floats) of the round's weights in plan_w
-    const short* plan_trip;    // [kWarps][kMaxRounds] bins per round (even, 0 = no more rounds)
-    const short* plan_band;    // [kWarps][kMaxRounds][4] band id or -1
-    const short* plan_astart;  // [kWarps][kMaxRounds][4] first bin (even) of the slot's run
+    const int* plan_woff;      // [kGroupWarps][kMaxRounds] offset (floats) of the round's weights in plan_w
+    const short* plan_trip;    // [kGroupWarps][kMaxRounds] bins per round (even, 0 = no more rounds)
+    const short* plan_band;    // [kGroupWarps][kMaxRounds][kSlots] band id or -1
+    const short* plan_astart;  // [kGroupWarps][kMaxRounds][kSlots] first bin (even) of the slot's run
     int n_plan_w;
     int n_mels;
     float clamp_min;
@@ -203,11 +211,11 @@ struct LogmelParams {
     float affine_inv_std;
     const float* bin_mean;
     const float* bin_std;
-    double* moments_partial;   // [gridDim.x][2][n_mels] or nullptr
+    double* moments_partial;   // [gridDim.x * kGroups][2][n_mels] or nullptr
 };
 
 struct SmemLayout {
-    int samples, scratch, twiddle, window, plan_w, out, affine, plan_woff, plan_trip, plan_band, plan_astart, moments, total_bytes;
+    int samples, scratch, twiddle, window, plan_w, affine, plan_woff, plan_trip, plan_band, plan_astart, moments, total_bytes;
 };
 
 __host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }   // odd: conflict-free both ways
@@ -215,24 +223,23 @@ __host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }
 __host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w, bool with_moments = false) {
     SmemLayout L;
     int off = 0;  // in 4-byte words
-    L.samples = off; off += kTileSamples;
-    L.scratch = off; off += kWarps * kScratchFloats;
+    L.samples = off; off += kGroups * kTileSamples;
+    L.scratch = off; off += kGroups * kGroupWarps * kScratchFloats;
     L.twiddle = off; off += 32 * 32 * 2;
     L.window = off; off += kNfft / 2;                             // first half only: w[n + N/2] = 1 - w[n]
     L.plan_w = off; off += (n_plan_w + 3) & ~3;
-    L.out = off; off += (kTileFrames * out_row_stride(n_mels) + 3) & ~3;
     L.affine = off; off += 2 * ((n_mels + 1) & ~1);
-    L.plan_woff = off; off += kWarps * kMaxRounds;
-    L.plan_trip = off; off += kWarps * kMaxRounds / 2;            // shorts
-    L.plan_band = off; off += kWarps * kMaxRounds * 4 / 2;        // shorts
-    L.plan_astart = off; off += kWarps * kMaxRounds * 4 / 2;      // shorts
+    L.plan_woff = off; off += kGroupWarps * kMaxRounds;
+    L.plan_trip = off; off += kGroupWarps * kMaxRounds / 2;               // shorts
+    L.plan_band = off; off += kGroupWarps * kMaxRounds * kSlots / 2;      // shorts
+    L.plan_astart = off; off += kGroupWarps * kMaxRounds * kSlots / 2;    // shorts
     off = (off + 1) & ~1;
-    L.moments = off; if (with_moments) off += 4 * n_mels;       // doubles [2][n_mels]
+    L.moments = off; if (with_moments) off += kGroups * 4 * n_mels;       // doubles [kGroups][2][n_mels]
     L.total_bytes = off * 4;
     return L;
 }
 
-// Position of a CTA in its contiguous tile range: which clip, which tile of the clip, and the clip's geometry.
+// Position of a group in its contiguous tile range: which clip, which tile of the clip, and the clip's geometry.
 struct ClipCursor {
     long long wav_base;    // element index of the clip's first sample in wav
     long long length;      // samples in the clip
@@ -289,7 +296,11 @@ __device__ __forceinline__ void cursor_advance(const LogmelParams& p, ClipCursor
     }
 }
 
-__device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const ClipCursor& t, float* s_samples) {
+__device__ __forceinline__ void group_sync(int grp) {   // named barrier of one 4-warp group (barrier 0 is __syncthreads)
+    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
+}
+
+__device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const ClipCursor& t, float* s_samples, int gt) {
     const int f0 = t.tile_in_clip * kTileFrames;
     const long long g0 = (long long)f0 * kHop - kNfft / 2;  // sample index (relative to the clip) of smem slot 0
     const float* src = p.wav + t.wav_base;
@@ -297,15 +308,15 @@ __device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const C
     if (interior) {
         const float* gp = src + g0;
         if ((reinterpret_cast<uintptr_t>(gp) & 15) == 0) {
-            for (int i = threadIdx.x; i < kTileSamples / 4; i += kThreads) cp_async16(s_samples + 4 * i, gp + 4 * i);
+            for (int i = gt; i < kTileSamples / 4; i += kGroupThreads) cp_async16(s_samples + 4 * i, gp + 4 * i);
         } else {
-            for (int i = threadIdx.x; i < kTileSamples; i += kThreads) cp_async4(s_samples + i, gp + i);
+            for (int i = gt; i < kTileSamples; i += kGroupThreads) cp_async4(s_samples + i, gp + i);
         }
     } else {
         // edge tile: reflect about sample 0 and sample L-1 (torch.stft center=True, pad_mode="reflect");
         // slots that belong only to frames >= T get zeros.
         const long long L = t.length;
-        for (int i = threadIdx.x; i < kTileSamples; i += kThreads) {
+        for (int i = gt; i < kTileSamples; i += kGroupThreads) {
             long long idx = g0 + i;
             if (idx < 0) idx = -idx;
             if (idx >= L) idx = 2 * (L - 1) - idx;
@@ -327,16 +338,16 @@ __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return
 // Store one staged tile.  Interior tiles (every frame exists and none is a pad-to-4 source) take loops without
 // per-element conditions; the last tiles of a clip take the general path (masking, reflected columns, tail fill).
 template <typename OutT>
-__device__ __forceinline__ void store_tile(const LogmelParams& p, const ClipCursor& c, const float* s_out, int n_mels, int S) {
+__device__ __forceinline__ void store_tile(const LogmelParams& p, const ClipCursor& c, const float* s_out, int n_mels, int S, int tid) {
     OutT* out = reinterpret_cast<OutT*>(p.out) + c.out_base;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5;   // thread / warp index inside the group
     const int f0 = c.tile_in_clip * kTileFrames;
     const int T = c.frames, T4 = c.frames_padded, pad = T4 - T;
     const bool interior = (f0 + kTileFrames - 1 <= T - 2 - pad);
     if (interior) {
         if (p.time_major) {
             OutT* row0 = out + (size_t)f0 * n_mels;
-            for (int f = warp; f < kTileFrames; f += kWarps) {
+            for (int f = warp; f < kTileFrames; f += kGroupWarps) {
                 OutT* row = row0 + f * n_mels;
                 const float* srow = s_out + f * S;
                 for (int b = lane; b < n_mels; b += 32) row[b] = to_out<OutT>(srow[b]);
@@ -344,13 +355,13 @@ __device__ __forceinline__ void store_tile(const LogmelParams& p, const ClipCurs
         } else {
             OutT* col0 = out + f0;
             const int f = tid & (kTileFrames - 1);
-            for (int b = tid >> 4; b < n_mels; b += kThreads / kTileFrames)
+            for (int b = tid / kTileFrames; b < n_mels; b += kGroupThreads / kTileFrames)
                 col0[(unsigned)b * (unsigned)c.cap + f] = to_out<OutT>(s_out[f * S + b]);
         }
         return;
     }
     const int n_out = kTileFrames * n_mels;
-    for (int idx = tid; idx < n_out; idx += kThreads) {
+    for (int idx = tid; idx < n_out; idx += kGroupThreads) {
         int f, b;
         if (p.time_major) { f = idx / n_mels; b = idx - f * n_mels; }
         else { b = idx / kTileFrames; f = idx - b * kTileFrames; }
@@ -380,32 +391,34 @@ template <bool kMoments, typename OutT>
 __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelParams p) {
     extern __shared__ __align__(16) float smem[];
     const SmemLayout L = make_smem_layout(p.n_mels, p.n_plan_w, kMoments);
-    float* s_samples = smem + L.samples;
-    float* s_scratch = smem + L.scratch;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int grp = tid / kGroupThreads;          // which of the CTA's independent groups
+    const int gt = tid % kGroupThreads;           // thread index inside the group
+    const int gw = gt >> 5;                       // warp index inside the group = frame pair of the tile
+    const int n_mels = p.n_mels;
+    const int S = out_row_stride(n_mels);
+    const bool write_out = p.out != nullptr;      // statistics-only launches have no feature output
+
+    float* s_samples = smem + L.samples + grp * kTileSamples;
+    float* s_scratch = smem + L.scratch + grp * kGroupWarps * kScratchFloats;
+    float* s_out = s_scratch + kOutStageOffset;   // staged edge tiles: above pair 0's power spectrum, dead during the mel phase
     float4* s_tw4 = reinterpret_cast<float4*>(smem + L.twiddle);
     float* s_win = smem + L.window;
     float* s_pw = smem + L.plan_w;
-    float* s_out = smem + L.out;
     float2* s_aff = reinterpret_cast<float2*>(smem + L.affine);   // per band (scale, shift): out = v * scale + shift
     int* s_woff = reinterpret_cast<int*>(smem + L.plan_woff);
-    short* s_nblk = reinterpret_cast<short*>(smem + L.plan_trip);
+    short* s_trip = reinterpret_cast<short*>(smem + L.plan_trip);
     short* s_band = reinterpret_cast<short*>(smem + L.plan_band);
     short* s_astart = reinterpret_cast<short*>(smem + L.plan_astart);
-    double* s_mom = reinterpret_cast<double*>(smem + L.moments);   // [2][n_mels], only when kMoments
+    double* s_mom = reinterpret_cast<double*>(smem + L.moments) + grp * 2 * n_mels;   // [2][n_mels] per group, only when kMoments
 
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-    const int n_mels = p.n_mels;
-    const int S = out_row_stride(n_mels);
-    const bool write_out = p.out != nullptr;   // statistics-only launches have no feature output
-
-    // ---- one-time table staging ----
+    // ---- one-time table staging (whole CTA) ----
     for (int i = tid; i < 16 * 32; i += kThreads) s_tw4[i] = p.twiddle[i];
     for (int i = tid; i < kNfft / 2; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < p.n_plan_w; i += kThreads) s_pw[i] = p.plan_w[i];
-    for (int i = tid; i < kWarps * kMaxRounds; i += kThreads) { s_woff[i] = p.plan_woff[i]; s_nblk[i] = p.plan_trip[i]; }
-    for (int i = tid; i < kWarps * kMaxRounds * 4; i += kThreads) { s_band[i] = p.plan_band[i]; s_astart[i] = p.plan_astart[i]; }
+    for (int i = tid; i < kGroupWarps * kMaxRounds; i += kThreads) { s_woff[i] = p.plan_woff[i]; s_trip[i] = p.plan_trip[i]; }
+    for (int i = tid; i < kGroupWarps * kMaxRounds * kSlots; i += kThreads) { s_band[i] = p.plan_band[i]; s_astart[i] = p.plan_astart[i]; }
     for (int i = tid; i < n_mels; i += kThreads) {
         float sc = 1.f, sh = 0.f;   // affine == 0: v * 1 + 0 is exact
         if (p.affine == 1) { sc = p.affine_inv_std; sh = -p.affine_mean * p.affine_inv_std; }
@@ -413,39 +426,44 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         s_aff[i] = make_float2(sc, sh);
     }
     if (kMoments)
-        for (int i = tid; i < 2 * n_mels; i += kThreads) s_mom[i] = 0.0;
+        for (int i = gt; i < 2 * n_mels; i += kGroupThreads) s_mom[i] = 0.0;
+    __syncthreads();
 
-    // ---- this CTA's contiguous tile range ----
-    const long long t_begin = (long long)p.n_tiles * blockIdx.x / gridDim.x;
-    const long long t_end = (long long)p.n_tiles * (blockIdx.x + 1) / gridDim.x;
+    // ---- this group's contiguous tile range ----
+    const long long n_groups = (long long)gridDim.x * kGroups, g_index = (long long)blockIdx.x * kGroups + grp;
+    const long long t_begin = (long long)p.n_tiles * g_index / n_groups;
+    const long long t_end = (long long)p.n_tiles * (g_index + 1) / n_groups;
 
     ClipCursor cur;
     if (t_begin < t_end) {
         cursor_init(p, cur, t_begin);
-        if (cur.tile_in_clip * kTileFrames < cur.frames) load_tile_samples(p, cur, s_samples);
+        if (cur.tile_in_clip * kTileFrames < cur.frames) load_tile_samples(p, cur, s_samples, gt);
     }
 
-    // ---- per-thread constants of the mel phase: lanes = 4 band slots x 8 frame pairs, up to kMaxRounds rounds per warp ----
-    const int q = lane >> 3;     // band slot within a round
-    const int pr = lane & 7;     // frame pair
+    // ---- per-thread constants of the mel phase: lanes = 8 band slots x 4 frame pairs ----
+    // A quarter-warp's 16-byte power loads touch 2 slots x 4 pairs.  The pair stride is 8 (mod 32) words, so one slot's four
+    // pairs fall on bank groups {0, 8, 16, 24} + 4 * ((astart/2 + i) mod 2): the host plan gives the two slots of a quarter
+    // opposite parity of astart/2, which makes the load conflict-free.
+    const int q = lane >> 2;     // band slot within a round
+    const int pr = lane & 3;     // frame pair
     const float* pair_scratch = s_scratch + pr * kScratchFloats;
+    float* scr = s_scratch + gw * kScratchFloats;
+    float2* scr2 = reinterpret_cast<float2*>(scr);
 
     for (long long tile = t_begin; tile < t_end; ++tile) {
         cp_async_wait_all();
-        __syncthreads();  // samples (and tables, first iteration) visible; previous tile's mel phase done with the scratch
+        group_sync(grp);  // samples visible; previous tile's mel phase / staged store done with the scratch
 
         const int f0 = cur.tile_in_clip * kTileFrames;
         const bool has_frames = f0 < cur.frames;  // false for pure tail-fill tiles
-        float* scr = s_scratch + warp * kScratchFloats;
-        float2* scr2 = reinterpret_cast<float2*>(scr);
 
         // ================= phase 1: one frame pair per warp =================
-        if (has_frames && f0 + 2 * warp < cur.frames && ACB_ABLATE != 7) {
+        if (has_frames && f0 + 2 * gw < cur.frames && ACB_ABLATE != 7) {
             float xr[32], xi[32];
             {
                 // Hann window folded into the first radix-2 stage: positions (2j, 2j+1) of the bit-reversed order hold
                 // samples n1 and n1 + 16, so  x[2j] = a*wa + b*wb ,  x[2j+1] = a*wa - b*wb  (3 ops instead of 4).
-                const float* sp = s_samples + (2 * warp) * kHop + lane;
+                const float* sp = s_samples + (2 * gw) * kHop + lane;
                 float v[40];
 #pragma unroll
 #if ACB_ABLATE == 6
@@ -519,17 +537,17 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 scr2[lane + 32 * m] = make_float2(pa, pb);
             }
         }
-        __syncthreads();  // power spectra of all pairs visible; sample tile is free again
+        group_sync(grp);  // power spectra of the group's pairs visible; sample tile is free again
 
         // prefetch the next tile's samples while the mel phase runs
         ClipCursor nxt = cur;
         if (tile + 1 < t_end) {
             cursor_advance(p, nxt);
-            if (nxt.tile_in_clip * kTileFrames < nxt.frames) load_tile_samples(p, nxt, s_samples);
+            if (nxt.tile_in_clip * kTileFrames < nxt.frames) load_tile_samples(p, nxt, s_samples, gt);
         }
 
         // interior tile: every frame exists and none is a pad-to-4 source -> mel-major results go straight to global
-        // memory from the mel phase (8 lanes x 2 frames = 64 contiguous bytes per band); other tiles and the
+        // memory from the mel phase (4 lanes x 2 frames = 32 contiguous bytes per band); other tiles and the
         // time-major layout are staged in shared memory and stored by store_tile().
         const int pad = cur.frames_padded - cur.frames;
         const bool direct = !p.time_major && (f0 + kTileFrames - 1 <= cur.frames - 2 - pad);
@@ -539,18 +557,18 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
             const int fA = f0 + 2 * pr;
             OutT* out_clip = reinterpret_cast<OutT*>(p.out) + cur.out_base;
             for (int r = 0; r < kMaxRounds; ++r) {
-                const int slot = warp * kMaxRounds + r;
-                const int trip = s_nblk[slot];
+                const int slot = gw * kMaxRounds + r;
+                const int trip = s_trip[slot];
                 if (trip == 0) break;  // warp-uniform; rounds are filled in order
-                const int b = s_band[slot * 4 + q];
-                const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + (s_astart[slot * 4 + q] >> 1);   // two bins x (A, B)
+                const int b = s_band[slot * kSlots + q];
+                const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + (s_astart[slot * kSlots + q] >> 1);   // two bins x (A, B)
                 const float2* w2 = reinterpret_cast<const float2*>(s_pw + s_woff[slot]) + q;
                 float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
                 const int half_trip = ACB_ABLATE == 4 ? 0 : (trip >> 1);
 #pragma unroll 4
                 for (int i = 0; i < half_trip; ++i) {
                     const float4 pw = p4[i];
-                    const float2 w = w2[4 * i];
+                    const float2 w = w2[kSlots * i];
                     acc0 = fmaf(w.x, pw.x, acc0);
                     acc1 = fmaf(w.x, pw.y, acc1);
                     acc2 = fmaf(w.y, pw.z, acc2);
@@ -572,13 +590,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                         s += c * (double)vB;
                         s2 += c * (double)vB * (double)vB;
                     }
-                    // the 8 pair lanes of a slot are a contiguous, aligned lane group (all 32 lanes take part)
+                    // the 4 pair lanes of a slot are a contiguous, aligned lane group (all 32 lanes take part)
 #pragma unroll
-                    for (int o = 4; o >= 1; o >>= 1) {
+                    for (int o = 2; o >= 1; o >>= 1) {
                         s += __shfl_xor_sync(0xffffffffu, s, o);
                         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                     }
-                    if (pr == 0 && b >= 0) { s_mom[b] += s; s_mom[n_mels + b] += s2; }   // each band has exactly one owner slot
+                    if (pr == 0 && b >= 0) { s_mom[b] += s; s_mom[n_mels + b] += s2; }   // each band has exactly one owner slot per group
                 }
                 if (b >= 0) {
                     const float2 af = s_aff[b];
@@ -597,17 +615,17 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 }
             }
         }
-        if (!direct) {   // CTA-uniform
-            __syncthreads();  // output tile staged
-            if (write_out) store_tile<OutT>(p, cur, s_out, n_mels, S);
+        if (!direct) {   // group-uniform
+            group_sync(grp);  // output tile staged
+            if (write_out) store_tile<OutT>(p, cur, s_out, n_mels, S, gt);
         }
         cur = nxt;
     }
     cp_async_wait_all();
 
     if (kMoments) {
-        __syncthreads();
-        for (int i = tid; i < 2 * n_mels; i += kThreads) p.moments_partial[(size_t)blockIdx.x * 2 * n_mels + i] = s_mom[i];
+        group_sync(grp);
+        for (int i = gt; i < 2 * n_mels; i += kGroupThreads) p.moments_partial[(size_t)g_index * 2 * n_mels + i] = s_mom[i];
     }
 }
 
@@ -870,56 +888,81 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     }
     if ((int)weights.size() > kMaxWeights) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: filterbank too dense");
 
-    // mel plan: bands sorted by (even-aligned) run length, groups of 4 (one per lane slot), groups dealt to the 8
-    // warps longest-processing-time first.  Within a group every slot is zero-padded to the group's trip count, so the
-    // kernel's inner loop is predicate-free; runs start on an even bin so two bins are fetched with one 16-byte load.
-    std::vector<int> astart(n_mels), alen(n_mels);
+    // mel plan: bands sorted by (even-aligned) run length, groups of 8 (one per lane slot), groups dealt to the 4 warps of a
+    // group longest-processing-time first.  Within a round every slot is zero-padded to the round's trip count, so the kernel's
+    // inner loop is predicate-free; runs start on an even bin so two bins are fetched with one 16-byte load.  Slots (2j, 2j+1)
+    // share a quarter-warp: they get opposite parity of astart/2 (a run may start one bin pair early, on zero weights), which
+    // keeps the 16-byte power loads free of bank conflicts (see the kernel).
+    std::vector<int> alen(n_mels), aend(n_mels);
     for (int m = 0; m < n_mels; ++m) {
-        astart[m] = start[m] & ~1;
-        const int end = start[m] + len[m];
-        alen[m] = ((end + 1) & ~1) - astart[m];
-        if (len[m] == 0) { astart[m] = 0; alen[m] = 2; }
+        if (len[m] == 0) { start[m] = 0; len[m] = 0; }
+        aend[m] = (start[m] + std::max(len[m], 1) + 1) & ~1;
+        alen[m] = aend[m] - (start[m] & ~1);
     }
     std::vector<int> order(n_mels);
     std::iota(order.begin(), order.end(), 0);
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return alen[a] > alen[b]; });
-    const int n_groups = (n_mels + 3) / 4;
-    std::vector<short> plan_band(kWarps * kMaxRounds * 4, (short)-1), plan_astart(kWarps * kMaxRounds * 4, (short)0),
-        plan_trip(kWarps * kMaxRounds, (short)0);
-    std::vector<int> plan_woff(kWarps * kMaxRounds, 0);
+    const int n_rounds = (n_mels + kSlots - 1) / kSlots;
+    std::vector<short> plan_band(kGroupWarps * kMaxRounds * kSlots, (short)-1), plan_astart(kGroupWarps * kMaxRounds * kSlots, (short)0),
+        plan_trip(kGroupWarps * kMaxRounds, (short)0);
+    std::vector<int> plan_woff(kGroupWarps * kMaxRounds, 0);
     std::vector<float> plan_w;
-    std::vector<int> load(kWarps, 0), rounds(kWarps, 0);
-    for (int g = 0; g < n_groups; ++g) {
+    std::vector<int> load(kGroupWarps, 0), rounds(kGroupWarps, 0);
+    for (int g = 0; g < n_rounds; ++g) {
         int best = -1;
-        for (int w = 0; w < kWarps; ++w)
+        for (int w = 0; w < kGroupWarps; ++w)
             if (rounds[w] < kMaxRounds && (best < 0 || load[w] < load[best])) best = w;
         if (best < 0) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel plan overflow");
+        // order the round's bands so that neighbours (2j, 2j+1) have opposite parity of astart/2 where possible
+        std::vector<int> par[2];
+        for (int q = 0; q < kSlots && kSlots * g + q < n_mels; ++q) {
+            const int m = order[kSlots * g + q];
+            par[((start[m] & ~1) >> 1) & 1].push_back(m);
+        }
+        std::vector<int> slots;
+        while (!par[0].empty() && !par[1].empty()) {
+            slots.push_back(par[0].back()); par[0].pop_back();
+            slots.push_back(par[1].back()); par[1].pop_back();
+        }
+        for (int k = 0; k < 2; ++k)
+            for (int m : par[k]) slots.push_back(m);
+        std::vector<int> shift(slots.size(), 0), as(slots.size(), 0);
         int trip = 2;
-        for (int q = 0; q < 4; ++q)
-            if (4 * g + q < n_mels) trip = std::max(trip, alen[order[4 * g + q]]);
+        for (int iter = 0; iter < 8; ++iter) {
+            trip = 2;
+            for (size_t i = 0; i < slots.size(); ++i) trip = std::max(trip, aend[slots[i]] - ((start[slots[i]] & ~1) - shift[i]));
+            for (size_t i = 0; i < slots.size(); ++i) {
+                as[i] = (start[slots[i]] & ~1) - shift[i];
+                if (as[i] + trip > kBins) as[i] = std::max(0, (kBins - trip) & ~1);   // keep every 16-byte read inside the 512-bin power array
+            }
+            bool changed = false;
+            for (size_t i = 0; i + 1 < slots.size(); i += 2) {
+                if ((((as[i] >> 1) ^ (as[i + 1] >> 1)) & 1) != 0) continue;
+                const size_t x = (as[i + 1] >= 2 && (start[slots[i + 1]] & ~1) - shift[i + 1] == as[i + 1]) ? i + 1
+                                 : ((as[i] >= 2 && (start[slots[i]] & ~1) - shift[i] == as[i]) ? i : slots.size());
+                if (x < slots.size()) { shift[x] += 2; changed = true; }
+            }
+            if (!changed) break;
+        }
         const int slot = best * kMaxRounds + rounds[best];
         plan_trip[slot] = (short)trip;
         plan_woff[slot] = (int)plan_w.size();
-        plan_w.resize(plan_w.size() + (size_t)trip * 4, 0.f);
+        plan_w.resize(plan_w.size() + (size_t)trip * kSlots, 0.f);
         float* wbase = plan_w.data() + plan_woff[slot];
-        for (int q = 0; q < 4; ++q) {
-            if (4 * g + q >= n_mels) continue;
-            const int m = order[4 * g + q];
-            plan_band[slot * 4 + q] = (short)m;
-            // keep every 16-byte read of the slot inside the 512-bin power array
-            int as = astart[m];
-            if (as + trip > kBins) as = std::max(0, (kBins - trip) & ~1);
-            plan_astart[slot * 4 + q] = (short)as;
+        for (size_t q = 0; q < slots.size(); ++q) {
+            const int m = slots[q];
+            plan_band[slot * kSlots + q] = (short)m;
+            plan_astart[slot * kSlots + q] = (short)as[q];
             for (int i = 0; i < len[m]; ++i) {
-                const int rel = start[m] + i - as;                 // bin offset inside the slot's window
+                const int rel = start[m] + i - as[q];                 // bin offset inside the slot's window
                 if (rel < 0 || rel >= trip) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel plan window error");
-                wbase[(rel >> 1) * 8 + q * 2 + (rel & 1)] = weights[off[m] + i];
+                wbase[(rel >> 1) * (2 * kSlots) + q * 2 + (rel & 1)] = weights[off[m] + i];
             }
         }
         load[best] += trip + 16;  // + fixed per-round epilogue cost
         rounds[best]++;
     }
-    if ((int)plan_w.size() > kMaxWeights * 2) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel plan too large");
+    if ((int)plan_w.size() > kMaxWeights * 4) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel plan too large");
 
     // twiddles W^(n2*l) = exp(-2*pi*i*n2*l/1024) in double, rounded once; entry [h][l] holds n2 = 2h and 2h + 1
     std::vector<float4> tw(16 * 32);
@@ -1003,7 +1046,7 @@ int acb_frontend_destroy(acb_frontend* fe) {
 
 int64_t acb_moments_workspace_bytes(const acb_frontend* fe) {
     if (!fe) return fail(ACB_ERR_INVALID, "acb_moments_workspace_bytes: null handle");
-    return (int64_t)fe->grid * 2 * fe->n_mels * (int64_t)sizeof(double);
+    return (int64_t)fe->grid * kGroups * 2 * fe->n_mels * (int64_t)sizeof(double);
 }
 
 int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* stream) {
@@ -1066,7 +1109,7 @@ int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* s
         if (p.out_bf16) logmel_fused_kernel<true, __nv_bfloat16><<<grid, kThreads, fe->smem_bytes_moments, st>>>(p);
         else logmel_fused_kernel<true, float><<<grid, kThreads, fe->smem_bytes_moments, st>>>(p);
         const int n_vals = 2 * fe->n_mels;
-        moments_reduce_kernel<<<(n_vals + 127) / 128, 128, 0, st>>>(p.moments_partial, grid, n_vals, a->moments);
+        moments_reduce_kernel<<<(n_vals + 127) / 128, 128, 0, st>>>(p.moments_partial, grid * kGroups, n_vals, a->moments);
     } else {
         if (p.out_bf16) logmel_fused_kernel<false, __nv_bfloat16><<<grid, kThreads, fe->smem_bytes, st>>>(p);
         else logmel_fused_kernel<false, float><<<grid, kThreads, fe->smem_bytes, st>>>(p);
