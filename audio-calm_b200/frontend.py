@@ -140,8 +140,8 @@ class LogMelFrontend:
     def _fill_common(self, a: LogmelArgs, out: torch.Tensor, layout: str, pad_multiple: int, fill_tail: bool,
                      fill_value: float, affine: Affine, peak: Optional[torch.Tensor], moments) -> list:
         keep = []
-        a.out = out.data_ptr()
-        a.out_dtype = {torch.float32: ACB_F32, torch.bfloat16: ACB_BF16}[out.dtype]
+        a.out = None if out is None else out.data_ptr()      # None: statistics-only launch, nothing is stored
+        a.out_dtype = ACB_F32 if out is None else {torch.float32: ACB_F32, torch.bfloat16: ACB_BF16}[out.dtype]
         a.out_layout = {"mel_major": ACB_MEL_MAJOR, "time_major": ACB_TIME_MAJOR}[layout]
         a.pad_multiple = int(pad_multiple)
         a.fill_tail = int(bool(fill_tail))
@@ -167,15 +167,19 @@ class LogMelFrontend:
     def forward(self, wav: torch.Tensor, *, out_dtype: torch.dtype = torch.float32, layout: str = "mel_major",
                 pad_multiple: int = 1, frame_capacity: Optional[int] = None, fill_tail: bool = False,
                 fill_value: float = 0.0, affine: Affine = None, peak: Optional[torch.Tensor] = None,
-                moments=None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                moments=None, out: Optional[torch.Tensor] = None, stats_only: bool = False) -> Optional[torch.Tensor]:
         """``wav[B, L]`` fp32 (contiguous rows) -> ``[B, n_mels, cap]`` (``mel_major``) or ``[B, cap, n_mels]``
         (``time_major``) with ``cap = frame_capacity or padded frame count``.
 
         ``peak``: per-clip max|x| from :meth:`peak_abs` -> fused ``process_audio_chunk`` scaling.
         ``affine``: ``(mean, std)`` scalars or per-bin tensors -> fused ``(x - mean) / std``.
         ``moments``: a :class:`~audio_calm_b200.stats.MelStatsAccumulator` updated with the un-normalised values.
+        ``stats_only``: accumulate ``moments`` without storing any features (returns ``None``): the dataset statistics
+        pass straight from waveforms, without the round trip through feature files of compute_mel_stats.py:19-28.
         """
         self._check_wav(wav)
+        if stats_only and moments is None:
+            raise ValueError("stats_only needs a moments accumulator")
         if wav.dim() != 2:
             raise ValueError("forward expects [B, L]; use MelExtractor for arbitrary leading dimensions")
         B, L = int(wav.shape[0]), int(wav.shape[1])
@@ -187,7 +191,9 @@ class LogMelFrontend:
         if wav.stride(1) != 1:
             wav = wav.contiguous()
         shape = (B, self.n_mels, cap) if layout == "mel_major" else (B, cap, self.n_mels)
-        if out is None:
+        if stats_only:
+            out = None
+        elif out is None:
             out = torch.empty(shape, dtype=out_dtype, device=self.device)
         elif tuple(out.shape) != shape or not out.is_contiguous() or out.device != self.device:
             raise ValueError(f"out must be a contiguous {shape} tensor on {self.device}")
@@ -214,7 +220,7 @@ class LogMelFrontend:
     def forward_ragged(self, batch: RaggedBatch, *, out_dtype: torch.dtype = torch.float32, layout: str = "mel_major",
                        pad_multiple: int = 1, frame_capacity: Optional[int] = None, fill_value: float = 0.0,
                        affine: Affine = None, peak: Optional[torch.Tensor] = None, moments=None,
-                       out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                       out: Optional[torch.Tensor] = None, stats_only: bool = False) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
         """Packed variable-length clips -> padded ``[B, n_mels, Tmax]`` (or ``[B, Tmax, n_mels]``) plus
         ``frames[B]`` (int64, valid = reflect-padded frame count per clip).  Frames beyond a clip's own count
         are set to ``fill_value`` (the training collator's ``audio_pad_val = 0.0``, train/train_calm.py:181,213-215).
@@ -227,13 +233,17 @@ class LogMelFrontend:
         if B and cap < int(frames.max()):
             raise ValueError("frame_capacity smaller than the longest clip's padded frame count")
         shape = (B, self.n_mels, cap) if layout == "mel_major" else (B, cap, self.n_mels)
-        if out is None:
+        if stats_only:
+            if moments is None:
+                raise ValueError("stats_only needs a moments accumulator")
+            out = None
+        elif out is None:
             out = torch.empty(shape, dtype=out_dtype, device=self.device)
         frames_t = torch.from_numpy(frames).to(self.device, non_blocking=True)
         if B == 0:
             return out, frames_t
         tile_start = np.zeros(B + 1, dtype=np.int32)
-        n_tiles = int(self._lib.acb_plan_tiles(lens.ctypes.data, B, self.n_fft, self.hop, cap, tile_start.ctypes.data))
+        n_tiles = int(self._lib.acb_plan_tiles(lens.ctypes.data, B, self.n_fft, self.hop, 0 if stats_only else cap, tile_start.ctypes.data))
         if n_tiles < 0:
             _lib.check(n_tiles, "acb_plan_tiles")
         tile_start_t = torch.from_numpy(tile_start).to(self.device, non_blocking=True)
@@ -246,7 +256,7 @@ class LogMelFrontend:
         a.n_tiles = n_tiles
         a.out_clip_stride = self.n_mels * cap
         a.frame_capacity = cap
-        keep = self._fill_common(a, out, layout, pad_multiple, True, fill_value, affine, peak, moments)
+        keep = self._fill_common(a, out, layout, pad_multiple, not stats_only, fill_value, affine, peak, moments)
         _lib.check(self._lib.acb_logmel_forward(self._handle, ctypes.byref(a), _stream_ptr(self.device)), "acb_logmel_forward")
         self.launches += 2 if moments is not None else 1
         if moments is not None:

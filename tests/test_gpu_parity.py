@@ -264,6 +264,25 @@ def test_moments_of_a_ragged_batch(fe):
     assert np.max(np.abs(m[:80] - s) / fr) < 1e-5 and np.max(np.abs(m[80:] - s2) / fr) < 1e-4
 
 
+def test_statistics_only_launch_matches_the_feature_launch(fe):
+    """out = NULL: the same fused kernel accumulates the moments and stores nothing (uniform and ragged batches)."""
+    x = dev(np.stack([o.synth_clip(40000, 400 + i) for i in range(5)]))
+    a1, a2 = acb.MelStatsAccumulator(80, "cuda"), acb.MelStatsAccumulator(80, "cuda")
+    peak = fe.peak_abs(x)
+    fe.forward(x, peak=peak, pad_multiple=4, moments=a1)
+    assert fe.forward(x, peak=peak, pad_multiple=4, moments=a2, stats_only=True) is None
+    assert a1.frames == a2.frames == 5 * 160 and torch.equal(a1.moments, a2.moments)          # deterministic, bit-identical
+    clips = [o.synth_clip(n, 500 + i) for i, n in enumerate([513, 4097, 24001, 100001])]
+    batch = acb.pack_clips([torch.from_numpy(c) for c in clips], fe.device)
+    b1, b2 = acb.MelStatsAccumulator(80, "cuda"), acb.MelStatsAccumulator(80, "cuda")
+    fe.forward_ragged(batch, pad_multiple=4, moments=b1)
+    out, frames = fe.forward_ragged(batch, pad_multiple=4, moments=b2, stats_only=True)
+    assert out is None and b1.frames == b2.frames == int(frames.sum())
+    assert torch.allclose(b1.moments, b2.moments, rtol=1e-12, atol=1e-9)                      # tile partition differs (no tail tiles)
+    with pytest.raises(ValueError):
+        fe.forward(x, stats_only=True)
+
+
 def test_per_utterance_normalisation(golden):
     import ctypes
     lib = acb._lib.load()
