@@ -53,8 +53,9 @@ constexpr int kGroupThreads = kGroupWarps * 32;
 constexpr int kGroups = 2;                                   // independent groups per CTA
 constexpr int kThreads = kGroups * kGroupThreads;
 constexpr int kTileSamples = (kTileFrames + 3) * kHop;       // 2816 samples staged per tile
-constexpr int kRowStride = 34;                               // complex elements per scratch row: 8-byte column stores and 16-byte row loads are both conflict-free
-constexpr int kScratchFloats = 32 * kRowStride * 2 + 8;      // 2184 floats / warp; == 8 (mod 32): see the mel phase
+constexpr int kRowStride = 36;                               // floats per row of a transpose plane: 4-byte column stores and 16-byte row loads are both conflict-free
+constexpr int kPlaneFloats = 32 * kRowStride;                // the real and the imaginary parts are transposed in separate planes
+constexpr int kScratchFloats = 2 * kPlaneFloats + 8;         // 2312 floats / warp; == 8 (mod 32): see the mel phase
 constexpr int kSlots = 8;                                    // band slots per mel round: lanes = 8 slots x 4 frame pairs
 constexpr int kMaxMels = 128;
 constexpr int kMaxRounds = 4;                                // mel plan: rounds of (8 bands) per warp
@@ -130,40 +131,77 @@ __device__ __forceinline__ void bfly(float& ur, float& ui, float& vr, float& vi)
     }
 }
 
+// ---- packed fp32 (FFMA2 / FADD2 / FMUL2, new on sm_100): two butterflies per instruction ----
+// The 32 complex values of an FFT-32 are held as 16 pairs (x[i], x[i + 16]) in 64-bit registers, real and imaginary parts
+// in separate arrays.  Stages 1-4 of the radix-2 DIT network combine indices i and i + half with both below 16 or both above,
+// and the twin butterfly 16 places up uses the same twiddle: one packed butterfly does both.  Stage 5 pairs i with i + 16,
+// i.e. the two halves of one register pair, and runs as scalar code on the halves.
+__device__ __forceinline__ float2 bcast2(float a) { return make_float2(a, a); }
+
+template <int TW>
+__device__ __forceinline__ void bfly2(float2& ur, float2& ui, float2& vr, float2& vi) {
+    if (TW == 0) {            // W = 1
+        const float2 sr = __fadd2_rn(ur, vr), si = __fadd2_rn(ui, vi);
+        vr = __ffma2_rn(vr, bcast2(-1.f), ur);
+        vi = __ffma2_rn(vi, bcast2(-1.f), ui);
+        ur = sr; ui = si;
+    } else if (TW == 8) {     // W = -i : W v = (vi, -vr)
+        const float2 sr = __fadd2_rn(ur, vi), si = __ffma2_rn(vr, bcast2(-1.f), ui);
+        const float2 dr = __ffma2_rn(vi, bcast2(-1.f), ur), di = __fadd2_rn(ui, vr);
+        ur = sr; ui = si; vr = dr; vi = di;
+    } else {                  // generic: u +- W v, 8 packed FMAs for two butterflies
+        constexpr float wr = kCos32[TW];
+        constexpr float wi = -kSin32[TW];
+        const float2 sr = __ffma2_rn(vi, bcast2(-wi), __ffma2_rn(vr, bcast2(wr), ur));
+        const float2 si = __ffma2_rn(vr, bcast2(wi), __ffma2_rn(vi, bcast2(wr), ui));
+        const float2 dr = __ffma2_rn(vi, bcast2(wi), __ffma2_rn(vr, bcast2(-wr), ur));
+        const float2 di = __ffma2_rn(vr, bcast2(-wi), __ffma2_rn(vi, bcast2(-wr), ui));
+        ur = sr; ui = si; vr = dr; vi = di;
+    }
+}
+
 template <int S, int K, int J>
-struct BflyLoop {
-    // stage S (m = 2^S), group base K, index J within the half-group
-    static __device__ __forceinline__ void run(float (&xr)[32], float (&xi)[32]) {
+struct Bfly2Loop {
+    // packed stage S <= 4 (m = 2^S), group base K < 16, index J within the half-group
+    static __device__ __forceinline__ void run(float2 (&pr)[16], float2 (&pi)[16]) {
         constexpr int m = 1 << S, half = m >> 1;
-        bfly<J * (32 / m)>(xr[K + J], xi[K + J], xr[K + J + half], xi[K + J + half]);
+        bfly2<J * (32 / m)>(pr[K + J], pi[K + J], pr[K + J + half], pi[K + J + half]);
         if constexpr (J + 1 < half) {
-            BflyLoop<S, K, J + 1>::run(xr, xi);
-        } else if constexpr (K + m < 32) {
-            BflyLoop<S, K + m, 0>::run(xr, xi);
+            Bfly2Loop<S, K, J + 1>::run(pr, pi);
+        } else if constexpr (K + m < 16) {
+            Bfly2Loop<S, K + m, 0>::run(pr, pi);
         }
     }
 };
 
-// In-register complex FFT-32, decimation in time: input in bit-reversed order, output natural order.
-__device__ __forceinline__ void fft32_dit(float (&xr)[32], float (&xi)[32]) {
-    BflyLoop<1, 0, 0>::run(xr, xi);
-    BflyLoop<2, 0, 0>::run(xr, xi);
-#if ACB_ABLATE != 1
-    BflyLoop<3, 0, 0>::run(xr, xi);
-    BflyLoop<4, 0, 0>::run(xr, xi);
-#endif
-    BflyLoop<5, 0, 0>::run(xr, xi);
+template <int J>
+struct LastStageLoop {
+    // stage 5: butterfly (J, J + 16) = the two halves of pair J, twiddle W32^J, scalar code
+    static __device__ __forceinline__ void run(float2 (&pr)[16], float2 (&pi)[16]) {
+        bfly<J>(pr[J].x, pi[J].x, pr[J].y, pi[J].y);
+        if constexpr (J + 1 < 16) LastStageLoop<J + 1>::run(pr, pi);
+    }
+};
+
+// In-register complex FFT-32, decimation in time: input in bit-reversed order, output natural order
+// (element k < 16 is pr[k].x, element k >= 16 is pr[k - 16].y).
+__device__ __forceinline__ void fft32_packed(float2 (&pr)[16], float2 (&pi)[16]) {
+    Bfly2Loop<1, 0, 0>::run(pr, pi);
+    Bfly2Loop<2, 0, 0>::run(pr, pi);
+    Bfly2Loop<3, 0, 0>::run(pr, pi);
+    Bfly2Loop<4, 0, 0>::run(pr, pi);
+    LastStageLoop<0>::run(pr, pi);
 }
 
 // Same, when stage 1 (span-1 butterflies, twiddle 1) has already been applied by the caller.
-__device__ __forceinline__ void fft32_dit_from_stage2(float (&xr)[32], float (&xi)[32]) {
-    BflyLoop<2, 0, 0>::run(xr, xi);
-#if ACB_ABLATE != 1
-    BflyLoop<3, 0, 0>::run(xr, xi);
-    BflyLoop<4, 0, 0>::run(xr, xi);
-#endif
-    BflyLoop<5, 0, 0>::run(xr, xi);
+__device__ __forceinline__ void fft32_packed_from_stage2(float2 (&pr)[16], float2 (&pi)[16]) {
+    Bfly2Loop<2, 0, 0>::run(pr, pi);
+    Bfly2Loop<3, 0, 0>::run(pr, pi);
+    Bfly2Loop<4, 0, 0>::run(pr, pi);
+    LastStageLoop<0>::run(pr, pi);
 }
+
+__host__ __device__ constexpr int brev3(int x) { return ((x & 1) << 2) | (x & 2) | ((x & 4) >> 2); }
 
 // --------------------------------------------------------------------------------------------
 // fused log-mel kernel
@@ -171,7 +209,8 @@ __device__ __forceinline__ void fft32_dit_from_stage2(float (&xr)[32], float (&x
 struct LogmelParams {
     // tables (device)
     const float* window;       // [1024]
-    const float4* twiddle;     // [2][32]  (W^l, W^2l) and (W^3l, W^4l) per lane l, W = exp(-2*pi*i/1024): seeds of the twiddle chains
+    const float4* twiddle;     // [5][32]  seeds of the twiddle chains per lane l, W = exp(-2*pi*i/1024):
+                               //          [k][l] = (Re W^kl, Re W^(k+16)l, Im W^kl, Im W^(k+16)l), k = 0..3;  [4][l] = (Re, Im W^4l, 0, 0)
     // mel plan: per (group warp, round) eight band slots with a common even trip count; weights zero-padded to the trip
     // and interleaved as [i/2][slot][2] so that a lane fetches two consecutive weights with one 8-byte load
     const float* plan_w;       // [n_plan_w]
@@ -225,7 +264,7 @@ __host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w,
     int off = 0;  // in 4-byte words
     L.samples = off; off += kGroups * kTileSamples;
     L.scratch = off; off += kGroups * kGroupWarps * kScratchFloats;
-    L.twiddle = off; off += 2 * 32 * 4;
+    L.twiddle = off; off += 5 * 32 * 4;
     L.window = off; off += kNfft / 2;                             // first half only: w[n + N/2] = 1 - w[n]
     L.plan_w = off; off += (n_plan_w + 3) & ~3;
     L.affine = off; off += 2 * ((n_mels + 1) & ~1);
@@ -414,7 +453,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     double* s_mom = reinterpret_cast<double*>(smem + L.moments) + grp * 2 * n_mels;   // [2][n_mels] per group, only when kMoments
 
     // ---- one-time table staging (whole CTA) ----
-    for (int i = tid; i < 2 * 32; i += kThreads) s_tw4[i] = p.twiddle[i];
+    for (int i = tid; i < 5 * 32; i += kThreads) s_tw4[i] = p.twiddle[i];
     for (int i = tid; i < kNfft / 2; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < p.n_plan_w; i += kThreads) s_pw[i] = p.plan_w[i];
     for (int i = tid; i < kGroupWarps * kMaxRounds; i += kThreads) { s_woff[i] = p.plan_woff[i]; s_trip[i] = p.plan_trip[i]; }
@@ -459,86 +498,92 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
 
         // ================= phase 1: one frame pair per warp =================
         if (has_frames && f0 + 2 * gw < cur.frames && ACB_ABLATE != 7) {
-            float xr[32], xi[32];
+            float2 pr[16], pi[16];   // element k < 16 in .x, element k + 16 in .y (see fft32_packed)
             {
-                // Hann window folded into the first radix-2 stage: positions (2j, 2j+1) of the bit-reversed order hold
-                // samples n1 and n1 + 16, so  x[2j] = a*wa + b*wb ,  x[2j+1] = a*wa - b*wb  (3 ops instead of 4).
+                // Hann window folded into the first radix-2 stage: positions (2j, 2j+1) of the bit-reversed order hold samples
+                // n1 and n1 + 16 (x[2j] = a*wa + b*wb, x[2j+1] = a*wa - b*wb); positions 16 higher hold samples n1 + 1, so a
+                // register pair is two adjacent sample rows.  Frame A is the real part, frame B (one hop later) the imaginary.
                 const float* sp = s_samples + (2 * gw) * kHop + lane;
-                float v[40];
+                float2 v[20];
 #pragma unroll
-#if ACB_ABLATE == 6
-                for (int r = 0; r < 40; ++r) v[r] = (float)(lane + r);
-#else
-                for (int r = 0; r < 40; ++r) v[r] = sp[32 * r];
-#endif
+                for (int r = 0; r < 20; ++r) v[r] = make_float2(sp[32 * (2 * r)], sp[32 * (2 * r + 1)]);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n1 = brev5(2 * j);          // < 16
-                    const float wa = s_win[32 * n1 + lane];
-                    const float wb = 1.f - wa;   // periodic Hann: w[n + N/2] = 1 - w[n] (only the first half of the window is staged)
-                    const float ar = v[n1] * wa, ai = v[n1 + 8] * wa;           // frame A (re) and frame B (im): B = A + one hop
-                    xr[2 * j] = fmaf(v[n1 + 16], wb, ar);
-                    xr[2 * j + 1] = fmaf(-v[n1 + 16], wb, ar);
-                    xi[2 * j] = fmaf(v[n1 + 24], wb, ai);
-                    xi[2 * j + 1] = fmaf(-v[n1 + 24], wb, ai);
+                for (int j = 0; j < 8; ++j) {
+                    const int t = brev5(2 * j) >> 1;      // sample rows n1 = 2t, 2t + 1 (n1 < 16)
+                    const float2 wa = make_float2(s_win[32 * (2 * t) + lane], s_win[32 * (2 * t + 1) + lane]);
+                    const float2 wb = __ffma2_rn(wa, bcast2(-1.f), bcast2(1.f));   // periodic Hann: w[n + N/2] = 1 - w[n]
+                    const float2 ar = __fmul2_rn(v[t], wa), br = __fmul2_rn(v[t + 8], wb);
+                    const float2 ai = __fmul2_rn(v[t + 4], wa), bi = __fmul2_rn(v[t + 12], wb);
+                    pr[2 * j] = __fadd2_rn(ar, br);
+                    pr[2 * j + 1] = __ffma2_rn(br, bcast2(-1.f), ar);
+                    pi[2 * j] = __fadd2_rn(ai, bi);
+                    pi[2 * j + 1] = __ffma2_rn(bi, bcast2(-1.f), ai);
                 }
             }
-            fft32_dit_from_stage2(xr, xi);  // over n1 -> k1 (natural order)
-#if ACB_ABLATE != 3
-            // twiddle W_1024^(k1*lane), then transposed store scr[k1][lane].  The 31 twiddles of a lane are powers of W^lane:
-            // four chains t[k+4] = t[k] * W^(4*lane) seeded with the exact W^lane .. W^(4*lane) (7 steps deep, ~4e-7 relative)
-            // cost 4 FMA-pipe instructions per twiddle instead of an 8-byte shared-memory load each.
+            fft32_packed_from_stage2(pr, pi);  // over n1 -> k1 (natural order)
+            // twiddle W_1024^(k1*lane), then transposed store plane[k1][lane].  The twiddles of a lane are powers of W^lane, kept
+            // as pairs T[k] = (W^(k*lane), W^((k+16)*lane)): four chains T[k+4] = T[k] * W^(4*lane) seeded with exact values
+            // (3 steps deep) cost packed FMA-pipe instructions instead of an 8-byte shared-memory load per twiddle.
             {
-#if ACB_ABLATE == 2
+                float* pre = scr + lane;
+                float* pim = scr + kPlaneFloats + lane;
+                float2 tr[4], ti[4];
 #pragma unroll
-                for (int k1 = 0; k1 < 32; ++k1) scr2[k1 * kRowStride + lane] = make_float2(xr[k1], xi[k1]);
-#else
-                const float4 s01 = s_tw4[lane], s23 = s_tw4[32 + lane];
-                float cr[4] = {s23.z, s01.x, s01.z, s23.x};   // chain k & 3 -> t for k = 4, 1, 2, 3
-                float ci[4] = {s23.w, s01.y, s01.w, s23.y};
-                const float wr = s23.z, wi = s23.w;            // W^(4*lane)
-                scr2[lane] = make_float2(xr[0], xi[0]);        // W^0 = 1
+                for (int c = 0; c < 4; ++c) {
+                    const float4 sd = s_tw4[c * 32 + lane];
+                    tr[c] = make_float2(sd.x, sd.y);
+                    ti[c] = make_float2(sd.z, sd.w);
+                }
+                const float4 w4 = s_tw4[4 * 32 + lane];
+                const float2 w4r = bcast2(w4.x), w4i = bcast2(w4.y), nw4i = bcast2(-w4.y);
 #pragma unroll
-                for (int k1 = 1; k1 < 32; ++k1) {
-                    const int c = k1 & 3;
-                    const float tr = cr[c], ti = ci[c];
-                    scr2[k1 * kRowStride + lane] = make_float2(fmaf(xr[k1], tr, -xi[k1] * ti), fmaf(xr[k1], ti, xi[k1] * tr));
-                    if (k1 + 4 < 32) {
-                        cr[c] = fmaf(tr, wr, -ti * wi);
-                        ci[c] = fmaf(tr, wi, ti * wr);
+                for (int k = 0; k < 16; ++k) {
+                    const int c = k & 3;
+                    const float2 nxi = __fmul2_rn(pi[k], bcast2(-1.f));
+                    const float2 yr = __ffma2_rn(nxi, ti[c], __fmul2_rn(pr[k], tr[c]));
+                    const float2 yi = __ffma2_rn(pr[k], ti[c], __fmul2_rn(pi[k], tr[c]));
+                    pre[k * kRowStride] = yr.x;
+                    pre[(k + 16) * kRowStride] = yr.y;
+                    pim[k * kRowStride] = yi.x;
+                    pim[(k + 16) * kRowStride] = yi.y;
+                    if (k + 4 < 16) {
+                        const float2 nr = __ffma2_rn(ti[c], nw4i, __fmul2_rn(tr[c], w4r));
+                        ti[c] = __ffma2_rn(tr[c], w4i, __fmul2_rn(ti[c], w4r));
+                        tr[c] = nr;
                     }
                 }
-#endif
             }
             __syncwarp();
-            // lane j = k1 now owns row j: the 32 values over n2, read 16 bytes (two values) at a time
+            // lane j = k1 now owns row j: the 32 values over n2, four per 16-byte load.  Values n2 = 4h, 4h+1 go to bit-reversed
+            // positions brev3(h) and brev3(h) + 16 -- one register pair -- and n2 = 4h+2, 4h+3 to the pair 8 places up.
             {
-                const float4* row4 = reinterpret_cast<const float4*>(scr2 + lane * kRowStride);
+                const float4* re4 = reinterpret_cast<const float4*>(scr + lane * kRowStride);
+                const float4* im4 = reinterpret_cast<const float4*>(scr + kPlaneFloats + lane * kRowStride);
 #pragma unroll
-                for (int h = 0; h < 16; ++h) {
-                    const float4 z = row4[h];
-                    xr[brev5(2 * h)] = z.x; xi[brev5(2 * h)] = z.y;
-                    xr[brev5(2 * h + 1)] = z.z; xi[brev5(2 * h + 1)] = z.w;
+                for (int h = 0; h < 8; ++h) {
+                    const float4 zr = re4[h], zi = im4[h];
+                    pr[brev3(h)] = make_float2(zr.x, zr.y);
+                    pr[brev3(h) + 8] = make_float2(zr.z, zr.w);
+                    pi[brev3(h)] = make_float2(zi.x, zi.y);
+                    pi[brev3(h) + 8] = make_float2(zi.z, zi.w);
                 }
             }
             __syncwarp();
-#endif
-            fft32_dit(xr, xi);  // over n2 -> k2 ; lane j holds Z[j + 32*k2]
+            fft32_packed(pr, pi);  // over n2 -> k2 ; lane j holds Z[j + 32*k2]
             // separate the two real spectra and take |X|^2 (x4; the 1/4 is folded into the weights):
             //   Z[k] = a+ib, Z[1024-k] = c+id  =>  4|XA|^2 = (a+c)^2+(b-d)^2 , 4|XB|^2 = (a-c)^2+(b+d)^2
-            // Z[1024-k] for k = j + 32m lives in lane (32-j)&31, register 31-m (register 32-m when j == 0).
+            // Z[1024-k] for k = j + 32m lives in lane (32-j)&31, element 31-m (element 32-m when j == 0).
             const int src_lane = (32 - lane) & 31;
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
-                const float offer_r = (lane == 0) ? xr[(32 - m) & 31] : xr[31 - m];
-                const float offer_i = (lane == 0) ? xi[(32 - m) & 31] : xi[31 - m];
-#if ACB_ABLATE == 5
-                const float c = offer_r, d = offer_i;
-#else
+                // elements 31-m and (32-m)&31: 31-m >= 16 is the high half of pair 15-m; (32-m)&31 is element 0 for m == 0
+                const float alt_r = (m == 0) ? pr[0].x : pr[16 - m].y;
+                const float alt_i = (m == 0) ? pi[0].x : pi[16 - m].y;
+                const float offer_r = (lane == 0) ? alt_r : pr[15 - m].y;
+                const float offer_i = (lane == 0) ? alt_i : pi[15 - m].y;
                 const float c = __shfl_sync(0xffffffffu, offer_r, src_lane);
                 const float d = __shfl_sync(0xffffffffu, offer_i, src_lane);
-#endif
-                const float a = xr[m], b = xi[m];
+                const float a = pr[m].x, b = pi[m].x;
                 const float apc = a + c, bmd = b - d, amc = a - c, bpd = b + d;
                 const float pa = fmaf(apc, apc, bmd * bmd);
                 const float pb = fmaf(amc, amc, bpd * bpd);
@@ -972,13 +1017,13 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     }
     if ((int)plan_w.size() > kMaxWeights * 4) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: mel plan too large");
 
-    // seeds of the in-register twiddle chains: W^(m*l) = exp(-2*pi*i*m*l/1024), m = 1..4, in double, rounded once
-    std::vector<float4> tw(2 * 32);
+    // seeds of the in-register twiddle chains: W^(m*l) = exp(-2*pi*i*m*l/1024) in double, rounded once
+    std::vector<float4> tw(5 * 32);
     for (int l = 0; l < 32; ++l) {
-        double c[5], sn[5];
-        for (int m = 1; m <= 4; ++m) { const double a = -2.0 * M_PI * (double)(m * l) / 1024.0; c[m] = cos(a); sn[m] = sin(a); }
-        tw[l] = make_float4((float)c[1], (float)sn[1], (float)c[2], (float)sn[2]);
-        tw[32 + l] = make_float4((float)c[3], (float)sn[3], (float)c[4], (float)sn[4]);
+        auto wre = [&](int m) { return (float)cos(-2.0 * M_PI * (double)(m * l) / 1024.0); };
+        auto wim = [&](int m) { return (float)sin(-2.0 * M_PI * (double)(m * l) / 1024.0); };
+        for (int k = 0; k < 4; ++k) tw[k * 32 + l] = make_float4(wre(k), wre(k + 16), wim(k), wim(k + 16));
+        tw[4 * 32 + l] = make_float4(wre(4), wim(4), 0.f, 0.f);
     }
 
     int prev = 0;
@@ -992,13 +1037,13 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     // pack the blob
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
-    const size_t o_win = take(sizeof(float) * kNfft), o_tw = take(sizeof(float4) * 64),
+    const size_t o_win = take(sizeof(float) * kNfft), o_tw = take(sizeof(float4) * 160),
                  o_pw = take(sizeof(float) * std::max<size_t>(plan_w.size(), 1)), o_po = take(sizeof(int) * plan_woff.size()),
                  o_pt = take(sizeof(short) * plan_trip.size()), o_pb = take(sizeof(short) * plan_band.size()),
                  o_pa = take(sizeof(short) * plan_astart.size());
     std::vector<unsigned char> host(o, 0);
     memcpy(host.data() + o_win, window_host, sizeof(float) * kNfft);
-    memcpy(host.data() + o_tw, tw.data(), sizeof(float4) * 64);
+    memcpy(host.data() + o_tw, tw.data(), sizeof(float4) * 160);
     if (!plan_w.empty()) memcpy(host.data() + o_pw, plan_w.data(), sizeof(float) * plan_w.size());
     memcpy(host.data() + o_po, plan_woff.data(), sizeof(int) * plan_woff.size());
     memcpy(host.data() + o_pt, plan_trip.data(), sizeof(short) * plan_trip.size());
