@@ -137,26 +137,27 @@ __device__ __forceinline__ void bfly(float& ur, float& ui, float& vr, float& vi)
 // and the twin butterfly 16 places up uses the same twiddle: one packed butterfly does both.  Stage 5 pairs i with i + 16,
 // i.e. the two halves of one register pair, and runs as scalar code on the halves.
 __device__ __forceinline__ float2 bcast2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }   // folds into the consumer's operand modifier
 
 template <int TW>
 __device__ __forceinline__ void bfly2(float2& ur, float2& ui, float2& vr, float2& vi) {
     if (TW == 0) {            // W = 1
         const float2 sr = __fadd2_rn(ur, vr), si = __fadd2_rn(ui, vi);
-        vr = __ffma2_rn(vr, bcast2(-1.f), ur);
-        vi = __ffma2_rn(vi, bcast2(-1.f), ui);
+        vr = __fadd2_rn(ur, neg2(vr));
+        vi = __fadd2_rn(ui, neg2(vi));
         ur = sr; ui = si;
     } else if (TW == 8) {     // W = -i : W v = (vi, -vr)
-        const float2 sr = __fadd2_rn(ur, vi), si = __ffma2_rn(vr, bcast2(-1.f), ui);
-        const float2 dr = __ffma2_rn(vi, bcast2(-1.f), ur), di = __fadd2_rn(ui, vr);
+        const float2 sr = __fadd2_rn(ur, vi), si = __fadd2_rn(ui, neg2(vr));
+        const float2 dr = __fadd2_rn(ur, neg2(vi)), di = __fadd2_rn(ui, vr);
         ur = sr; ui = si; vr = dr; vi = di;
-    } else {                  // generic: u +- W v, 8 packed FMAs for two butterflies
+    } else {                  // generic: s = u + W v by 4 packed FMAs, d = 2u - s by 2 more (6 for two butterflies)
         constexpr float wr = kCos32[TW];
         constexpr float wi = -kSin32[TW];
         const float2 sr = __ffma2_rn(vi, bcast2(-wi), __ffma2_rn(vr, bcast2(wr), ur));
         const float2 si = __ffma2_rn(vr, bcast2(wi), __ffma2_rn(vi, bcast2(wr), ui));
-        const float2 dr = __ffma2_rn(vi, bcast2(wi), __ffma2_rn(vr, bcast2(-wr), ur));
-        const float2 di = __ffma2_rn(vr, bcast2(-wi), __ffma2_rn(vi, bcast2(-wr), ui));
-        ur = sr; ui = si; vr = dr; vi = di;
+        vr = __ffma2_rn(ur, bcast2(2.f), neg2(sr));
+        vi = __ffma2_rn(ui, bcast2(2.f), neg2(si));
+        ur = sr; ui = si;
     }
 }
 
@@ -511,13 +512,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 for (int j = 0; j < 8; ++j) {
                     const int t = brev5(2 * j) >> 1;      // sample rows n1 = 2t, 2t + 1 (n1 < 16)
                     const float2 wa = make_float2(s_win[32 * (2 * t) + lane], s_win[32 * (2 * t + 1) + lane]);
-                    const float2 wb = __ffma2_rn(wa, bcast2(-1.f), bcast2(1.f));   // periodic Hann: w[n + N/2] = 1 - w[n]
+                    const float2 wb = __fadd2_rn(bcast2(1.f), neg2(wa));   // periodic Hann: w[n + N/2] = 1 - w[n]
                     const float2 ar = __fmul2_rn(v[t], wa), br = __fmul2_rn(v[t + 8], wb);
                     const float2 ai = __fmul2_rn(v[t + 4], wa), bi = __fmul2_rn(v[t + 12], wb);
                     pr[2 * j] = __fadd2_rn(ar, br);
-                    pr[2 * j + 1] = __ffma2_rn(br, bcast2(-1.f), ar);
+                    pr[2 * j + 1] = __fadd2_rn(ar, neg2(br));
                     pi[2 * j] = __fadd2_rn(ai, bi);
-                    pi[2 * j + 1] = __ffma2_rn(bi, bcast2(-1.f), ai);
+                    pi[2 * j + 1] = __fadd2_rn(ai, neg2(bi));
                 }
             }
             fft32_packed_from_stage2(pr, pi);  // over n1 -> k1 (natural order)
@@ -535,19 +536,18 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                     ti[c] = make_float2(sd.z, sd.w);
                 }
                 const float4 w4 = s_tw4[4 * 32 + lane];
-                const float2 w4r = bcast2(w4.x), w4i = bcast2(w4.y), nw4i = bcast2(-w4.y);
+                const float2 w4r = bcast2(w4.x), w4i = bcast2(w4.y);
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     const int c = k & 3;
-                    const float2 nxi = __fmul2_rn(pi[k], bcast2(-1.f));
-                    const float2 yr = __ffma2_rn(nxi, ti[c], __fmul2_rn(pr[k], tr[c]));
+                    const float2 yr = __ffma2_rn(neg2(pi[k]), ti[c], __fmul2_rn(pr[k], tr[c]));
                     const float2 yi = __ffma2_rn(pr[k], ti[c], __fmul2_rn(pi[k], tr[c]));
                     pre[k * kRowStride] = yr.x;
                     pre[(k + 16) * kRowStride] = yr.y;
                     pim[k * kRowStride] = yi.x;
                     pim[(k + 16) * kRowStride] = yi.y;
                     if (k + 4 < 16) {
-                        const float2 nr = __ffma2_rn(ti[c], nw4i, __fmul2_rn(tr[c], w4r));
+                        const float2 nr = __ffma2_rn(neg2(ti[c]), w4i, __fmul2_rn(tr[c], w4r));
                         ti[c] = __ffma2_rn(tr[c], w4i, __fmul2_rn(ti[c], w4r));
                         tr[c] = nr;
                     }
@@ -1131,8 +1131,16 @@ int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* s
     p.clip_stride = a->clip_stride; p.uniform_length = a->uniform_length;
     p.tile_start = a->tile_start; p.n_clips = a->n_clips; p.n_tiles = a->n_tiles;
     p.uniform_tiles_per_clip = 1;
-    if (!a->tile_start) {
-        if (a->clip_length) return fail(ACB_ERR_INVALID, "acb_logmel_forward: ragged clips need tile_start (acb_plan_tiles)");
+    if (!a->tile_start && a->clip_length) {
+        // ragged clips without a tile plan: allowed for padded outputs (fill_tail), where every clip covers the whole row of
+        // frame_capacity frames and the tile count per clip is uniform.  The caller vouches that no clip is shorter than
+        // n_fft/2 + 1 samples and that every padded frame count fits frame_capacity (frontend.py checks both on the host).
+        if (!a->fill_tail || a->frame_capacity_per_clip)
+            return fail(ACB_ERR_INVALID, "acb_logmel_forward: ragged clips need tile_start (acb_plan_tiles) unless fill_tail pads every clip to frame_capacity");
+        p.uniform_tiles_per_clip = (int)((a->frame_capacity + kTileFrames - 1) / kTileFrames);
+        if ((int64_t)p.uniform_tiles_per_clip * a->n_clips != a->n_tiles)
+            return fail(ACB_ERR_INVALID, "acb_logmel_forward: n_tiles does not match n_clips * tiles per clip");
+    } else if (!a->tile_start) {
         const int64_t T = acb_frames_for_length(a->uniform_length, fe->n_fft, fe->hop);
         if (T < 0) return fail(ACB_ERR_INVALID, "acb_logmel_forward: clips of " + std::to_string(a->uniform_length) +
                                                     " samples are too short for reflect padding of " + std::to_string(fe->n_fft / 2));

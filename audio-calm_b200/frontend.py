@@ -228,7 +228,10 @@ class LogMelFrontend:
         self._check_wav(batch.wav)
         lens = np.ascontiguousarray(batch.lengths_host, dtype=np.int64)
         B = int(lens.shape[0])
-        frames = np.array([padded_frames(self.frames_for_length(int(n)), pad_multiple) for n in lens], dtype=np.int64)
+        if B and int(lens.min()) <= self.n_fft // 2:
+            self.frames_for_length(int(lens.min()))          # raises like the reference's reflect padding
+        frames = 1 + lens // self.hop
+        frames = (frames + pad_multiple - 1) // pad_multiple * pad_multiple
         cap = int(frame_capacity) if frame_capacity is not None else (int(frames.max()) if B else 0)
         if B and cap < int(frames.max()):
             raise ValueError("frame_capacity smaller than the longest clip's padded frame count")
@@ -242,16 +245,22 @@ class LogMelFrontend:
         frames_t = torch.from_numpy(frames).to(self.device, non_blocking=True)
         if B == 0:
             return out, frames_t
-        tile_start = np.zeros(B + 1, dtype=np.int32)
-        n_tiles = int(self._lib.acb_plan_tiles(lens.ctypes.data, B, self.n_fft, self.hop, 0 if stats_only else cap, tile_start.ctypes.data))
-        if n_tiles < 0:
-            _lib.check(n_tiles, "acb_plan_tiles")
-        tile_start_t = torch.from_numpy(tile_start).to(self.device, non_blocking=True)
         a = LogmelArgs()
         a.wav = batch.wav.data_ptr()
         a.clip_offset = batch.offsets.data_ptr()
         a.clip_length = batch.lengths.data_ptr()
-        a.tile_start = tile_start_t.data_ptr()
+        tile_start_t = None
+        if stats_only:
+            # only the frames that exist are visited: per-clip tile counts differ -> host plan (prefix sums) shipped to the device
+            tile_start = np.zeros(B + 1, dtype=np.int32)
+            n_tiles = int(self._lib.acb_plan_tiles(lens.ctypes.data, B, self.n_fft, self.hop, 0, tile_start.ctypes.data))
+            if n_tiles < 0:
+                _lib.check(n_tiles, "acb_plan_tiles")
+            tile_start_t = torch.from_numpy(tile_start).to(self.device, non_blocking=True)
+            a.tile_start = tile_start_t.data_ptr()
+        else:
+            # padded output: every clip covers its whole row, so the tile count per clip is uniform and no plan is needed
+            n_tiles = B * ((cap + self.frames_per_tile - 1) // self.frames_per_tile)
         a.n_clips = B
         a.n_tiles = n_tiles
         a.out_clip_stride = self.n_mels * cap

@@ -81,7 +81,8 @@ typedef struct acb_logmel_args {
     const int64_t* clip_length;  /* device [n_clips]: samples in clip i;            NULL => uniform_length */
     int64_t clip_stride;         /* used when clip_offset is NULL */
     int64_t uniform_length;      /* used when clip_length is NULL */
-    const int32_t* tile_start;   /* device [n_clips + 1] from acb_plan_tiles;        NULL => uniform clips */
+    const int32_t* tile_start;   /* device [n_clips + 1] from acb_plan_tiles;        NULL => uniform clips, or ragged clips
+                                  * with fill_tail (every clip then covers ceil(frame_capacity / tile) tiles) */
     int32_t n_clips;
     int32_t n_tiles;             /* total tiles (last entry of tile_start) */
     /* ---- optional fused peak normalisation (preprocess/core.py:108-110) ---- */
