@@ -242,6 +242,8 @@ class LogMelFrontend:
             out = None
         elif out is None:
             out = torch.empty(shape, dtype=out_dtype, device=self.device)
+        elif tuple(out.shape) != shape or not out.is_contiguous() or out.device != self.device:
+            raise ValueError(f"out must be a contiguous {shape} tensor on {self.device}")
         frames_t = torch.from_numpy(frames).to(self.device, non_blocking=True)
         if B == 0:
             return out, frames_t

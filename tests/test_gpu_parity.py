@@ -283,6 +283,46 @@ def test_statistics_only_launch_matches_the_feature_launch(fe):
         fe.forward(x, stats_only=True)
 
 
+@pytest.mark.parametrize("layout", ["mel_major", "time_major"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_no_write_outside_the_output(fe, layout, dtype):
+    """Guard bands around every output (compute-sanitizer is closed on this pool): nothing outside [B, 80, cap] is touched,
+    for uniform and ragged launches, odd frame counts, pad-to-4, tail fill and both layouts."""
+    guard = 4096
+    sentinel = 12345.0
+
+    def guarded(shape):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * guard,), sentinel, dtype=dtype, device="cuda")
+        return buf, buf[guard:guard + n].view(*shape)
+
+    def intact(buf, n):
+        return bool((buf[:guard] == sentinel).all()) and bool((buf[guard + n:] == sentinel).all())
+
+    for L, B, pad, cap in ((513, 3, 1, None), (1279, 2, 4, None), (4097, 5, 4, 24), (16000, 2, 1, 70), (40001, 3, 4, None)):
+        x = dev(np.stack([o.synth_clip(L, 600 + i) for i in range(B)]))
+        T4 = acb.padded_frames(1 + L // 256, pad)
+        c = cap or T4
+        shape = (B, 80, c) if layout == "mel_major" else (B, c, 80)
+        buf, out = guarded(shape)
+        fe.forward(x, layout=layout, pad_multiple=pad, frame_capacity=c, fill_tail=cap is not None, fill_value=0.0, out=out)
+        torch.cuda.synchronize()
+        assert intact(buf, out.numel()), (L, B, pad, cap)
+        if cap is not None:
+            tail = out[:, :, T4:] if layout == "mel_major" else out[:, T4:, :]
+            assert bool((tail == 0).all())
+    clips = [o.synth_clip(n, 700 + i) for i, n in enumerate([513, 777, 4097, 24001, 9000])]
+    batch = acb.pack_clips([torch.from_numpy(c) for c in clips], fe.device)
+    for pad in (1, 4):
+        cap = acb.padded_frames(1 + 24001 // 256, pad) + 3
+        shape = (5, 80, cap) if layout == "mel_major" else (5, cap, 80)
+        buf, out = guarded(shape)
+        fe.forward_ragged(batch, layout=layout, out_dtype=dtype, pad_multiple=pad, frame_capacity=cap, out=out)
+        torch.cuda.synchronize()
+        assert intact(buf, out.numel()), ("ragged", pad)
+        assert not bool((out == sentinel).any())                      # every element of the padded batch was written
+
+
 def test_per_utterance_normalisation(golden):
     import ctypes
     lib = acb._lib.load()
