@@ -10,13 +10,15 @@ directory as that package.  Layout:
     frontend.py              LogMelFrontend: batched + ragged launches, fused peak-norm / affine / moments
     stats.py                 per-bin moments, single all-reduce, finalise like compute_mel_stats.py
     sharding.py              utterance sharding across ranks (length-balanced)
+    collate.py               training-feed collation on the device (crop / zero-pad to 256 frames; ragged pad + transpose)
     preprocess/              drop-in mirrors of the reference's preprocess/{core,compute_mel_stats,process_dataset}.py
 """
 from . import _lib, tables  # noqa: F401
 from .frontend import (LogMelFrontend, MEL_MEAN_DEFAULT, MEL_STD_DEFAULT, RaggedBatch, frames_for_length,  # noqa: F401
                        pack_clips, padded_frames)
 from .stats import MelStats, MelStatsAccumulator, finalize_moments  # noqa: F401
-from . import frontend, stats, sharding  # noqa: F401
+from . import collate, frontend, stats, sharding  # noqa: F401
+from .collate import crop_collate, pad_collate, pad_collate_packed  # noqa: F401
 
 __all__ = ["LogMelFrontend", "MelStatsAccumulator", "MelStats", "RaggedBatch", "pack_clips", "frames_for_length",
            "padded_frames", "finalize_moments", "MEL_MEAN_DEFAULT", "MEL_STD_DEFAULT"]

@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "acb_abi_version", "acb_last_error", "acb_frames_per_tile", "acb_frames_for_length", "acb_padded_frames",
     "acb_plan_tiles", "acb_frontend_create", "acb_frontend_destroy", "acb_moments_workspace_bytes",
     "acb_logmel_forward", "acb_peak_abs", "acb_process_audio_chunk", "acb_moments_accumulate",
-    "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host",
+    "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host", "acb_crop_pad", "acb_pad_transpose",
 ]
 
 
@@ -152,6 +152,10 @@ def load() -> ctypes.CDLL:
         lib.acb_moments_finalize.argtypes = [vp, i32, i64, f64, vp, vp, vp, vp]
         lib.acb_normalize_per_utterance.restype = ctypes.c_int
         lib.acb_normalize_per_utterance.argtypes = [vp, vp, i32, i32, i64, vp, f32, vp]
+        lib.acb_crop_pad.restype = ctypes.c_int
+        lib.acb_crop_pad.argtypes = [vp, i32, i32, i32, i64, i64, vp, vp, vp, i64, f32, vp]
+        lib.acb_pad_transpose.restype = ctypes.c_int
+        lib.acb_pad_transpose.argtypes = [vp, i32, vp, vp, i32, i32, vp, i64, f32, vp, vp, vp]
         lib.acb_logmel_forward_host.restype = ctypes.c_int
         lib.acb_logmel_forward_host.argtypes = [vp, vp, i32, i64, vp, ctypes.POINTER(LogmelArgs), vp, vp, i32, vp]
         if lib.acb_abi_version() != 1:

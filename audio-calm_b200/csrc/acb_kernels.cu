@@ -842,6 +842,69 @@ __global__ void __launch_bounds__(128) normalize_rows_kernel(const float* __rest
     for (long long i = threadIdx.x; i < T; i += blockDim.x) dst[i] = __fdiv_rn(src[i] - mean, sd);
 }
 
+// --------------------------------------------------------------------------------------------
+// training-feed collation of stored features (train/train_vae.py:83-116, train/train_calm.py:205-215)
+// --------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// out[b][d][t] = feat[b][d][start[b] + t] while start[b] + t < frames[b], else pad: the crop / zero-pad of MelDataset.__getitem__
+// followed by the stack of data_collator.  One CTA per (clip, band) row; reads and writes are contiguous along t.
+template <typename T>
+__global__ void __launch_bounds__(256) crop_pad_kernel(const T* __restrict__ feat, int n_mels, long long cap, long long clip_stride,
+                                                       const long long* __restrict__ frames, const long long* __restrict__ start,
+                                                       T* __restrict__ out, long long out_frames, float pad_value) {
+    const int clip = blockIdx.x / n_mels, b = blockIdx.x - clip * n_mels;
+    const long long n = frames ? frames[clip] : cap;
+    const long long s0 = start ? start[clip] : 0;
+    const T* src = feat + (long long)clip * clip_stride + (long long)b * cap;
+    T* dst = out + ((long long)clip * n_mels + b) * out_frames;
+    const T padv = from_float<T>(pad_value);
+    for (long long t = threadIdx.x; t < out_frames; t += blockDim.x) {
+        const long long f = s0 + t;
+        dst[t] = (f >= 0 && f < n) ? src[f] : padv;
+    }
+}
+
+// Ragged time-major features [sum T_i][dim] -> channels-first padded batch out[b][d][t] (CalmCollator: pad_sequence of (T, D)
+// items, then transpose(1, 2)), with the optional time mask of _apply_spec_augment (frames [mask_start, mask_start + mask_len)
+// set to 0).  32 x 32 tiles are transposed through shared memory so that both sides stay coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256) pad_transpose_kernel(const T* __restrict__ feat, const long long* __restrict__ row_offset,
+                                                            const long long* __restrict__ lens, int dim, T* __restrict__ out,
+                                                            long long out_frames, float pad_value,
+                                                            const long long* __restrict__ mask_start, const long long* __restrict__ mask_len) {
+    __shared__ float tile[32][33];
+    const int clip = blockIdx.z;
+    const long long t0 = (long long)blockIdx.x * 32;
+    const int d0 = blockIdx.y * 32;
+    const long long n = lens[clip];
+    const T* src = feat + row_offset[clip] * dim;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const long long m0 = mask_start ? mask_start[clip] : 0, m1 = mask_start ? m0 + mask_len[clip] : 0;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {                        // read: rows = time, columns = feature dim (contiguous)
+        const long long t = t0 + r;
+        float v = pad_value;
+        if (t < n && d0 + tx < dim) {
+            v = (float)src[t * dim + d0 + tx];
+            if (t >= m0 && t < m1) v = 0.f;
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {                        // write: rows = feature dim, columns = time (contiguous)
+        const int d = d0 + r;
+        const long long t = t0 + tx;
+        if (d < dim && t < out_frames) out[((long long)clip * dim + d) * out_frames + t] = from_float<T>(tile[tx][r]);
+    }
+}
+
 }  // namespace acb
 
 // ==============================================================================================
@@ -1261,6 +1324,51 @@ int acb_normalize_per_utterance(const float* feat, float* out, int32_t n_clips, 
     if (!feat || !out || n_mels < 1 || frame_capacity < 1) return fail(ACB_ERR_INVALID, "acb_normalize_per_utterance: bad argument");
     normalize_rows_kernel<<<n_clips * n_mels, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         feat, out, n_mels, frame_capacity, reinterpret_cast<const long long*>(frames), min_std);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
+int acb_crop_pad(const void* feat, int32_t dtype, int32_t n_clips, int32_t n_mels, int64_t frame_capacity, int64_t clip_stride,
+                 const int64_t* frames, const int64_t* start, void* out, int64_t out_frames, float pad_value, void* stream) {
+    if (n_clips <= 0 || out_frames <= 0) return ACB_OK;
+    if (!feat || !out || n_mels < 1 || frame_capacity < 1) return fail(ACB_ERR_INVALID, "acb_crop_pad: bad argument");
+    if (dtype != ACB_F32 && dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_crop_pad: bad dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)n_clips * (unsigned)n_mels;
+    const int threads = out_frames >= 256 ? 256 : 128;
+    if (dtype == ACB_F32)
+        crop_pad_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(feat), n_mels, frame_capacity, clip_stride,
+                                                        reinterpret_cast<const long long*>(frames), reinterpret_cast<const long long*>(start),
+                                                        static_cast<float*>(out), out_frames, pad_value);
+    else
+        crop_pad_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(feat), n_mels, frame_capacity, clip_stride,
+                                                                reinterpret_cast<const long long*>(frames), reinterpret_cast<const long long*>(start),
+                                                                static_cast<__nv_bfloat16*>(out), out_frames, pad_value);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
+int acb_pad_transpose(const void* feat_tm, int32_t dtype, const int64_t* row_offset, const int64_t* lens, int32_t n_clips, int32_t dim,
+                      void* out, int64_t out_frames, float pad_value, const int64_t* mask_start, const int64_t* mask_len, void* stream) {
+    if (n_clips <= 0 || out_frames <= 0) return ACB_OK;
+    if (!feat_tm || !row_offset || !lens || !out || dim < 1) return fail(ACB_ERR_INVALID, "acb_pad_transpose: bad argument");
+    if ((mask_start == nullptr) != (mask_len == nullptr)) return fail(ACB_ERR_INVALID, "acb_pad_transpose: mask_start and mask_len go together");
+    if (dtype != ACB_F32 && dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_pad_transpose: bad dtype");
+    if (n_clips > 65535) return fail(ACB_ERR_INVALID, "acb_pad_transpose: at most 65535 clips per call");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const dim3 grid((unsigned)((out_frames + 31) / 32), (unsigned)((dim + 31) / 32), (unsigned)n_clips);
+    if (dtype == ACB_F32)
+        pad_transpose_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(feat_tm), reinterpret_cast<const long long*>(row_offset),
+                                                          reinterpret_cast<const long long*>(lens), dim, static_cast<float*>(out), out_frames,
+                                                          pad_value, reinterpret_cast<const long long*>(mask_start),
+                                                          reinterpret_cast<const long long*>(mask_len));
+    else
+        pad_transpose_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(feat_tm),
+                                                                  reinterpret_cast<const long long*>(row_offset),
+                                                                  reinterpret_cast<const long long*>(lens), dim,
+                                                                  static_cast<__nv_bfloat16*>(out), out_frames, pad_value,
+                                                                  reinterpret_cast<const long long*>(mask_start),
+                                                                  reinterpret_cast<const long long*>(mask_len));
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
 }

@@ -140,6 +140,23 @@ int acb_moments_finalize(const double* moments_host, int32_t n_mels, int64_t fra
 int acb_normalize_per_utterance(const float* feat, float* out, int32_t n_clips, int32_t n_mels,
                                 int64_t frame_capacity, const int64_t* frames, float min_std, void* stream);
 
+/* Crop / zero-pad of stored features to a fixed number of frames, stacked: MelDataset.__getitem__ + data_collator
+ * (train/train_vae.py:83-116).  feat device MEL_MAJOR [n_clips][n_mels][frame_capacity] fp32 or bf16 (clip_stride elements
+ * between clips), frames[i] valid frames (device, NULL => frame_capacity), start[i] first frame of the crop (device, NULL => 0;
+ * the caller draws random starts for training and (T - crop) / 2 for eval, like the reference).
+ * out device [n_clips][n_mels][out_frames], same dtype: out[i][b][t] = feat[i][b][start[i] + t] inside the clip, else pad_value. */
+int acb_crop_pad(const void* feat, int32_t dtype, int32_t n_clips, int32_t n_mels, int64_t frame_capacity, int64_t clip_stride,
+                 const int64_t* frames, const int64_t* start, void* out, int64_t out_frames, float pad_value, void* stream);
+
+/* Ragged collation to a channels-first padded batch: CalmCollator's pad_sequence(batch_first) + transpose(1, 2)
+ * (train/train_calm.py:205-215), with the optional time mask of _apply_spec_augment (:184-191).
+ * feat_tm device, time-major rows [sum lens][dim] fp32 or bf16; row_offset[i] first row of clip i, lens[i] its rows (device);
+ * out device [n_clips][dim][out_frames], same dtype, pad_value beyond lens[i]; mask_start/mask_len (device, both or neither):
+ * rows [mask_start[i], mask_start[i] + mask_len[i]) of clip i are written as 0. */
+int acb_pad_transpose(const void* feat_tm, int32_t dtype, const int64_t* row_offset, const int64_t* lens, int32_t n_clips,
+                      int32_t dim, void* out, int64_t out_frames, float pad_value, const int64_t* mask_start,
+                      const int64_t* mask_len, void* stream);
+
 /* Host-buffer convenience path (pinned or pageable host memory): H2D copy, acb_logmel_forward on uniform
  * clips [n_clips][length], D2H copy, chunked over `n_chunks` so copies overlap compute.  dev_in/dev_out
  * are caller-provided device staging buffers (n_clips*length floats / n_clips*n_mels*frame_capacity
