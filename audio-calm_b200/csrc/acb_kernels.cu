@@ -1120,10 +1120,19 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     const SmemLayout Lm = make_smem_layout(n_mels, fe->n_plan_w, true);
     fe->smem_bytes = L.total_bytes;
     fe->smem_bytes_moments = Lm.total_bytes;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lm.total_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lm.total_bytes);
+    // The attribute is per function, not per handle: several front-ends (different n_mels) may live in one process, so it is
+    // always raised to the device's opt-in maximum; the launch passes the handle's own size.
+    const int optin = (int)prop.sharedMemPerBlockOptin;
+    if (e == cudaSuccess && Lm.total_bytes > optin) {
+        if (fe->d_blob) cudaFree(fe->d_blob);
+        delete fe;
+        cudaSetDevice(prev);
+        return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: filterbank plan needs more shared memory than the device offers");
+    }
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     int occ = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, logmel_fused_kernel<false, float>, kThreads, L.total_bytes);
     if (e != cudaSuccess) {

@@ -164,6 +164,25 @@ def test_layouts_and_affine(fe, golden):
     assert float(np.max(np.abs(y[0].cpu().numpy() - gn))) < EXPECT
 
 
+@pytest.mark.parametrize("n_mels,f_max", [(20, 8000.0), (40, 7600.0), (128, 8000.0), (57, 4000.0)])
+def test_other_filterbanks_and_log10(n_mels, f_max):
+    """The kernel plan is built from whatever bank the host hands over (MelExtractor(n_mels=...) in the reference's signature):
+    band counts that are not multiples of the 8-slot rounds, narrow and wide bands, a bank that stops below Nyquist; and log10."""
+    fe2 = acb.LogMelFrontend("cuda", n_mels=n_mels, f_max=f_max)
+    x = np.stack([o.synth_clip(24001, 900 + i) for i in range(2)])
+    y = fe2.forward(dev(x), pad_multiple=4)
+    assert tuple(y.shape) == (2, n_mels, 96)
+    for i in range(2):
+        ref = o.pad_time_reflect(o.logmel(x[i], fe2.window.numpy(), fe2.fb.numpy()), 4)
+        assert float(np.max(np.abs(y[i].cpu().numpy() - ref))) < EXPECT, (n_mels, i)
+    fe10 = acb.LogMelFrontend("cuda", n_mels=n_mels, f_max=f_max, log="log10", clamp_min=1e-10)
+    z = fe10.forward(dev(x))
+    for i in range(2):
+        mel = fe10.fb.numpy().astype(np.float64).T @ o.power_spectrogram(x[i], fe10.window.numpy())
+        ref = np.log10(np.maximum(mel, 1e-10))
+        assert float(np.max(np.abs(z[i].cpu().numpy() - ref))) < TOL_F32, (n_mels, i)     # 1e-10 clamp: fp32 FFT noise floor shows near silence
+
+
 def test_bf16_normalised_output(fe):
     x = np.stack([o.synth_clip(48000, 60 + i) for i in range(3)])
     y = fe.forward(dev(x), out_dtype=torch.bfloat16, affine=(acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT))
