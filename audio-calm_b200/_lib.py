@@ -37,6 +37,7 @@ EXPORTED_SYMBOLS = [
     "acb_plan_tiles", "acb_frontend_create", "acb_frontend_destroy", "acb_moments_workspace_bytes",
     "acb_logmel_forward", "acb_peak_abs", "acb_process_audio_chunk", "acb_moments_accumulate",
     "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host", "acb_crop_pad", "acb_pad_transpose",
+    "acb_moments_accumulate_workspace_bytes",
 ]
 
 
@@ -147,7 +148,9 @@ def load() -> ctypes.CDLL:
         lib.acb_process_audio_chunk.restype = ctypes.c_int
         lib.acb_process_audio_chunk.argtypes = [vp, i32, i64, vp, vp, vp]
         lib.acb_moments_accumulate.restype = ctypes.c_int
-        lib.acb_moments_accumulate.argtypes = [vp, i32, i32, i32, i64, i64, vp, vp, vp]
+        lib.acb_moments_accumulate.argtypes = [vp, i32, i32, i32, i64, i64, vp, vp, vp, vp]
+        lib.acb_moments_accumulate_workspace_bytes.restype = i64
+        lib.acb_moments_accumulate_workspace_bytes.argtypes = [i32]
         lib.acb_moments_finalize.restype = ctypes.c_int
         lib.acb_moments_finalize.argtypes = [vp, i32, i64, f64, vp, vp, vp, vp]
         lib.acb_normalize_per_utterance.restype = ctypes.c_int

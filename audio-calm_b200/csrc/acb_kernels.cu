@@ -427,6 +427,15 @@ __device__ __forceinline__ void store_tile(const LogmelParams& p, const ClipCurs
     }
 }
 
+// (hi, lo) += x with the rounding error of hi + x carried in lo (Knuth two-sum; no fast-math reassociation is enabled)
+__device__ __forceinline__ void two_sum_add(float2& acc, float x) {
+    const float t = __fadd_rn(acc.x, x);
+    const float bb = __fsub_rn(t, acc.x);
+    const float e = __fadd_rn(__fsub_rn(acc.x, __fsub_rn(t, bb)), __fsub_rn(x, bb));
+    acc.y = __fadd_rn(acc.y, e);
+    acc.x = t;
+}
+
 template <bool kMoments, typename OutT>
 __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -451,7 +460,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     short* s_trip = reinterpret_cast<short*>(smem + L.plan_trip);
     short* s_band = reinterpret_cast<short*>(smem + L.plan_band);
     short* s_astart = reinterpret_cast<short*>(smem + L.plan_astart);
-    double* s_mom = reinterpret_cast<double*>(smem + L.moments) + grp * 2 * n_mels;   // [2][n_mels] per group, only when kMoments
+    float2* s_mom = reinterpret_cast<float2*>(smem + L.moments) + grp * 2 * n_mels;   // [2][n_mels] (hi, lo) pairs per group, only when kMoments
 
     // ---- one-time table staging (whole CTA) ----
     for (int i = tid; i < 5 * 32; i += kThreads) s_tw4[i] = p.twiddle[i];
@@ -466,7 +475,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         s_aff[i] = make_float2(sc, sh);
     }
     if (kMoments)
-        for (int i = gt; i < 2 * n_mels; i += kGroupThreads) s_mom[i] = 0.0;
+        for (int i = gt; i < 2 * n_mels; i += kGroupThreads) s_mom[i] = make_float2(0.f, 0.f);
     __syncthreads();
 
     // ---- this group's contiguous tile range ----
@@ -631,17 +640,21 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 float vA = (mA > p.clamp_min) ? __log2f(mA) * p.log_scale : p.log_floor;
                 float vB = (mB > p.clamp_min) ? __log2f(mB) * p.log_scale : p.log_floor;
                 if (kMoments) {
-                    // frames T-2-j (j < pad) are stored twice (reflected pad-to-4 columns) and counted twice
-                    double s = 0.0, s2 = 0.0;
+                    // frames T-2-j (j < pad) are stored twice (reflected pad-to-4 columns) and counted twice.  The tile's 8 frames of a
+                    // band are summed in fp32 (two values per lane, then the slot's 4 pair lanes by shuffle) and enter the group's
+                    // accumulators once per (band, tile).  The accumulators are compensated fp32 pairs (hi, lo), exact to ~2^-46 and
+                    // turned into fp64 once at the end of the kernel: vector fp64 is a scarce pipe on B200.
+                    float s = 0.f, s2 = 0.f;
                     if (b >= 0 && fA < cur.frames) {
-                        const double c = (fA <= cur.frames - 2 && fA > cur.frames - 2 - pad) ? 2.0 : 1.0;
-                        s += c * (double)vA;
-                        s2 += c * (double)vA * (double)vA;
+                        const float c = (fA <= cur.frames - 2 && fA > cur.frames - 2 - pad) ? 2.f : 1.f;
+                        s = c * vA;
+                        s2 = s * vA;
                     }
                     if (b >= 0 && fA + 1 < cur.frames) {
-                        const double c = (fA + 1 <= cur.frames - 2 && fA + 1 > cur.frames - 2 - pad) ? 2.0 : 1.0;
-                        s += c * (double)vB;
-                        s2 += c * (double)vB * (double)vB;
+                        const float c = (fA + 1 <= cur.frames - 2 && fA + 1 > cur.frames - 2 - pad) ? 2.f : 1.f;
+                        const float cv = c * vB;
+                        s += cv;
+                        s2 = fmaf(cv, vB, s2);
                     }
                     // the 4 pair lanes of a slot are a contiguous, aligned lane group (all 32 lanes take part)
 #pragma unroll
@@ -649,7 +662,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                         s += __shfl_xor_sync(0xffffffffu, s, o);
                         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                     }
-                    if (pr == 0 && b >= 0) { s_mom[b] += s; s_mom[n_mels + b] += s2; }   // each band has exactly one owner slot per group
+                    if (pr == 0 && b >= 0) {   // each band has exactly one owner slot per group
+                        two_sum_add(s_mom[b], s);
+                        two_sum_add(s_mom[n_mels + b], s2);
+                    }
                 }
                 if (b >= 0) {
                     const float2 af = s_aff[b];
@@ -678,17 +694,21 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
 
     if (kMoments) {
         group_sync(grp);
-        for (int i = gt; i < 2 * n_mels; i += kGroupThreads) p.moments_partial[(size_t)g_index * 2 * n_mels + i] = s_mom[i];
+        for (int i = gt; i < 2 * n_mels; i += kGroupThreads)
+            p.moments_partial[(size_t)g_index * 2 * n_mels + i] = (double)s_mom[i].x + (double)s_mom[i].y;
     }
 }
 
-// Sum per-CTA partials in a fixed order (deterministic) and add into the running accumulators.
-__global__ void moments_reduce_kernel(const double* __restrict__ partial, int n_parts, int n_vals, double* __restrict__ acc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Sum the per-group partials in a fixed order (deterministic) and add into the running accumulators: one warp per value,
+// lanes stride over the partials (independent loads), then a shuffle tree.
+__global__ void __launch_bounds__(256) moments_reduce_kernel(const double* __restrict__ partial, int n_parts, int n_vals, double* __restrict__ acc) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n_vals) return;
     double s = 0.0;
-    for (int k = 0; k < n_parts; ++k) s += partial[(size_t)k * n_vals + i];
-    acc[i] += s;
+    for (int k = lane; k < n_parts; k += 32) s += partial[(size_t)k * n_vals + i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) acc[i] += s;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -784,12 +804,26 @@ __global__ void __launch_bounds__(256) moments_rows_kernel(const T* __restrict__
         const int clip = (int)(row / n_mels), b = (int)(row - (long long)clip * n_mels);
         const long long n_fr = frames ? frames[clip] : cap;
         const T* src = feat + (long long)clip * clip_stride + (long long)b * cap;
-        double s = 0.0, s2 = 0.0;
-        for (long long i = lane; i < n_fr; i += 32) {
-            const double v = (double)load_feat<T>(src, i);
-            s += v;
-            s2 += v * v;
+        // four coalesced 128-byte loads in flight per lane, four independent fp64 accumulator pairs
+        double sa[4] = {0.0, 0.0, 0.0, 0.0}, sb[4] = {0.0, 0.0, 0.0, 0.0};
+        long long i = lane;
+        for (; i + 96 < n_fr; i += 128) {
+            float f[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) f[k] = load_feat<T>(src, i + 32 * k);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double v = (double)f[k];
+                sa[k] += v;
+                sb[k] += v * v;
+            }
         }
+        for (; i < n_fr; i += 32) {
+            const double v = (double)load_feat<T>(src, i);
+            sa[0] += v;
+            sb[0] += v * v;
+        }
+        double s = (sa[0] + sa[1]) + (sa[2] + sa[3]), s2 = (sb[0] + sb[1]) + (sb[2] + sb[3]);
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -1243,7 +1277,7 @@ int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* s
         if (p.out_bf16) logmel_fused_kernel<true, __nv_bfloat16><<<grid, kThreads, fe->smem_bytes_moments, st>>>(p);
         else logmel_fused_kernel<true, float><<<grid, kThreads, fe->smem_bytes_moments, st>>>(p);
         const int n_vals = 2 * fe->n_mels;
-        moments_reduce_kernel<<<(n_vals + 127) / 128, 128, 0, st>>>(p.moments_partial, grid * kGroups, n_vals, a->moments);
+        moments_reduce_kernel<<<(n_vals + 7) / 8, 256, 0, st>>>(p.moments_partial, grid * kGroups, n_vals, a->moments);
     } else {
         if (p.out_bf16) logmel_fused_kernel<false, __nv_bfloat16><<<grid, kThreads, fe->smem_bytes, st>>>(p);
         else logmel_fused_kernel<false, float><<<grid, kThreads, fe->smem_bytes, st>>>(p);
@@ -1281,17 +1315,21 @@ int acb_process_audio_chunk(const float* wav_cl, int32_t channels, int64_t lengt
     return ACB_OK;
 }
 
+int64_t acb_moments_accumulate_workspace_bytes(int32_t n_mels) {
+    return (int64_t)sizeof(double) * 148 * 8 * 2 * (int64_t)(n_mels > 0 ? n_mels : 0);
+}
+
 int acb_moments_accumulate(const void* feat, int32_t dtype, int32_t n_clips, int32_t n_mels, int64_t frame_capacity,
-                           int64_t clip_stride, const int64_t* frames, double* moments, void* stream) {
+                           int64_t clip_stride, const int64_t* frames, double* moments, void* workspace, void* stream) {
     if (n_clips <= 0) return ACB_OK;
     if (!feat || !moments || n_mels < 1 || frame_capacity < 1) return fail(ACB_ERR_INVALID, "acb_moments_accumulate: bad argument");
     if (dtype != ACB_F32 && dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_moments_accumulate: bad dtype");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int warps = 8;
     const long long n_rows = (long long)n_clips * n_mels;
-    const int grid = (int)std::min<long long>(148 * 4, (n_rows + warps - 1) / warps);
-    double* partial = nullptr;
-    ACB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(double) * (size_t)grid * 2 * n_mels, st));
+    const int grid = (int)std::min<long long>(148 * 8, (n_rows + warps - 1) / warps);
+    double* partial = static_cast<double*>(workspace);   // caller-owned scratch (acb_moments_accumulate_workspace_bytes), or a stream-ordered one
+    if (!workspace) ACB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(double) * (size_t)grid * 2 * n_mels, st));
     const size_t smem = sizeof(double) * warps * 2 * n_mels;
     if (dtype == ACB_F32)
         moments_rows_kernel<float><<<grid, warps * 32, smem, st>>>(static_cast<const float*>(feat), n_clips, n_mels, frame_capacity,
@@ -1300,9 +1338,9 @@ int acb_moments_accumulate(const void* feat, int32_t dtype, int32_t n_clips, int
         moments_rows_kernel<__nv_bfloat16><<<grid, warps * 32, smem, st>>>(static_cast<const __nv_bfloat16*>(feat), n_clips, n_mels,
                                                                             frame_capacity, clip_stride,
                                                                             reinterpret_cast<const long long*>(frames), partial);
-    moments_reduce_kernel<<<(2 * n_mels + 127) / 128, 128, 0, st>>>(partial, grid, 2 * n_mels, moments);
+    moments_reduce_kernel<<<(2 * n_mels + 7) / 8, 256, 0, st>>>(partial, grid, 2 * n_mels, moments);
     cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(partial, st);
+    if (!workspace) cudaFreeAsync(partial, st);
     if (e != cudaSuccess) return cuda_fail(e, "acb_moments_accumulate launch");
     return ACB_OK;
 }

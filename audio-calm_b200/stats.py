@@ -69,6 +69,7 @@ class MelStatsAccumulator:
         self.device = torch.device(device)
         self.moments = torch.zeros(2 * self.n_mels, dtype=torch.float64, device=self.device)
         self.frames = 0
+        self._ws: Optional[torch.Tensor] = None   # scratch of acb_moments_accumulate, allocated on first use
 
     # -- S1: moments of features that already exist (files written by the dataset driver) --
     def update(self, feat: torch.Tensor, frames: Optional[torch.Tensor] = None) -> None:
@@ -90,8 +91,11 @@ class MelStatsAccumulator:
             frames = frames.to(feat.device, torch.int64).contiguous()
             fr_ptr = frames.data_ptr()
         dtype = _lib.ACB_F32 if feat.dtype == torch.float32 else _lib.ACB_BF16
+        if self._ws is None:
+            self._ws = torch.empty(int(lib.acb_moments_accumulate_workspace_bytes(self.n_mels)) // 8, dtype=torch.float64, device=self.device)
         _lib.check(lib.acb_moments_accumulate(feat.data_ptr(), dtype, B, M, cap, M * cap, fr_ptr, self.moments.data_ptr(),
-                                              torch.cuda.current_stream(feat.device).cuda_stream), "acb_moments_accumulate")
+                                              self._ws.data_ptr(), torch.cuda.current_stream(feat.device).cuda_stream),
+                   "acb_moments_accumulate")
         self.frames += int(frames.sum().item()) if frames is not None else B * cap
 
     # -- combine shards: one collective --

@@ -126,9 +126,12 @@ int acb_process_audio_chunk(const float* wav_cl, int32_t channels, int64_t lengt
 
 /* Per-bin moments of already-extracted features (compute_mel_stats.py:19-28 over saved files):
  * feat device, MEL_MAJOR [n_clips][n_mels][frame_capacity] fp32 or bf16, frames[i] valid frames of clip i
- * (device [n_clips]; NULL => all frame_capacity).  Accumulates into moments[2 * n_mels] (device, fp64). */
+ * (device [n_clips]; NULL => all frame_capacity).  Accumulates into moments[2 * n_mels] (device, fp64).
+ * workspace: device scratch of acb_moments_accumulate_workspace_bytes(n_mels) bytes owned by the caller, or NULL
+ * (a stream-ordered allocation is made and freed inside the call). */
+int64_t acb_moments_accumulate_workspace_bytes(int32_t n_mels);
 int acb_moments_accumulate(const void* feat, int32_t dtype, int32_t n_clips, int32_t n_mels, int64_t frame_capacity,
-                           int64_t clip_stride, const int64_t* frames, double* moments, void* stream);
+                           int64_t clip_stride, const int64_t* frames, double* moments, void* workspace, void* stream);
 
 /* Finalise on the host (compute_mel_stats.py:30-33): per-bin mean/std and the reference's global scalars.
  * moments_host[2 * n_mels], frames = total frame count (all clips).  var floor as in the reference (1e-8). */
