@@ -12,7 +12,8 @@
 // Structure: a CTA (256 threads, 2 CTAs per SM) holds TWO independent groups of 4 warps; a group owns a contiguous range
 // of 8-frame tiles, its own sample buffer, scratch and named barrier, so four groups per SM run out of phase and the
 // FMA-heavy and the shared-memory-heavy parts of different groups overlap.  Per tile a group does:
-//   1. cp.async the tile's (8+3)*256 samples into shared memory (reflection handled for edge tiles);
+//   1. one bulk async copy (cp.async.bulk + mbarrier) brings the tile's (8+3)*256 samples into shared memory (edge tiles,
+//      which need reflection, are gathered by the group);
 //   2. each warp takes one pair of adjacent frames (A, B) and runs ONE complex 1024-point FFT of
 //      A + iB as 32 x 32: radix-2 DIT FFT-32 in registers (FMA butterflies), twiddle, transpose through
 //      a warp-private padded scratch, second FFT-32; the two real spectra are separated with warp
@@ -21,7 +22,8 @@
 //      lanes = 8 bands x 4 frame pairs, warp-uniform trip counts from a host-built balanced schedule;
 //      clamp, log, optional affine, optional fp64 moments; interior tiles store straight from registers;
 //   4. edge tiles are staged in shared memory and stored with masking, reflected pad-to-4 columns and tail fill.
-// The next tile's samples are prefetched (cp.async) while step 3/4 run.
+// The next tile's samples are prefetched while step 3/4 run; the first FFT-32 of the next tile runs before the barrier that
+// frees the scratch, so a warp never waits for its group with nothing to do.
 #include "audiocalm_b200.h"
 
 #include <cuda_bf16.h>
@@ -83,16 +85,28 @@ static int cuda_fail(cudaError_t e, const char* what) {
 // --------------------------------------------------------------------------------------------
 // device helpers
 // --------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+// ---- mbarrier + 1-D bulk async copy (TMA without a tensor map): sample tiles land in shared memory without LSU work ----
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
-    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(smem)), "l"(gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
 
 __host__ __device__ constexpr int brev5(int x) {
     return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
@@ -255,7 +269,7 @@ struct LogmelParams {
 };
 
 struct SmemLayout {
-    int samples, scratch, twiddle, window, plan_w, affine, plan_woff, plan_trip, plan_band, plan_astart, moments, total_bytes;
+    int samples, scratch, twiddle, window, plan_w, affine, plan_woff, plan_trip, plan_band, plan_astart, mbar, moments, total_bytes;
 };
 
 __host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }   // odd: conflict-free both ways
@@ -274,7 +288,8 @@ __host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w,
     L.plan_band = off; off += kGroupWarps * kMaxRounds * kSlots / 2;      // shorts
     L.plan_astart = off; off += kGroupWarps * kMaxRounds * kSlots / 2;    // shorts
     off = (off + 1) & ~1;
-    L.moments = off; if (with_moments) off += kGroups * 4 * n_mels;       // doubles [kGroups][2][n_mels]
+    L.mbar = off; off += 2 * kGroups;                                     // one 8-byte mbarrier per group ("sample tile landed")
+    L.moments = off; if (with_moments) off += kGroups * 4 * n_mels;       // float2 [kGroups][2][n_mels]
     L.total_bytes = off * 4;
     return L;
 }
@@ -340,32 +355,35 @@ __device__ __forceinline__ void group_sync(int grp) {   // named barrier of one 
     asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
 }
 
-__device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const ClipCursor& t, float* s_samples, int gt) {
+// Stage one tile's samples; the group's mbarrier completes a phase when they have landed.  Called by all threads of the group.
+// Interior tiles are ONE bulk async copy issued by one thread (the copy engine writes shared memory and counts the bytes on the
+// mbarrier); edge tiles (reflection about sample 0 / L-1, torch.stft center=True pad_mode="reflect") and unaligned clips are
+// gathered by the whole group, which then arrives once.
+__device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const ClipCursor& t, float* s_samples, int gt, int grp,
+                                                  unsigned long long* full) {
     const int f0 = t.tile_in_clip * kTileFrames;
     const long long g0 = (long long)f0 * kHop - kNfft / 2;  // sample index (relative to the clip) of smem slot 0
     const float* src = p.wav + t.wav_base;
     const bool interior = (g0 >= 0) && (g0 + kTileSamples <= t.length);
-    if (interior) {
-        const float* gp = src + g0;
-        if ((reinterpret_cast<uintptr_t>(gp) & 15) == 0) {
-            for (int i = gt; i < kTileSamples / 4; i += kGroupThreads) cp_async16(s_samples + 4 * i, gp + 4 * i);
-        } else {
-            for (int i = gt; i < kTileSamples; i += kGroupThreads) cp_async4(s_samples + i, gp + i);
+    if (interior && (reinterpret_cast<uintptr_t>(src + g0) & 15) == 0) {   // group-uniform
+        if (gt == 0) {
+            mbar_arrive_expect_tx(full, kTileSamples * (unsigned)sizeof(float));
+            bulk_copy_g2s(s_samples, src + g0, kTileSamples * (unsigned)sizeof(float), full);
         }
-    } else {
-        // edge tile: reflect about sample 0 and sample L-1 (torch.stft center=True, pad_mode="reflect");
-        // slots that belong only to frames >= T get zeros.
-        const long long L = t.length;
-        for (int i = gt; i < kTileSamples; i += kGroupThreads) {
-            long long idx = g0 + i;
-            if (idx < 0) idx = -idx;
-            if (idx >= L) idx = 2 * (L - 1) - idx;
-            float v = 0.f;
-            if (idx >= 0 && idx < L) v = __ldg(src + idx);
-            s_samples[i] = v;
-        }
+        return;
     }
-    cp_async_commit();
+    // slots that belong only to frames >= T get zeros
+    const long long L = t.length;
+    for (int i = gt; i < kTileSamples; i += kGroupThreads) {
+        long long idx = g0 + i;
+        if (idx < 0) idx = -idx;
+        if (idx >= L) idx = 2 * (L - 1) - idx;
+        float v = 0.f;
+        if (idx >= 0 && idx < L) v = __ldg(src + idx);
+        s_samples[i] = v;
+    }
+    group_sync(grp);
+    if (gt == 0) mbar_arrive(full);
 }
 
 template <typename OutT>
@@ -461,6 +479,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     short* s_band = reinterpret_cast<short*>(smem + L.plan_band);
     short* s_astart = reinterpret_cast<short*>(smem + L.plan_astart);
     float2* s_mom = reinterpret_cast<float2*>(smem + L.moments) + grp * 2 * n_mels;   // [2][n_mels] (hi, lo) pairs per group, only when kMoments
+    unsigned long long* s_full = reinterpret_cast<unsigned long long*>(smem + L.mbar) + grp;   // "sample tile landed"
 
     // ---- one-time table staging (whole CTA) ----
     for (int i = tid; i < 5 * 32; i += kThreads) s_tw4[i] = p.twiddle[i];
@@ -476,6 +495,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     }
     if (kMoments)
         for (int i = gt; i < 2 * n_mels; i += kGroupThreads) s_mom[i] = make_float2(0.f, 0.f);
+    if (gt == 0) {
+        mbar_init(s_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     // ---- this group's contiguous tile range ----
@@ -484,9 +507,12 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     const long long t_end = (long long)p.n_tiles * (g_index + 1) / n_groups;
 
     ClipCursor cur;
+    bool staged = false;          // group-uniform: a sample tile was requested for the current tile
+    unsigned full_parity = 0;
     if (t_begin < t_end) {
         cursor_init(p, cur, t_begin);
-        if (cur.tile_in_clip * kTileFrames < cur.frames) load_tile_samples(p, cur, s_samples, gt);
+        staged = cur.tile_in_clip * kTileFrames < cur.frames;
+        if (staged) load_tile_samples(p, cur, s_samples, gt, grp, s_full);
     }
 
     // ---- per-thread constants of the mel phase: lanes = 8 band slots x 4 frame pairs ----
@@ -494,20 +520,25 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     // pairs fall on bank groups {0, 8, 16, 24} + 4 * ((astart/2 + i) mod 2): the host plan gives the two slots of a quarter
     // opposite parity of astart/2, which makes the load conflict-free.
     const int q = lane >> 2;     // band slot within a round
-    const int pr = lane & 3;     // frame pair
-    const float* pair_scratch = s_scratch + pr * kScratchFloats;
+    const int pl = lane & 3;     // frame pair served by this lane in the mel phase
+    const float* pair_scratch = s_scratch + pl * kScratchFloats;
     float* scr = s_scratch + gw * kScratchFloats;
     float2* scr2 = reinterpret_cast<float2*>(scr);
 
     for (long long tile = t_begin; tile < t_end; ++tile) {
-        cp_async_wait_all();
-        group_sync(grp);  // samples visible; previous tile's mel phase / staged store done with the scratch
+        if (staged) {             // the tile's samples have landed (bulk copy counted in, or the gathering group arrived)
+            mbar_wait(s_full, full_parity);
+            full_parity ^= 1;
+        }
 
         const int f0 = cur.tile_in_clip * kTileFrames;
         const bool has_frames = f0 < cur.frames;  // false for pure tail-fill tiles
+        const bool active = has_frames && f0 + 2 * gw < cur.frames && ACB_ABLATE != 7;   // this warp's frame pair exists
 
         // ================= phase 1: one frame pair per warp =================
-        if (has_frames && f0 + 2 * gw < cur.frames && ACB_ABLATE != 7) {
+        // The first FFT-32 needs only the samples and registers, so it runs BEFORE the barrier that frees the scratch: a warp that
+        // is done with the previous tile's mel phase does not wait for the slower warps of its group here.
+        if (active) {
             float2 pr[16], pi[16];   // element k < 16 in .x, element k + 16 in .y (see fft32_packed)
             {
                 // Hann window folded into the first radix-2 stage: positions (2j, 2j+1) of the bit-reversed order hold samples
@@ -531,6 +562,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 }
             }
             fft32_packed_from_stage2(pr, pi);  // over n1 -> k1 (natural order)
+            group_sync(grp);  // the group is done with the previous tile's mel phase / staged store: the scratch is free
             // twiddle W_1024^(k1*lane), then transposed store plane[k1][lane].  The twiddles of a lane are powers of W^lane, kept
             // as pairs T[k] = (W^(k*lane), W^((k+16)*lane)): four chains T[k+4] = T[k] * W^(4*lane) seeded with exact values
             // (3 steps deep) cost packed FMA-pipe instructions instead of an 8-byte shared-memory load per twiddle.
@@ -599,13 +631,18 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                 scr2[lane + 32 * m] = make_float2(pa, pb);
             }
         }
+        else {
+            group_sync(grp);  // warps without a frame pair (tail of a clip) take part in the same barrier
+        }
         group_sync(grp);  // power spectra of the group's pairs visible; sample tile is free again
 
         // prefetch the next tile's samples while the mel phase runs
         ClipCursor nxt = cur;
+        staged = false;
         if (tile + 1 < t_end) {
             cursor_advance(p, nxt);
-            if (nxt.tile_in_clip * kTileFrames < nxt.frames) load_tile_samples(p, nxt, s_samples, gt);
+            staged = nxt.tile_in_clip * kTileFrames < nxt.frames;
+            if (staged) load_tile_samples(p, nxt, s_samples, gt, grp, s_full);
         }
 
         // interior tile: every frame exists and none is a pad-to-4 source -> mel-major results go straight to global
@@ -616,7 +653,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
 
         // ================= phase 2: banded mel projection, clamp, log, affine, moments =================
         if (has_frames && ACB_ABLATE != 8) {
-            const int fA = f0 + 2 * pr;
+            const int fA = f0 + 2 * pl;
             OutT* out_clip = reinterpret_cast<OutT*>(p.out) + cur.out_base;
             for (int r = 0; r < kMaxRounds; ++r) {
                 const int slot = gw * kMaxRounds + r;
@@ -662,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                         s += __shfl_xor_sync(0xffffffffu, s, o);
                         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                     }
-                    if (pr == 0 && b >= 0) {   // each band has exactly one owner slot per group
+                    if (pl == 0 && b >= 0) {   // each band has exactly one owner slot per group
                         two_sum_add(s_mom[b], s);
                         two_sum_add(s_mom[n_mels + b], s2);
                     }
@@ -678,8 +715,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                             dst[1] = to_out<OutT>(vB);
                         }
                     } else {
-                        s_out[(2 * pr) * S + b] = vA;
-                        s_out[(2 * pr + 1) * S + b] = vB;
+                        s_out[(2 * pl) * S + b] = vA;
+                        s_out[(2 * pl + 1) * S + b] = vB;
                     }
                 }
             }
@@ -690,7 +727,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         }
         cur = nxt;
     }
-    cp_async_wait_all();
 
     if (kMoments) {
         group_sync(grp);
