@@ -269,7 +269,7 @@ struct LogmelParams {
 };
 
 struct SmemLayout {
-    int samples, scratch, twiddle, window, plan_w, affine, plan_woff, plan_trip, plan_band, plan_astart, mbar, moments, total_bytes;
+    int samples, scratch, twiddle, window, plan_w, affine, plan_rec, mbar, moments, total_bytes;
 };
 
 __host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }   // odd: conflict-free both ways
@@ -283,11 +283,8 @@ __host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w,
     L.window = off; off += kNfft / 2;                             // first half only: w[n + N/2] = 1 - w[n]
     L.plan_w = off; off += (n_plan_w + 3) & ~3;
     L.affine = off; off += 2 * ((n_mels + 1) & ~1);
-    L.plan_woff = off; off += kGroupWarps * kMaxRounds;
-    L.plan_trip = off; off += kGroupWarps * kMaxRounds / 2;               // shorts
-    L.plan_band = off; off += kGroupWarps * kMaxRounds * kSlots / 2;      // shorts
-    L.plan_astart = off; off += kGroupWarps * kMaxRounds * kSlots / 2;    // shorts
-    off = (off + 1) & ~1;
+    off = (off + 3) & ~3;
+    L.plan_rec = off; off += kGroupWarps * kMaxRounds * kSlots * 4;       // int4 per (warp, round, slot): the mel phase's per-lane constants
     L.mbar = off; off += 2 * kGroups;                                     // one 8-byte mbarrier per group ("sample tile landed")
     L.moments = off; if (with_moments) off += kGroups * 4 * n_mels;       // float2 [kGroups][2][n_mels]
     L.total_bytes = off * 4;
@@ -393,6 +390,15 @@ __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 to_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+template <typename OutT>
+__device__ __forceinline__ void store_pair(OutT* dst, float a, float b);
+template <>
+__device__ __forceinline__ void store_pair<float>(float* dst, float a, float b) { *reinterpret_cast<float2*>(dst) = make_float2(a, b); }
+template <>
+__device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(dst) = __floats2bfloat162_rn(a, b);
+}
+
 // Store one staged tile.  Interior tiles (every frame exists and none is a pad-to-4 source) take loops without
 // per-element conditions; the last tiles of a clip take the general path (masking, reflected columns, tail fill).
 template <typename OutT>
@@ -445,6 +451,13 @@ __device__ __forceinline__ void store_tile(const LogmelParams& p, const ClipCurs
     }
 }
 
+// log2 of a value known to be a normal float (it is above the clamp): the bare MUFU.LG2, without __log2f's denormal rescue
+__device__ __forceinline__ float lg2_normal(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // (hi, lo) += x with the rounding error of hi + x carried in lo (Knuth two-sum; no fast-math reassociation is enabled)
 __device__ __forceinline__ void two_sum_add(float2& acc, float x) {
     const float t = __fadd_rn(acc.x, x);
@@ -474,10 +487,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     float* s_win = smem + L.window;
     float* s_pw = smem + L.plan_w;
     float2* s_aff = reinterpret_cast<float2*>(smem + L.affine);   // per band (scale, shift): out = v * scale + shift
-    int* s_woff = reinterpret_cast<int*>(smem + L.plan_woff);
-    short* s_trip = reinterpret_cast<short*>(smem + L.plan_trip);
-    short* s_band = reinterpret_cast<short*>(smem + L.plan_band);
-    short* s_astart = reinterpret_cast<short*>(smem + L.plan_astart);
+    int4* s_rec = reinterpret_cast<int4*>(smem + L.plan_rec);   // {power offset (16-byte units), weight offset (8-byte units), band, trip}
     float2* s_mom = reinterpret_cast<float2*>(smem + L.moments) + grp * 2 * n_mels;   // [2][n_mels] (hi, lo) pairs per group, only when kMoments
     unsigned long long* s_full = reinterpret_cast<unsigned long long*>(smem + L.mbar) + grp;   // "sample tile landed"
 
@@ -485,8 +495,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
     for (int i = tid; i < 5 * 32; i += kThreads) s_tw4[i] = p.twiddle[i];
     for (int i = tid; i < kNfft / 2; i += kThreads) s_win[i] = p.window[i];
     for (int i = tid; i < p.n_plan_w; i += kThreads) s_pw[i] = p.plan_w[i];
-    for (int i = tid; i < kGroupWarps * kMaxRounds; i += kThreads) { s_woff[i] = p.plan_woff[i]; s_trip[i] = p.plan_trip[i]; }
-    for (int i = tid; i < kGroupWarps * kMaxRounds * kSlots; i += kThreads) { s_band[i] = p.plan_band[i]; s_astart[i] = p.plan_astart[i]; }
+    for (int i = tid; i < kGroupWarps * kMaxRounds * kSlots; i += kThreads) {
+        const int slot = i / kSlots, qq = i - slot * kSlots;
+        s_rec[i] = make_int4(p.plan_astart[i] >> 1, (p.plan_woff[slot] >> 1) + qq, p.plan_band[i], p.plan_trip[slot]);
+    }
     for (int i = tid; i < n_mels; i += kThreads) {
         float sc = 1.f, sh = 0.f;   // affine == 0: v * 1 + 0 is exact
         if (p.affine == 1) { sc = p.affine_inv_std; sh = -p.affine_mean * p.affine_inv_std; }
@@ -655,13 +667,14 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         if (has_frames && ACB_ABLATE != 8) {
             const int fA = f0 + 2 * pl;
             OutT* out_clip = reinterpret_cast<OutT*>(p.out) + cur.out_base;
+            const bool pair_store = ((cur.cap & 1) == 0) && ((reinterpret_cast<uintptr_t>(out_clip) & (2 * sizeof(OutT) - 1)) == 0);
             for (int r = 0; r < kMaxRounds; ++r) {
-                const int slot = gw * kMaxRounds + r;
-                const int trip = s_trip[slot];
+                const int4 rec = s_rec[(gw * kMaxRounds + r) * kSlots + q];
+                const int trip = rec.w;
                 if (trip == 0) break;  // warp-uniform; rounds are filled in order
-                const int b = s_band[slot * kSlots + q];
-                const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + (s_astart[slot * kSlots + q] >> 1);   // two bins x (A, B)
-                const float2* w2 = reinterpret_cast<const float2*>(s_pw + s_woff[slot]) + q;
+                const int b = rec.z;
+                const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + rec.x;   // two bins x (A, B)
+                const float2* w2 = reinterpret_cast<const float2*>(s_pw) + rec.y;
                 float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
                 const int half_trip = ACB_ABLATE == 4 ? 0 : (trip >> 1);
 #pragma unroll 4
@@ -674,8 +687,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                     acc3 = fmaf(w.y, pw.w, acc3);
                 }
                 const float mA = (acc0 + acc2) * cur.gain, mB = (acc1 + acc3) * cur.gain;
-                float vA = (mA > p.clamp_min) ? __log2f(mA) * p.log_scale : p.log_floor;
-                float vB = (mB > p.clamp_min) ? __log2f(mB) * p.log_scale : p.log_floor;
+                float vA = (mA > p.clamp_min) ? lg2_normal(mA) * p.log_scale : p.log_floor;
+                float vB = (mB > p.clamp_min) ? lg2_normal(mB) * p.log_scale : p.log_floor;
                 if (kMoments) {
                     // frames T-2-j (j < pad) are stored twice (reflected pad-to-4 columns) and counted twice.  The tile's 8 frames of a
                     // band are summed in fp32 (two values per lane, then the slot's 4 pair lanes by shuffle) and enter the group's
@@ -711,8 +724,12 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                     if (direct) {
                         if (write_out) {
                             OutT* dst = out_clip + (size_t)((unsigned)b * (unsigned)cur.cap) + fA;
-                            dst[0] = to_out<OutT>(vA);
-                            dst[1] = to_out<OutT>(vB);
+                            if (pair_store) {   // frames A and B in one store (the row pitch and the clip's base keep the pair aligned)
+                                store_pair<OutT>(dst, vA, vB);
+                            } else {
+                                dst[0] = to_out<OutT>(vA);
+                                dst[1] = to_out<OutT>(vB);
+                            }
                         }
                     } else {
                         s_out[(2 * pl) * S + b] = vA;
@@ -1051,6 +1068,7 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
                                              std::to_string(n_fft) + ", hop=" + std::to_string(hop) + ")");
     if (n_mels < 1 || n_mels > kMaxMels) return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: n_mels must be in [1, 128]");
     if (log_kind != ACB_LOG_NATURAL && log_kind != ACB_LOG_10) return fail(ACB_ERR_INVALID, "acb_frontend_create: bad log_kind");
+    if (!(clamp_min >= 1.17549435e-38f)) return fail(ACB_ERR_INVALID, "acb_frontend_create: clamp_min must be a positive normal float");
     const int n_freq = n_fft / 2 + 1;
 
     // banded form of the filterbank; the 1/4 of the packed-pair power spectrum is folded in (exact scaling)
