@@ -120,3 +120,50 @@ def test_stats_cli_over_saved_features(tmp_path, capsys, manifest):
     assert lines[-2:] == want["printed"]
     assert stats.count == want["total_count"]
     assert abs(stats.mel_mean - want["mean"]) < 1e-6 and abs(stats.mel_std - want["std"]) < 1e-6
+
+
+def _ref_latent_stats(files, reduce_dim):
+    """The reference loop (preprocess/compute_latent_stats.py:15-40) restated with the same torch calls, in fp64 to serve as truth."""
+    sum1 = sum2 = None
+    count = 0
+    for f in files:
+        payload = torch.load(f, map_location="cpu", weights_only=True)
+        lat = payload.get("latent", payload) if isinstance(payload, dict) else payload
+        if lat.dim() == 2 and lat.shape[0] in (64, 80, 128, 192):
+            lat = lat.transpose(0, 1)
+        lat = lat.double()
+        lat = lat.contiguous().reshape(-1) if reduce_dim else lat.contiguous()
+        s1, s2 = lat.sum(dim=0), (lat * lat).sum(dim=0)
+        sum1, sum2 = (s1, s2) if sum1 is None else (sum1 + s1, sum2 + s2)
+        count += lat.shape[0]
+    mean = sum1 / count
+    std = torch.sqrt((sum2 / count - mean * mean).clamp(min=1e-12))
+    return mean, std
+
+
+@pytest.mark.gpu
+def test_latent_stats_scalar_and_per_dim(tmp_path, capsys):
+    g = torch.Generator().manual_seed(5)
+    files = []
+    for i, (T, as_dt) in enumerate([(96, True), (41, False), (300, True), (7, False)]):      # (D, T) and (T, D) payloads, bare tensor too
+        lat = torch.randn(T, 128, generator=g) * 1.2 + 0.04
+        payload = {"latent": lat.transpose(0, 1).contiguous() if as_dt else lat, "vae_path": "x"} if i != 3 else lat
+        p = tmp_path / "lat" / f"sub{i % 2}" / f"l{i}.pt"
+        p.parent.mkdir(parents=True, exist_ok=True)
+        torch.save(payload, str(p))
+        files.append(str(p))
+    files = sorted(files)
+    mean, std = compute_latent_stats.latent_stats(files, "cuda", reduce_dim=True)
+    rm, rs = _ref_latent_stats(files, True)
+    assert abs(mean - float(rm)) < 1e-6 and abs(std - float(rs)) < 1e-6
+    mean_d, std_d = compute_latent_stats.latent_stats(files, "cuda", reduce_dim=False)
+    rm, rs = _ref_latent_stats(files, False)
+    assert tuple(mean_d.shape) == (128,) and mean_d.dtype == torch.float32
+    assert float((mean_d.double() - rm).abs().max()) < 1e-6 and float((std_d.double() - rs).abs().max()) < 1e-6
+    out = tmp_path / "latent_stats.pt"
+    compute_latent_stats.main(["--latent_dir", str(tmp_path / "lat"), "--per_dim", "--out", str(out)])
+    saved = torch.load(str(out))
+    assert set(saved) == {"mean", "std"} and tuple(saved["mean"].shape) == (128,)           # the reference's only on-disk stats layout
+    compute_latent_stats.main(["--latent_dir", str(tmp_path / "lat")])
+    lines = capsys.readouterr().out.strip().splitlines()
+    assert lines[-2] == f"latent_mean: {mean:.6f}" and lines[-1] == f"latent_std : {std:.6f}"

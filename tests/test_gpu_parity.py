@@ -405,3 +405,24 @@ def test_long_clip_60s_and_determinism(fe):
     assert tuple(a.shape) == (2, 80, 3752) and torch.equal(a, b)                        # run-to-run bit-identical
     ref = oracle_mel(fe, x[1].cpu().numpy(), pad=4)
     assert float(np.max(np.abs(a[1].cpu().numpy() - ref))) < EXPECT
+
+
+def test_fuzz_shapes_against_oracle(fe):
+    """Seeded sweep over lengths (tile and hop boundaries +-1), batch sizes, pad-to-4, layouts and the fused peak normalisation."""
+    rng = np.random.default_rng(2024)
+    lengths = [513, 514, 767, 768, 1023, 1024, 1025, 2047, 2048, 2049, 2303, 2304, 2559, 2560, 2561, 4095, 4096, 6143, 6144, 6145]
+    lengths += [int(x) for x in rng.integers(513, 40000, size=12)]
+    for k, L in enumerate(lengths):
+        B = int(rng.integers(1, 4))
+        pad = 4 if k % 2 else 1
+        layout = "time_major" if k % 3 == 0 else "mel_major"
+        use_peak = k % 4 == 1
+        x = np.stack([o.synth_clip(L, 3000 + 7 * k + i) * (0.2 + 0.7 * i) for i in range(B)])
+        xd = dev(x)
+        y = fe.forward(xd, pad_multiple=pad, layout=layout, peak=fe.peak_abs(xd) if use_peak else None)
+        y = (y.transpose(1, 2) if layout == "time_major" else y).cpu().numpy()
+        for i in range(B):
+            w = o.process_audio_chunk(x[i][None])[0] if use_peak else x[i]
+            ref = oracle_mel(fe, w, pad=pad)
+            assert y[i].shape == ref.shape, (L, pad)
+            assert float(np.max(np.abs(y[i] - ref))) < EXPECT, (L, B, pad, layout, use_peak)
