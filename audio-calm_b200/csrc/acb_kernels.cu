@@ -646,6 +646,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         else {
             group_sync(grp);  // warps without a frame pair (tail of a clip) take part in the same barrier
         }
+        // the mel phase's per-lane constants are loaded one round ahead; the first record's latency hides behind the barrier
+        const int4* my_rec = s_rec + (gw * kMaxRounds) * kSlots + q;
+        int4 rec_next = my_rec[0];
         group_sync(grp);  // power spectra of the group's pairs visible; sample tile is free again
 
         // prefetch the next tile's samples while the mel phase runs
@@ -669,10 +672,12 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
             OutT* out_clip = reinterpret_cast<OutT*>(p.out) + cur.out_base;
             const bool pair_store = ((cur.cap & 1) == 0) && ((reinterpret_cast<uintptr_t>(out_clip) & (2 * sizeof(OutT) - 1)) == 0);
             for (int r = 0; r < kMaxRounds; ++r) {
-                const int4 rec = s_rec[(gw * kMaxRounds + r) * kSlots + q];
+                const int4 rec = rec_next;
                 const int trip = rec.w;
                 if (trip == 0) break;  // warp-uniform; rounds are filled in order
+                if (r + 1 < kMaxRounds) rec_next = my_rec[(r + 1) * kSlots];
                 const int b = rec.z;
+                const float2 af = s_aff[b < 0 ? 0 : b];   // issued early: needed only after the log
                 const float4* p4 = reinterpret_cast<const float4*>(pair_scratch) + rec.x;   // two bins x (A, B)
                 const float2* w2 = reinterpret_cast<const float2*>(s_pw) + rec.y;
                 float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
@@ -718,7 +723,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
                     }
                 }
                 if (b >= 0) {
-                    const float2 af = s_aff[b];
                     vA = fmaf(vA, af.x, af.y);
                     vB = fmaf(vB, af.x, af.y);
                     if (direct) {
