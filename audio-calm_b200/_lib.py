@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "acb_plan_tiles", "acb_frontend_create", "acb_frontend_destroy", "acb_moments_workspace_bytes",
     "acb_logmel_forward", "acb_peak_abs", "acb_process_audio_chunk", "acb_moments_accumulate",
     "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host", "acb_crop_pad", "acb_pad_transpose",
-    "acb_moments_accumulate_workspace_bytes",
+    "acb_moments_accumulate_workspace_bytes", "acb_pcm16_to_float", "acb_logmel_forward_host_pcm16",
 ]
 
 
@@ -161,6 +161,10 @@ def load() -> ctypes.CDLL:
         lib.acb_pad_transpose.argtypes = [vp, i32, vp, vp, i32, i32, vp, i64, f32, vp, vp, vp]
         lib.acb_logmel_forward_host.restype = ctypes.c_int
         lib.acb_logmel_forward_host.argtypes = [vp, vp, i32, i64, vp, ctypes.POINTER(LogmelArgs), vp, vp, i32, vp]
+        lib.acb_pcm16_to_float.restype = ctypes.c_int
+        lib.acb_pcm16_to_float.argtypes = [vp, vp, i64, vp]
+        lib.acb_logmel_forward_host_pcm16.restype = ctypes.c_int
+        lib.acb_logmel_forward_host_pcm16.argtypes = [vp, vp, i32, i64, vp, ctypes.POINTER(LogmelArgs), vp, vp, vp, i32, vp]
         if lib.acb_abi_version() != 1:
             raise RuntimeError(f"{LIB_PATH}: ABI version {lib.acb_abi_version()} != 1; rebuild")
         _lib = lib

@@ -934,6 +934,28 @@ __global__ void __launch_bounds__(128) normalize_rows_kernel(const float* __rest
 }
 
 // --------------------------------------------------------------------------------------------
+// 16-bit PCM transport: int16 samples -> fp32 in [-1, 1) exactly as torchaudio.load(normalize=True) scales them (x / 32768)
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pcm16_to_float_kernel(const short* __restrict__ in, float* __restrict__ out, long long n, float scale) {
+    const long long n8 = ((reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) ? n / 8 : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long i = t0; i < n8; i += stride) {   // 16 bytes in, 32 bytes out per thread and step
+        const int4 v = __ldg(reinterpret_cast<const int4*>(in) + i);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            f[2 * k] = (float)(short)(w[k] & 0xffff) * scale;
+            f[2 * k + 1] = (float)(w[k] >> 16) * scale;
+        }
+        float4* o = reinterpret_cast<float4*>(out) + 2 * i;
+        o[0] = make_float4(f[0], f[1], f[2], f[3]);
+        o[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    for (long long i = n8 * 8 + t0; i < n; i += stride) out[i] = (float)in[i] * scale;
+}
+
+// --------------------------------------------------------------------------------------------
 // training-feed collation of stored features (train/train_vae.py:83-116, train/train_calm.py:205-215)
 // --------------------------------------------------------------------------------------------
 template <typename T>
@@ -1478,8 +1500,19 @@ int acb_pad_transpose(const void* feat_tm, int32_t dtype, const int64_t* row_off
     return ACB_OK;
 }
 
-int acb_logmel_forward_host(const acb_frontend* fe_c, const float* wav_host, int32_t n_clips, int64_t length, void* out_host,
-                            acb_logmel_args* tmpl, float* dev_in, void* dev_out, int32_t n_chunks, void* stream) {
+int acb_pcm16_to_float(const int16_t* pcm, float* out, int64_t n, void* stream) {
+    if (n <= 0) return ACB_OK;
+    if (!pcm || !out) return fail(ACB_ERR_INVALID, "acb_pcm16_to_float: null argument");
+    const int blocks = (int)std::min<int64_t>(148 * 8, (n / 8 + 255) / 256 + 1);
+    pcm16_to_float_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(pcm, out, n, 1.0f / 32768.0f);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
+// Shared body of the host-buffer paths.  dev_pcm == nullptr: wav_host holds fp32 samples; otherwise int16 PCM that is staged in
+// dev_pcm and widened on the device (half the bytes over PCIe).
+static int forward_host_impl(const acb_frontend* fe_c, const void* wav_host, int32_t n_clips, int64_t length, void* out_host,
+                             acb_logmel_args* tmpl, int16_t* dev_pcm, float* dev_in, void* dev_out, int32_t n_chunks, void* stream) {
     if (!fe_c || !wav_host || !out_host || !tmpl || !dev_in || !dev_out) return fail(ACB_ERR_INVALID, "acb_logmel_forward_host: null argument");
     if (n_clips <= 0) return ACB_OK;
     auto* fe = const_cast<acb_frontend*>(fe_c);
@@ -1511,10 +1544,20 @@ int acb_logmel_forward_host(const acb_frontend* fe_c, const float* wav_host, int
     for (int c = 0; c < n_chunks && rc == ACB_OK; ++c) {
         const int c0 = (int)((int64_t)n_clips * c / n_chunks), c1 = (int)((int64_t)n_clips * (c + 1) / n_chunks);
         if (c1 == c0) continue;
-        ACB_CUDA(cudaMemcpyAsync(dev_in + (int64_t)c0 * length, wav_host + (int64_t)c0 * length, sizeof(float) * (size_t)(c1 - c0) * length,
-                                 cudaMemcpyHostToDevice, fe->s_in));
+        const size_t n_samples = (size_t)(c1 - c0) * length;
+        if (dev_pcm) {
+            ACB_CUDA(cudaMemcpyAsync(dev_pcm + (int64_t)c0 * length, static_cast<const int16_t*>(wav_host) + (int64_t)c0 * length,
+                                     sizeof(int16_t) * n_samples, cudaMemcpyHostToDevice, fe->s_in));
+        } else {
+            ACB_CUDA(cudaMemcpyAsync(dev_in + (int64_t)c0 * length, static_cast<const float*>(wav_host) + (int64_t)c0 * length,
+                                     sizeof(float) * n_samples, cudaMemcpyHostToDevice, fe->s_in));
+        }
         ACB_CUDA(cudaEventRecord(fe->ev[2 * c], fe->s_in));
         ACB_CUDA(cudaStreamWaitEvent(st, fe->ev[2 * c], 0));
+        if (dev_pcm) {
+            rc = acb_pcm16_to_float(dev_pcm + (int64_t)c0 * length, dev_in + (int64_t)c0 * length, (int64_t)n_samples, st);
+            if (rc != ACB_OK) break;
+        }
         acb_logmel_args a = *tmpl;
         a.wav = dev_in + (int64_t)c0 * length;
         a.clip_offset = nullptr; a.clip_length = nullptr; a.tile_start = nullptr;
@@ -1540,6 +1583,17 @@ int acb_logmel_forward_host(const acb_frontend* fe_c, const float* wav_host, int
     if (e2 != cudaSuccess) return cuda_fail(e2, "acb_logmel_forward_host sync");
     if (e3 != cudaSuccess) return cuda_fail(e3, "acb_logmel_forward_host sync");
     return ACB_OK;
+}
+
+int acb_logmel_forward_host(const acb_frontend* fe, const float* wav_host, int32_t n_clips, int64_t length, void* out_host,
+                            acb_logmel_args* tmpl, float* dev_in, void* dev_out, int32_t n_chunks, void* stream) {
+    return forward_host_impl(fe, wav_host, n_clips, length, out_host, tmpl, nullptr, dev_in, dev_out, n_chunks, stream);
+}
+
+int acb_logmel_forward_host_pcm16(const acb_frontend* fe, const int16_t* pcm_host, int32_t n_clips, int64_t length, void* out_host,
+                                  acb_logmel_args* tmpl, int16_t* dev_pcm, float* dev_in, void* dev_out, int32_t n_chunks, void* stream) {
+    if (!dev_pcm) return fail(ACB_ERR_INVALID, "acb_logmel_forward_host_pcm16: null staging buffer");
+    return forward_host_impl(fe, pcm_host, n_clips, length, out_host, tmpl, dev_pcm, dev_in, dev_out, n_chunks, stream);
 }
 
 }  // extern "C"

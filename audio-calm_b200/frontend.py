@@ -297,11 +297,17 @@ class LogMelFrontend:
     # ------------------------------------------------------------------ host-buffer path (pinned memory in/out)
     def forward_host(self, wav_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, *, out_dtype=torch.float32,
                      pad_multiple: int = 1, affine: Affine = None, n_chunks: int = 8,
-                     staging: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+                     staging: Optional[Tuple[torch.Tensor, ...]] = None) -> torch.Tensor:
         """Host ``wav[B, L]`` (pinned for full speed) -> host ``[B, n_mels, T4]``: chunked H2D copy, fused kernel and
-        D2H copy overlapped on three streams inside ``acb_logmel_forward_host``."""
-        if wav_host.is_cuda or wav_host.dtype != torch.float32 or wav_host.dim() != 2 or not wav_host.is_contiguous():
-            raise ValueError("forward_host expects a contiguous host float32 [B, L] tensor")
+        D2H copy overlapped on three streams inside ``acb_logmel_forward_host``.
+
+        ``wav_host`` is float32 (what the reference moves, process_dataset.py:135-140) or **int16 PCM**: 16-bit samples are
+        widened on the device to ``x / 32768`` -- the exact values ``torchaudio.load`` yields for 16-bit files -- so the result is
+        bit-identical while the host->device traffic, which bounds this path, halves.
+        ``staging``: optional device buffers ``(wav fp32 [B, L], out [B, n_mels, T4][, pcm int16 [B, L]])`` to reuse across calls."""
+        pcm = wav_host.dtype == torch.int16
+        if wav_host.is_cuda or wav_host.dtype not in (torch.float32, torch.int16) or wav_host.dim() != 2 or not wav_host.is_contiguous():
+            raise ValueError("forward_host expects a contiguous host float32 or int16 [B, L] tensor")
         B, L = int(wav_host.shape[0]), int(wav_host.shape[1])
         T4 = padded_frames(self.frames_for_length(L), pad_multiple)
         if out_host is None:
@@ -309,12 +315,29 @@ class LogMelFrontend:
         if staging is None:
             staging = (torch.empty((B, L), dtype=torch.float32, device=self.device),
                        torch.empty((B, self.n_mels, T4), dtype=out_host.dtype, device=self.device))
+        if pcm and len(staging) < 3:
+            staging = (staging[0], staging[1], torch.empty((B, L), dtype=torch.int16, device=self.device))
         a = LogmelArgs()
         a.frame_capacity = T4
         keep = self._fill_common(a, staging[1], "mel_major", pad_multiple, False, 0.0, affine, None, None)
-        _lib.check(self._lib.acb_logmel_forward_host(self._handle, wav_host.data_ptr(), B, L, out_host.data_ptr(), ctypes.byref(a),
-                                                     staging[0].data_ptr(), staging[1].data_ptr(), int(n_chunks),
-                                                     _stream_ptr(self.device)), "acb_logmel_forward_host")
-        self.launches += min(int(n_chunks), B)
+        if pcm:
+            _lib.check(self._lib.acb_logmel_forward_host_pcm16(self._handle, wav_host.data_ptr(), B, L, out_host.data_ptr(), ctypes.byref(a),
+                                                               staging[2].data_ptr(), staging[0].data_ptr(), staging[1].data_ptr(),
+                                                               int(n_chunks), _stream_ptr(self.device)), "acb_logmel_forward_host_pcm16")
+        else:
+            _lib.check(self._lib.acb_logmel_forward_host(self._handle, wav_host.data_ptr(), B, L, out_host.data_ptr(), ctypes.byref(a),
+                                                         staging[0].data_ptr(), staging[1].data_ptr(), int(n_chunks),
+                                                         _stream_ptr(self.device)), "acb_logmel_forward_host")
+        self.launches += min(int(n_chunks), B) * (2 if pcm else 1)
         del keep
         return out_host
+
+    def pcm16_to_float(self, pcm: torch.Tensor) -> torch.Tensor:
+        """Device int16 PCM -> float32 ``x / 32768`` (``acb_pcm16_to_float``), any shape."""
+        if not pcm.is_cuda or pcm.dtype != torch.int16:
+            raise RuntimeError("pcm16_to_float expects a device int16 tensor")
+        pcm = pcm.contiguous()
+        out = torch.empty(pcm.shape, dtype=torch.float32, device=pcm.device)
+        _lib.check(self._lib.acb_pcm16_to_float(pcm.data_ptr(), out.data_ptr(), pcm.numel(), _stream_ptr(pcm.device)), "acb_pcm16_to_float")
+        self.launches += 1
+        return out

@@ -168,6 +168,14 @@ int acb_logmel_forward_host(const acb_frontend* fe, const float* wav_host, int32
                             void* out_host, acb_logmel_args* args_template, float* dev_in, void* dev_out,
                             int32_t n_chunks, void* stream);
 
+/* 16-bit PCM transport (an extension: the reference moves fp32 over PCIe, preprocess/process_dataset.py:135-140).
+ * int16 samples are widened on the device to x / 32768, exactly the values torchaudio.load(normalize=True) produces for
+ * 16-bit files, so every result is bit-identical to the fp32 path; host->device traffic halves. */
+int acb_pcm16_to_float(const int16_t* pcm, float* out, int64_t n, void* stream);                       /* pcm, out: device */
+int acb_logmel_forward_host_pcm16(const acb_frontend* fe, const int16_t* pcm_host, int32_t n_clips, int64_t length,
+                                  void* out_host, acb_logmel_args* args_template, int16_t* dev_pcm, float* dev_in,
+                                  void* dev_out, int32_t n_chunks, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

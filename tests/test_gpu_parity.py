@@ -370,6 +370,22 @@ def _device_clips(n_clips, length, seed):
     return x
 
 
+def test_pcm16_transport_is_bit_identical(fe):
+    """int16 PCM in, widened on the device: same bits as the fp32 path fed with x / 32768 (torchaudio's int16 scaling)."""
+    rng = np.random.default_rng(7)
+    pcm = torch.from_numpy(rng.integers(-32768, 32768, size=(6, 24001), dtype=np.int16))
+    pcm[0, :5] = torch.tensor([-32768, 32767, 0, 1, -1], dtype=torch.int16)
+    xf = pcm.to(torch.float32) / 32768.0
+    assert torch.equal(fe.pcm16_to_float(pcm.cuda()).cpu(), xf)
+    for odd in (1, 3):                                                       # unaligned views take the scalar path
+        assert torch.equal(fe.pcm16_to_float(pcm.cuda().reshape(-1)[odd:odd + 1001]).cpu(), xf.reshape(-1)[odd:odd + 1001])
+    aff = (acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT)
+    a = fe.forward_host(xf.pin_memory(), affine=aff, pad_multiple=4, n_chunks=3)
+    b = fe.forward_host(pcm.pin_memory(), affine=aff, pad_multiple=4, n_chunks=3)
+    assert torch.equal(a, b)
+    assert torch.equal(a.cuda(), fe.forward(xf.cuda(), affine=aff, pad_multiple=4))
+
+
 def test_config2_batch_256x30s(fe):
     """batch 256 x 30 s -> normalised log-mel fp32: frame count exact, sampled clips within 1e-4 of the oracle,
     batch-independence, and the gain property ln-mel(2x) = ln-mel(x) + ln 4 away from the clamp."""
