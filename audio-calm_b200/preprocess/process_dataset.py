@@ -102,23 +102,32 @@ def transcript_for(wav_path: str, args, cv_mapping: Dict[str, str]) -> Optional[
 
 
 def load_audio(path: str) -> torch.Tensor:
-    """Decode + resample to 16 kHz on the host: ``[C, L]`` float32 (process_dataset.py:135-137).  I/O, not on the hot path."""
+    """Decode (+ resample to 16 kHz) on the host: ``[C, L]`` (process_dataset.py:135-137).  I/O, not on the hot path.
+
+    16-bit files that already are 16 kHz come back as **int16**: the driver ships them as PCM (half the PCIe bytes) and widens them
+    on the device to ``x / 32768`` -- exactly what ``torchaudio.load`` (normalize=True) would have produced.  Everything else is float32."""
     try:
         import torchaudio
-        wav, sr = torchaudio.load(path)
+        wav, sr = torchaudio.load(path, normalize=False)
     except Exception:  # noqa: BLE001 - torchaudio without a decoding backend: plain PCM .wav through scipy
         from scipy.io import wavfile
         import numpy as np
         sr, data = wavfile.read(path)
-        if data.dtype.kind == "i":
-            data = data.astype(np.float32) / float(1 << (8 * data.dtype.itemsize - 1))
-        elif data.dtype.kind == "u":
-            data = (data.astype(np.float32) - 128.0) / 128.0
-        wav = torch.from_numpy(np.atleast_2d(data.astype(np.float32).T if data.ndim == 2 else data.astype(np.float32)))
+        wav = torch.from_numpy(np.ascontiguousarray(np.atleast_2d(data.T if data.ndim == 2 else data)))
+    if wav.dtype == torch.int16 and sr == TARGET_SR:
+        return wav.contiguous()
+    if wav.dtype == torch.int16:
+        wav = wav.to(torch.float32) / 32768.0
+    elif wav.dtype == torch.int32:
+        wav = wav.to(torch.float32) / 2147483648.0
+    elif wav.dtype == torch.uint8:
+        wav = (wav.to(torch.float32) - 128.0) / 128.0
+    else:
+        wav = wav.to(torch.float32)
     if sr != TARGET_SR:
         import torchaudio
         wav = torchaudio.transforms.Resample(sr, TARGET_SR)(wav)
-    return wav.float()
+    return wav
 
 
 # ------------------------------------------------------------------------------------------- the per-GPU engine
@@ -149,6 +158,8 @@ class ShardRunner:
             clips, prenormalised = [], []
             for i, (_, _, _, wav) in enumerate(items):
                 w = wav.to(self.device, non_blocking=True)
+                if w.dtype == torch.int16:
+                    w = self.fe.pcm16_to_float(w)          # 16-bit PCM transport, widened on the device
                 if w.shape[0] == 1:
                     clips.append(w[0])
                 else:

@@ -67,8 +67,14 @@ def test_load_audio_pcm_wav(tmp_path):
     x = (o.hash_noise(4000, 3) * 30000).astype(np.int16)
     wavfile.write(str(tmp_path / "a.wav"), 16000, x)
     w = pd.load_audio(str(tmp_path / "a.wav"))
-    assert w.dtype == torch.float32 and tuple(w.shape) == (1, 4000)
-    assert np.allclose(w.numpy()[0], x.astype(np.float32) / 32768.0, atol=1e-7)
+    assert tuple(w.shape) == (1, 4000)
+    if w.dtype == torch.int16:                                # 16 kHz 16-bit files travel as PCM and are widened on the device
+        assert np.array_equal(w.numpy()[0], x)
+    else:
+        assert w.dtype == torch.float32 and np.allclose(w.numpy()[0], x.astype(np.float32) / 32768.0, atol=1e-7)
+    wavfile.write(str(tmp_path / "b.wav"), 16000, (x.astype(np.float32) / 32768.0))
+    wf = pd.load_audio(str(tmp_path / "b.wav"))
+    assert wf.dtype == torch.float32 and np.allclose(wf.numpy()[0], x.astype(np.float32) / 32768.0, atol=1e-7)
 
 
 def test_iter_files_generators(tmp_path):
@@ -90,6 +96,10 @@ def test_driver_mel_only_matches_reference_pipeline(tmp_path):
     for rel, x in clips.items():
         _write_wav(str(root / rel), x)
     _write_wav(str(root / "s2/c3/short.wav"), o.hash_noise(300, 26))                                  # too short: reported, not fatal
+    from scipy.io import wavfile
+    pcm = (o.synth_clip(30000, 27) * 32767).astype(np.int16)                                          # a 16-bit PCM file: shipped as int16
+    wavfile.write(str(root / "s2/c3/u5.wav"), 16000, pcm)
+    clips["s2/c3/u5.wav"] = pcm.astype(np.float32) / 32768.0
     args = _args(in_dir=str(root), out_dir=str(out))
     runner = pd.ShardRunner(args, 0, batch_samples=70000, decode_threads=2)                           # forces several ragged launches
     runner.run(pd.scan_files(str(root)))
