@@ -104,3 +104,24 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _lib.load()
+
+
+def test_product_package_never_touches_the_oracle_or_a_cpu_fallback():
+    """The oracle is test infrastructure: nothing under audio-calm_b200/ may import it, and the arithmetic entry points must
+    refuse CPU tensors instead of falling back."""
+    import re
+    pkg = os.path.join(ROOT, "audio-calm_b200")
+    offenders = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", src, re.M) or "ref_torch_port" in src or "logmel_oracle" in src:
+                    offenders.append(os.path.join(dirpath, f))
+    assert not offenders, offenders
+    import torch
+    from audio_calm_b200.preprocess.core import MelExtractor
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MelExtractor()(torch.zeros(1, 4000))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        acb.LogMelFrontend("cpu")
