@@ -5,6 +5,8 @@ The directory name carries a hyphen (it is mandated by the build contract), so t
 directory as that package.  Layout:
 
     csrc/acb_kernels.cu      hand-written CUDA kernels + the extern "C" ABI (include/audiocalm_b200.h)
+    csrc/acb_dftgemm.cu      tensor-core route: STFT as a split-fp16 DFT-GEMM on tcgen05 (Whisper-style preset)
+    whisper.py               WhisperLogMel: WhisperFeatureExtractor-compatible features on that route
     _lib.py                  nvcc build + ctypes binding (fails loudly when the .so is missing)
     tables.py                window / slaney filterbank, bit-identical to the reference's torch tables
     frontend.py              LogMelFrontend: batched + ragged launches, fused peak-norm / affine / moments
@@ -19,7 +21,9 @@ from .frontend import (LogMelFrontend, MEL_MEAN_DEFAULT, MEL_STD_DEFAULT, Ragged
 from .stats import MelStats, MelStatsAccumulator, finalize_moments  # noqa: F401
 from . import collate, frontend, stats, sharding  # noqa: F401
 from .collate import crop_collate, pad_collate, pad_collate_packed  # noqa: F401
+from . import whisper  # noqa: F401
+from .whisper import WhisperLogMel, whisper_tables  # noqa: F401
 
 __all__ = ["LogMelFrontend", "MelStatsAccumulator", "MelStats", "RaggedBatch", "pack_clips", "frames_for_length",
-           "padded_frames", "finalize_moments", "MEL_MEAN_DEFAULT", "MEL_STD_DEFAULT"]
+           "padded_frames", "finalize_moments", "MEL_MEAN_DEFAULT", "MEL_STD_DEFAULT", "WhisperLogMel", "whisper_tables"]
 __version__ = "0.1.0"

@@ -18,7 +18,7 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_NAME = "libaudiocalm_b200.so"
 LIB_PATH = os.path.join(CSRC, LIB_NAME)
-SOURCES = ["acb_kernels.cu"]
+SOURCES = ["acb_kernels.cu", "acb_dftgemm.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = [
     "acb_logmel_forward", "acb_peak_abs", "acb_process_audio_chunk", "acb_moments_accumulate",
     "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host", "acb_crop_pad", "acb_pad_transpose",
     "acb_moments_accumulate_workspace_bytes", "acb_pcm16_to_float", "acb_logmel_forward_host_pcm16",
+    "acb_dftgemm_frames", "acb_dftgemm_create", "acb_dftgemm_destroy", "acb_dftgemm_forward", "acb_dftgemm_check",
 ]
 
 
@@ -74,6 +75,25 @@ class LogmelArgs(ctypes.Structure):
         ("bin_std", ctypes.c_void_p),
         ("moments", ctypes.c_void_p),
         ("moments_workspace", ctypes.c_void_p),
+    ]
+
+
+class DftGemmArgs(ctypes.Structure):
+    """Mirror of ``struct acb_dftgemm_args`` (include/audiocalm_b200.h)."""
+    _fields_ = [
+        ("wav", ctypes.c_void_p),
+        ("clip_stride", ctypes.c_int64),
+        ("length", ctypes.c_int64),
+        ("n_clips", ctypes.c_int32),
+        ("drop_last_frame", ctypes.c_int32),
+        ("out", ctypes.c_void_p),
+        ("out_clip_stride", ctypes.c_int64),
+        ("frame_capacity", ctypes.c_int64),
+        ("dyn_range", ctypes.c_float),
+        ("affine", ctypes.c_int32),
+        ("affine_mean", ctypes.c_float),
+        ("affine_std", ctypes.c_float),
+        ("clip_max", ctypes.c_void_p),
     ]
 
 
@@ -165,6 +185,17 @@ def load() -> ctypes.CDLL:
         lib.acb_pcm16_to_float.argtypes = [vp, vp, i64, vp]
         lib.acb_logmel_forward_host_pcm16.restype = ctypes.c_int
         lib.acb_logmel_forward_host_pcm16.argtypes = [vp, vp, i32, i64, vp, ctypes.POINTER(LogmelArgs), vp, vp, vp, i32, vp]
+        lib.acb_dftgemm_frames.restype = i64
+        lib.acb_dftgemm_frames.argtypes = [i64, ctypes.c_int]
+        lib.acb_dftgemm_create.restype = ctypes.c_int
+        lib.acb_dftgemm_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           vp, vp, f32, ctypes.c_int]
+        lib.acb_dftgemm_destroy.restype = ctypes.c_int
+        lib.acb_dftgemm_destroy.argtypes = [vp]
+        lib.acb_dftgemm_forward.restype = ctypes.c_int
+        lib.acb_dftgemm_forward.argtypes = [vp, ctypes.POINTER(DftGemmArgs), vp]
+        lib.acb_dftgemm_check.restype = ctypes.c_int
+        lib.acb_dftgemm_check.argtypes = [vp, vp]
         if lib.acb_abi_version() != 1:
             raise RuntimeError(f"{LIB_PATH}: ABI version {lib.acb_abi_version()} != 1; rebuild")
         _lib = lib

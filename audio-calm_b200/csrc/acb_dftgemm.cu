@@ -1,0 +1,721 @@
+// B200 (sm_100a) tensor-core route of the log-mel front-end: STFT as a DFT-GEMM on tcgen05 with split-fp16 operands.
+//
+// This is the "Whisper-style" preset BASELINE.json's north star words the path as (n_fft 400, hop 160, 80-band bank of
+// models/mel_filters.npz, log10 with clamp, max-8 dynamic-range floor, (x + 4) / 4) -- what the reference runs inside the Hugging
+// Face ASR pipeline that scores its TTS output (eval/eval_calm.py:548-552 -> transformers.WhisperFeatureExtractor).  The
+// reference's own extractor (preprocess/core.py, n_fft 1024) stays on the CUDA-core FFT kernel in acb_kernels.cu: DESIGN.md
+// section 3.1 measures why a DFT-GEMM loses there.  At n_fft = 400 the GEMM is 6.5x smaller per frame and wins.
+//
+// Math (one frame x[0..399], periodic symmetric window w[n] = w[400-n], xw = w * x, indices mod 400):
+//   s[n] = xw[n] + xw[n+200], d[n] = xw[n] - xw[n+200]                      (radix-2 split: even / odd bins)
+//   se[n] = s[n] + s[200-n], so[n] = s[n] - s[200-n], de[n] = d[n] - d[200-n], do[n] = d[n] + d[200-n],  n = 0..100
+//   Re X[2m]   =  sum_n c_n se[n] cos(2 pi m n / 200)          Im X[2m]   = -sum_n so[n] sin(2 pi m n / 200)
+//   Re X[2m+1] =  sum_n c_n de[n] cos(2 pi (2m+1) n / 400)     Im X[2m+1] = -sum_n c_n do[n] sin(2 pi (2m+1) n / 400)
+//   (c_n = 1/2 on the self-paired rows n = 0 / 100, folded into the matrices.)
+// Four real GEMMs  D_g[128 frames x 112] = A_g[128 x 112] * B_g[112 x 112]^T  replace a 400 x 402 DFT: 4x fewer flops.
+// fp32 accuracy from fp16 tensor cores: A = A_hi + A_lo, B = B_hi + B_lo (fp16 pairs, 22 significant bits),
+// D = A_hi B_hi + A_lo B_hi + A_hi B_lo accumulated in fp32 in TMEM (measured 2e-6 on the final features).
+//
+// Kernel (persistent, one CTA of 256 threads per SM, tiles of 128 frames of one clip):
+//   1. the tile's samples are staged in shared memory by bulk async copies (one per 160-sample hop block, rows padded to 164
+//      floats so a warp's 16-byte loads of 32 different frames are conflict-free); edge tiles are gathered with reflection;
+//   2. K loop, 7 steps of 16: all threads build the step's A slices (window, folds, fp16 hi/lo split) in the canonical
+//      K-major no-swizzle core-matrix layout, the step's B slices (28 KB) arrive by one bulk copy from L2, one thread issues
+//      12 tcgen05.mma (M 128, N 112, K 16) and commits to an mbarrier; A/B are double-buffered so the MMAs of step k run under
+//      the CUDA-core work of step k+1;
+//   3. epilogue: thread = frame row; tcgen05.ld 16 columns of each accumulator, |X|^2 in registers, a streaming banded mel
+//      projection (every bin feeds at most two consecutive bands: two running accumulators, bands are emitted in order),
+//      clamp, log, coalesced stores (32 consecutive frames of one band per warp), per-clip max by atomicMax.  The two halves
+//      of the CTA take bins [0, 96) and [96, 201); the two bands that straddle the cut are exchanged through shared memory.
+//   4. a second, HBM-bound kernel applies the dynamic-range floor (per-clip max - 8) and the affine (x + 4) / 4.
+#include "audiocalm_b200.h"
+
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace acb {
+extern thread_local std::string g_last_error;
+}
+
+namespace acbg {
+
+constexpr int kNfft = 400;
+constexpr int kHop = 160;
+constexpr int kBinsAll = 201;
+constexpr int kTileFrames = 128;
+constexpr int kThreads = 256;
+constexpr int kKpad = 112;                       // K of every GEMM (n = 0..100 used)
+constexpr int kNpad = 112;                       // N of every GEMM (m = 0..100 used)
+constexpr int kKsteps = kKpad / 16;              // 7
+constexpr int kGemms = 4;
+constexpr int kBlocks = kTileFrames + 3;         // hop blocks staged per tile
+constexpr int kPitch = 164;                      // floats per staged hop block
+constexpr int kSampleFloats = kBlocks * kPitch;  // 21484
+constexpr int kASliceBytes = 2 * kTileFrames * 16;            // two k-halves x 128 rows x 8 halves
+constexpr int kAStageBytes = kGemms * 2 * kASliceBytes;       // 32768
+constexpr int kBSliceBytes = kNpad * 16 * 2;                  // 3584
+constexpr int kBStageBytes = kGemms * 2 * kBSliceBytes;       // 28672
+constexpr int kProgBins = 224;                   // 7 chunks of 32 bins
+constexpr int kSplitChunk = 3;                   // lower half: chunks [0, 3) = bins [0, 96); upper half: chunks [3, 7)
+constexpr int kTmemCols = 512;
+constexpr int kMaxMels = 128;
+
+// shared memory carve-up (bytes)
+constexpr int kOffSamples = 0;
+constexpr int kOffA = (kSampleFloats * 4 + 127) & ~127;       // 85952
+constexpr int kOffB = kOffA + 2 * kAStageBytes;               // +65536
+constexpr int kOffWin = kOffB + 2 * kBStageBytes;             // +57344
+constexpr int kOffProg = kOffWin + 2 * kKpad * 4;
+constexpr int kOffXchg = kOffProg + kProgBins * 16;
+constexpr int kOffBar = kOffXchg + 2 * kTileFrames * 4;
+constexpr int kSmemBytes = kOffBar + 64;
+static_assert(kOffWin % 16 == 0 && kOffProg % 16 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+static int fail(int code, const std::string& msg) {
+    acb::g_last_error = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    acb::g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+    return ACB_ERR_CUDA;
+}
+#define ACBG_CUDA(call)                                       \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------------
+// device helpers: mbarrier, bulk copy, tcgen05
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded wait: a wrong descriptor or a lost completion must not hang the GPU box.  Returns false after ~2^26 polls.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (int spin = 0; spin < (1 << 26) && !ok; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor: 8-row x 16-byte core matrices (rows 16 bytes apart);
+// lbo = byte distance between core matrices adjacent in K, sbo = between 8-row groups (validated on B200 by
+// tools/microbench/umma_hankel.cu).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version of sm_100
+    return d;
+}
+// kind::f16 instruction descriptor: D = f32 (bit 4), A = B = fp16 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
+    uint32_t u[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+                   "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ float lg2_normal(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// order-preserving int key of a float (atomicMax on ints)
+__device__ __forceinline__ int float_key(float v) {
+    const int b = __float_as_int(v);
+    return b >= 0 ? b : (b ^ 0x7fffffff);
+}
+__host__ __device__ __forceinline__ float key_float(int k) {
+    const int b = k >= 0 ? k : (k ^ 0x7fffffff);
+#ifdef __CUDA_ARCH__
+    return __int_as_float(b);
+#else
+    float f;
+    std::memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+struct Params {
+    // tables (device)
+    const uint8_t* b_slices;   // [kKsteps][kGemms][2][kBSliceBytes] fp16 DFT matrices, core-matrix layout
+    const float* win_fwd;      // [112] w[n] (0 beyond n = 100)
+    const float* win_rev;      // [112] w[200 - n] (0 beyond n = 100)
+    const float4* prog;        // [224] per bin: (w0, w1, emit code, 0)
+    int band_split;            // first unfinished band at the cut between the two epilogue halves
+    int n_mels;
+    float clamp_min, log_scale, log_floor;
+    // batch
+    const float* wav;
+    long long clip_stride;
+    long long length;
+    int n_clips;
+    int tiles_per_clip;
+    int frames_out;            // frames stored per clip
+    // output
+    float* out;
+    long long out_clip_stride;
+    long long frame_capacity;
+    int* clip_max;             // [n_clips] ordered-int keys, or nullptr
+    int* error_flag;           // set to 1 when a barrier wait timed out
+};
+
+// A-operand values of one thread for one K step: 8 consecutive n of its frame row, for the 4 GEMMs
+struct Fold8 {
+    float se[8], so[8], de[8], dd[8];
+};
+
+__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// split 8 fp32 values into fp16 (hi, lo) and store them as one 16-byte core-matrix row each
+__device__ __forceinline__ void split_store(const float (&v)[8], uint8_t* dst_hi, uint8_t* dst_lo) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
+        const __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
+        hi[i] = pack_half2(h0, h1);
+        lo[i] = pack_half2(l0, l1);
+    }
+    *reinterpret_cast<uint4*>(dst_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// staged float index of linear position `lin` (= 160 * row + 120 + n) with padded hop blocks
+__device__ __forceinline__ int staged_index(int lin) {
+    const int blk = lin / kHop;
+    return blk * kPitch + (lin - blk * kHop);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* s_samples = reinterpret_cast<float*>(smem + kOffSamples);
+    uint8_t* s_a = smem + kOffA;
+    uint8_t* s_b = smem + kOffB;
+    float* s_wf = reinterpret_cast<float*>(smem + kOffWin);
+    float* s_wr = s_wf + kKpad;
+    const float4* s_prog = reinterpret_cast<const float4*>(smem + kOffProg);
+    float* s_xchg = reinterpret_cast<float*>(smem + kOffXchg);
+    const uint32_t bar_base = smem_u32(smem + kOffBar);
+    const uint32_t bar_smp = bar_base, bar_bfull0 = bar_base + 8, bar_mma0 = bar_base + 24, bar_tile = bar_base + 40;
+    uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 48);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row = ((warp & 3) << 5) | lane;     // frame row of the tile = TMEM lane
+    const int hsel = warp >> 2;                   // prep: k-half of the K step; epilogue: bin range
+
+    // ---- one-time setup ----
+    for (int i = tid; i < kKpad; i += kThreads) { s_wf[i] = p.win_fwd[i]; s_wr[i] = p.win_rev[i]; }
+    for (int i = tid; i < kProgBins; i += kThreads) reinterpret_cast<float4*>(smem + kOffProg)[i] = p.prog[i];
+    if (tid == 0) {
+        mbar_init(bar_smp, 1);
+        mbar_init(bar_bfull0, 1);
+        mbar_init(bar_bfull0 + 8, 1);
+        mbar_init(bar_mma0, 1);
+        mbar_init(bar_mma0 + 8, 1);
+        mbar_init(bar_tile, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem_slot)), "r"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem_slot;
+    const uint32_t idesc = make_idesc_f16(kTileFrames, kNpad);
+
+    const int n_tiles = p.n_clips * p.tiles_per_clip;
+    uint32_t gs = 0;            // global K-step counter (stage = gs & 1, use = gs >> 1)
+    uint32_t smp_uses = 0;      // completed phases of bar_smp
+    uint32_t tile_iter = 0;
+    bool ok = true;
+
+    // sample staging of one tile; returns true when the bulk-copy path was taken (then bar_smp completes a phase)
+    auto stage_samples = [&](int tile) -> bool {
+        const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
+        const float* src = p.wav + (long long)clip * p.clip_stride;
+        const long long g0 = (long long)(tic * kTileFrames - 2) * kHop;     // clip sample held by staged block 0, offset 0
+        const bool interior = g0 >= 0 && g0 + (long long)kBlocks * kHop <= p.length && ((reinterpret_cast<uintptr_t>(src + g0) & 15) == 0);
+        if (interior) {
+            if (warp == 0) {
+                if (lane == 0) mbar_arrive_expect_tx(bar_smp, kBlocks * kHop * 4);
+                __syncwarp();
+                for (int j = lane; j < kBlocks; j += 32)
+                    bulk_copy_g2s(smem_u32(s_samples + j * kPitch), src + g0 + (long long)j * kHop, kHop * 4, bar_smp);
+            }
+            return true;
+        }
+        const long long L = p.length;
+        for (int i = tid; i < kBlocks * kHop; i += kThreads) {
+            const int j = i / kHop, o = i - j * kHop;
+            long long idx = g0 + i;
+            if (idx < 0) idx = -idx;                       // reflection about sample 0 (torch.stft center=True, pad_mode="reflect")
+            if (idx >= L) idx = 2 * (L - 1) - idx;         // and about sample L - 1
+            float v = 0.f;
+            if (idx >= 0 && idx < L) v = __ldg(src + idx);
+            s_samples[j * kPitch + o] = v;
+        }
+        return false;
+    };
+
+    int tile = blockIdx.x;
+    bool smp_async = false;
+    if (tile < n_tiles) smp_async = stage_samples(tile);
+
+    for (; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+        const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
+        if (smp_async) {
+            ok = mbar_wait(bar_smp, smp_uses & 1) && ok;
+            ++smp_uses;
+        } else {
+            __syncthreads();   // gathered samples visible
+        }
+
+        // ================= K loop: build A slices, stream B slices, issue MMAs =================
+        const float* srow = s_samples;   // + staged_index(160 * row + 120 + n)
+        for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
+            const uint32_t st = gs & 1u, use = gs >> 1;
+            if (gs >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;   // MMAs that read this stage are complete
+            if (tid == 0) {
+                mbar_arrive_expect_tx(bar_bfull0 + 8 * st, kBStageBytes);
+                bulk_copy_g2s(smem_u32(s_b + st * kBStageBytes), p.b_slices + (size_t)ks * kBStageBytes, kBStageBytes, bar_bfull0 + 8 * st);
+            }
+            // ---- this thread's 8 values of n: n0 .. n0 + 7 ----
+            const int n0 = 16 * ks + 8 * hsel;
+            const int base = kHop * row + 120;
+            float xa[8], xc[8], xb[8], xe[8];
+            {
+                const float* pa = srow + staged_index(base + n0);              // x[n0 .. n0+7]
+                const float* pc = srow + staged_index(base + 200 + n0);        // x[200+n0 .. 200+n0+7]
+                const float4 a0 = *reinterpret_cast<const float4*>(pa), a1 = *reinterpret_cast<const float4*>(pa + 4);
+                const float4 c0 = *reinterpret_cast<const float4*>(pc), c1 = *reinterpret_cast<const float4*>(pc + 4);
+                xa[0] = a0.x; xa[1] = a0.y; xa[2] = a0.z; xa[3] = a0.w; xa[4] = a1.x; xa[5] = a1.y; xa[6] = a1.z; xa[7] = a1.w;
+                xc[0] = c0.x; xc[1] = c0.y; xc[2] = c0.z; xc[3] = c0.w; xc[4] = c1.x; xc[5] = c1.y; xc[6] = c1.z; xc[7] = c1.w;
+                // x[200 - n0 - i] and x[400 - n0 - i], i = 0..7: the aligned group of 8 below plus one element above
+                const float* pb = srow + staged_index(base + 192 - n0);        // x[192-n0 .. 199-n0]
+                const float* pb8 = srow + staged_index(base + 200 - n0);       // x[200-n0]
+                const float4 b0 = *reinterpret_cast<const float4*>(pb), b1 = *reinterpret_cast<const float4*>(pb + 4);
+                xb[0] = *pb8; xb[1] = b1.w; xb[2] = b1.z; xb[3] = b1.y; xb[4] = b1.x; xb[5] = b0.w; xb[6] = b0.z; xb[7] = b0.y;
+                const float* pe = srow + staged_index(base + 392 - n0);        // x[392-n0 .. 399-n0]
+                const float* pe8 = srow + staged_index(base + (n0 == 0 ? 0 : 400 - n0));   // x[400-n0], index taken mod 400
+                const float4 e0 = *reinterpret_cast<const float4*>(pe), e1 = *reinterpret_cast<const float4*>(pe + 4);
+                xe[0] = *pe8; xe[1] = e1.w; xe[2] = e1.z; xe[3] = e1.y; xe[4] = e1.x; xe[5] = e0.w; xe[6] = e0.z; xe[7] = e0.y;
+            }
+            Fold8 f;
+            {
+                const float4 wf0 = *reinterpret_cast<const float4*>(s_wf + n0), wf1 = *reinterpret_cast<const float4*>(s_wf + n0 + 4);
+                const float4 wr0 = *reinterpret_cast<const float4*>(s_wr + n0), wr1 = *reinterpret_cast<const float4*>(s_wr + n0 + 4);
+                const float wa[8] = {wf0.x, wf0.y, wf0.z, wf0.w, wf1.x, wf1.y, wf1.z, wf1.w};
+                const float wb[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float pa = wa[i] * xa[i], pe = wa[i] * xe[i];      // w[400-n] = w[n]
+                    const float pb = wb[i] * xb[i], pc = wb[i] * xc[i];      // w[200+n] = w[200-n]
+                    const float sn = pa + pc, sr = pb + pe, dn = pa - pc, dr = pb - pe;
+                    f.se[i] = sn + sr;
+                    f.so[i] = sn - sr;
+                    f.de[i] = dn - dr;
+                    f.dd[i] = dn + dr;
+                }
+            }
+            {
+                uint8_t* dst = s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16;
+                split_store(f.se, dst + 0 * kASliceBytes, dst + 1 * kASliceBytes);
+                split_store(f.so, dst + 2 * kASliceBytes, dst + 3 * kASliceBytes);
+                split_store(f.de, dst + 4 * kASliceBytes, dst + 5 * kASliceBytes);
+                split_store(f.dd, dst + 6 * kASliceBytes, dst + 7 * kASliceBytes);
+            }
+            fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
+            __syncthreads();
+            if (tid == 0) {
+                ok = mbar_wait(bar_bfull0 + 8 * st, use & 1u) && ok;   // B slices of this step have landed
+                tc_fence_after();
+                const uint32_t a_base = smem_u32(s_a + st * kAStageBytes), b_base = smem_u32(s_b + st * kBStageBytes);
+#pragma unroll
+                for (int g = 0; g < kGemms; ++g) {
+                    const uint64_t a_hi = make_desc(a_base + (2 * g) * kASliceBytes, kTileFrames * 16, 128);
+                    const uint64_t a_lo = make_desc(a_base + (2 * g + 1) * kASliceBytes, kTileFrames * 16, 128);
+                    const uint64_t b_hi = make_desc(b_base + (2 * g) * kBSliceBytes, 128, 256);
+                    const uint64_t b_lo = make_desc(b_base + (2 * g + 1) * kBSliceBytes, 128, 256);
+                    const uint32_t d = tmem + (uint32_t)(g * kNpad);
+                    mma_f16_ss(d, a_hi, b_hi, idesc, ks > 0);
+                    mma_f16_ss(d, a_lo, b_hi, idesc, 1);
+                    mma_f16_ss(d, a_hi, b_lo, idesc, 1);
+                }
+                mma_commit(bar_mma0 + 8 * st);
+                if (ks == kKsteps - 1) mma_commit(bar_tile);
+            }
+        }
+        // every thread is past its last read of the sample tile (the barrier of the last K step): prefetch the next tile
+        const int next_tile = tile + gridDim.x;
+        const bool next_async = next_tile < n_tiles ? stage_samples(next_tile) : false;
+
+        // ================= epilogue: |X|^2, streaming banded mel, log, store =================
+        ok = mbar_wait(bar_tile, tile_iter & 1u) && ok;
+        tc_fence_after();
+        {
+            const int frame = tic * kTileFrames + row;
+            const bool valid = frame < p.frames_out;
+            float* out_col = p.out + (long long)clip * p.out_clip_stride + frame;
+            const uint32_t t_row = tmem + ((uint32_t)((warp & 3) << 5) << 16);
+            float acc0 = 0.f, acc1 = 0.f, vmax = -3.0e38f;
+            int band = hsel ? p.band_split : 0;
+            int xslot = 0;
+            const int c_begin = hsel ? kSplitChunk : 0, c_end = hsel ? kKsteps : kSplitChunk;
+            auto emit_global = [&](float m, int b) {
+                const float v = (m > p.clamp_min) ? lg2_normal(m) * p.log_scale : p.log_floor;
+                if (valid) {
+                    out_col[(long long)b * p.frame_capacity] = v;
+                    vmax = fmaxf(vmax, v);
+                }
+            };
+            for (int c = c_begin; c < c_end; ++c) {
+                float d0[16], d1[16], d2[16], d3[16];
+                tmem_ld16(t_row + (uint32_t)(0 * kNpad + 16 * c), d0);
+                tmem_ld16(t_row + (uint32_t)(1 * kNpad + 16 * c), d1);
+                tmem_ld16(t_row + (uint32_t)(2 * kNpad + 16 * c), d2);
+                tmem_ld16(t_row + (uint32_t)(3 * kNpad + 16 * c), d3);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float re = (i & 1) ? d2[i >> 1] : d0[i >> 1];
+                    const float im = (i & 1) ? d3[i >> 1] : d1[i >> 1];
+                    const float pw = fmaf(re, re, im * im);
+                    const float4 pg = s_prog[32 * c + i];
+                    acc0 = fmaf(pg.x, pw, acc0);
+                    acc1 = fmaf(pg.y, pw, acc1);
+                    const int code = __float_as_int(pg.z);
+                    if (code != 0) {     // uniform over the CTA half
+                        const int n_emit = code & 3;
+                        for (int e = 0; e < n_emit; ++e) {
+                            if (code & (4 << e)) {       // a band that straddles the cut: hand the partial sum to the lower half
+                                s_xchg[xslot * kTileFrames + row] = acc0;
+                                if (++xslot == 2) asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
+                            } else {
+                                emit_global(acc0, band);
+                            }
+                            acc0 = acc1;
+                            acc1 = 0.f;
+                            ++band;
+                        }
+                    }
+                }
+            }
+            if (hsel == 0) {   // the two bands open at the cut: add the upper half's partial sums and emit them
+                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+                emit_global(acc0 + s_xchg[row], band);
+                if (band + 1 < p.n_mels) emit_global(acc1 + s_xchg[kTileFrames + row], band + 1);
+            }
+            if (p.clip_max) {
+#pragma unroll
+                for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+                if (lane == 0 && vmax > -3.0e38f) atomicMax(p.clip_max + clip, float_key(vmax));
+            }
+        }
+        tc_fence_before();
+        __syncthreads();      // TMEM and the exchange buffer are free for the next tile
+        tc_fence_after();
+        smp_async = next_async;
+    }
+
+    if (!ok && p.error_flag) atomicExch(p.error_flag, 1);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
+}
+
+// Dynamic-range floor and affine of the stored features (WhisperFeatureExtractor: maximum(x, max - 8), then (x + 4) / 4).
+__global__ void __launch_bounds__(256) dftgemm_finalize_kernel(float* __restrict__ out, long long out_clip_stride, long long frame_capacity,
+                                                               int n_mels, int frames, const int* __restrict__ clip_max, float dyn_range,
+                                                               float scale, float shift) {
+    const int clip = blockIdx.y;
+    float* base = out + (long long)clip * out_clip_stride;
+    const float floor_v = clip_max ? key_float(clip_max[clip]) - dyn_range : -3.0e38f;
+    const long long n = (long long)n_mels * frames;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / frames, t = i - b * frames;
+        float* q = base + b * frame_capacity + t;
+        *q = fmaf(fmaxf(*q, floor_v), scale, shift);
+    }
+}
+
+}  // namespace acbg
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+struct acb_dftgemm {
+    int device = 0;
+    int n_mels = 0;
+    int log_kind = 0;
+    float clamp_min = 0.f;
+    int num_sms = 0;
+    int band_split = 0;
+    void* d_blob = nullptr;
+    const uint8_t* d_b = nullptr;
+    const float* d_wf = nullptr;
+    const float* d_wr = nullptr;
+    const float4* d_prog = nullptr;
+    int* d_err = nullptr;
+};
+
+using namespace acbg;
+
+static uint16_t half_bits(float v) {
+    const __half h = __float2half_rn(v);
+    uint16_t u;
+    std::memcpy(&u, &h, 2);
+    return u;
+}
+static float half_value(uint16_t u) {
+    __half h;
+    std::memcpy(&h, &u, 2);
+    return __half2float(h);
+}
+
+extern "C" {
+
+int64_t acb_dftgemm_frames(int64_t length, int drop_last_frame) {
+    if (length <= kNfft / 2) return -1;
+    return 1 + length / kHop - (drop_last_frame ? 1 : 0);
+}
+
+int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_mels, const float* window_host, const float* fb_host,
+                       float clamp_min, int log_kind) {
+    if (!out || !window_host || !fb_host) return fail(ACB_ERR_INVALID, "acb_dftgemm_create: null argument");
+    if (n_fft != kNfft || hop != kHop)
+        return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: the tensor-core route is built for n_fft=400, hop=160 (got n_fft=" +
+                                             std::to_string(n_fft) + ", hop=" + std::to_string(hop) + ")");
+    if (n_mels < 2 || n_mels > kMaxMels) return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: n_mels must be in [2, 128]");
+    if (log_kind != ACB_LOG_NATURAL && log_kind != ACB_LOG_10) return fail(ACB_ERR_INVALID, "acb_dftgemm_create: bad log_kind");
+    if (!(clamp_min >= 1.17549435e-38f)) return fail(ACB_ERR_INVALID, "acb_dftgemm_create: clamp_min must be a positive normal float");
+    // the folds need w[n] == w[400 - n]
+    for (int n = 1; n < kNfft / 2; ++n)
+        if (std::fabs(window_host[n] - window_host[kNfft - n]) > 1e-6f * std::fmax(1.f, std::fabs(window_host[n])))
+            return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: the window is not symmetric (w[n] != w[n_fft - n])");
+
+    // ---- DFT matrices, fp16 (hi, lo), [ks][g][hi/lo] slices in the K-major no-swizzle core-matrix layout ----
+    std::vector<uint8_t> bsl((size_t)kKsteps * kBStageBytes, 0);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int g = 0; g < kGemms; ++g)
+        for (int m = 0; m < kNpad; ++m)
+            for (int n = 0; n < kKpad; ++n) {
+                double v = 0.0;
+                if (g == 0 && m <= 100 && n <= 100) v = std::cos(two_pi * ((m * n) % 200) / 200.0) * ((n == 0 || n == 100) ? 0.5 : 1.0);
+                if (g == 1 && m <= 100 && n >= 1 && n <= 99) v = std::sin(two_pi * ((m * n) % 200) / 200.0);
+                if (g == 2 && m <= 99 && n <= 99) v = std::cos(two_pi * (((2 * m + 1) * n) % 400) / 400.0) * (n == 0 ? 0.5 : 1.0);
+                if (g == 3 && m <= 99 && n >= 1 && n <= 100) v = std::sin(two_pi * (((2 * m + 1) * n) % 400) / 400.0) * (n == 100 ? 0.5 : 1.0);
+                const float vf = (float)v;
+                const uint16_t hi = half_bits(vf);
+                const uint16_t lo = half_bits((float)(v - (double)half_value(hi)));
+                const int ks = n / 16, kk = n % 16;
+                const size_t off = (size_t)(m / 8) * 256 + (size_t)(kk / 8) * 128 + (size_t)(m % 8) * 16 + (size_t)(kk % 8) * 2;
+                uint8_t* s_hi = bsl.data() + (size_t)ks * kBStageBytes + (size_t)(2 * g) * kBSliceBytes + off;
+                uint8_t* s_lo = bsl.data() + (size_t)ks * kBStageBytes + (size_t)(2 * g + 1) * kBSliceBytes + off;
+                std::memcpy(s_hi, &hi, 2);
+                std::memcpy(s_lo, &lo, 2);
+            }
+
+    // ---- window halves ----
+    std::vector<float> wf(kKpad, 0.f), wr(kKpad, 0.f);
+    for (int n = 0; n <= 100; ++n) { wf[n] = window_host[n]; wr[n] = window_host[200 - n]; }
+
+    // ---- streaming mel program: every bin feeds at most the two bands (j0, j0 + 1); bands are emitted in order ----
+    std::vector<int> last(n_mels, -1);
+    for (int b = 0; b < n_mels; ++b)
+        for (int k = 0; k < kBinsAll; ++k)
+            if (fb_host[(size_t)k * n_mels + b] != 0.f) last[b] = k;
+    for (int b = 0; b < n_mels; ++b)
+        if (last[b] < 0) last[b] = b ? last[b - 1] : 0;      // an all-zero band is emitted right after its predecessor
+    for (int b = 1; b < n_mels; ++b)
+        if (last[b] < last[b - 1]) return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: filterbank bands are not ordered by frequency");
+    std::vector<float> prog((size_t)kProgBins * 4, 0.f);
+    int j0 = 0, band_split = -1;
+    const int split_bin = kSplitChunk * 32;
+    for (int k = 0; k < kProgBins; ++k) {
+        if (k == split_bin) band_split = j0;
+        float w0 = 0.f, w1 = 0.f;
+        if (k < kBinsAll) {
+            for (int b = 0; b < n_mels; ++b) {
+                const float w = fb_host[(size_t)k * n_mels + b];
+                if (w == 0.f) continue;
+                if (b == j0) w0 = w;
+                else if (b == j0 + 1) w1 = w;
+                else return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: filterbank bin " + std::to_string(k) +
+                                                          " feeds bands other than two consecutive ones (band " + std::to_string(b) + ")");
+            }
+        }
+        int n_emit = 0, code = 0;
+        while (j0 < n_mels && n_emit < 2 && (last[j0] <= k || k == kProgBins - 1)) {
+            // the first two bands finished by the upper half are the ones open at the cut: they go through the exchange buffer
+            if (k >= split_bin && band_split >= 0 && j0 < band_split + 2) code |= 4 << n_emit;
+            ++j0;
+            ++n_emit;
+        }
+        code |= n_emit;
+        prog[(size_t)k * 4 + 0] = w0;
+        prog[(size_t)k * 4 + 1] = w1;
+        std::memcpy(&prog[(size_t)k * 4 + 2], &code, 4);
+    }
+    if (j0 != n_mels) return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: filterbank does not fit the streaming mel program");
+    if (band_split < 0 || band_split + 2 > n_mels)
+        return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: fewer than two bands above bin 96");
+    // the lower half must not have emitted past band_split + 0 before the cut, and the exchange needs both bands finished above it
+    // (guaranteed by construction: band_split is the first unfinished band at bin 96).
+
+    acb_dftgemm* fe = new acb_dftgemm();
+    fe->device = device;
+    fe->n_mels = n_mels;
+    fe->log_kind = log_kind;
+    fe->clamp_min = clamp_min;
+    fe->band_split = band_split;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    auto bail = [&](int rc) { cudaSetDevice(prev); delete fe; return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(fail(ACB_ERR_CUDA, "acb_dftgemm_create: cudaSetDevice failed"));
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(ACB_ERR_CUDA, "acb_dftgemm_create: cudaGetDeviceProperties failed"));
+    if (prop.major != 10) return bail(fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: needs an sm_100 device (tcgen05)"));
+    fe->num_sms = prop.multiProcessorCount;
+    const size_t b_bytes = bsl.size(), w_bytes = kKpad * 4, p_bytes = prog.size() * 4;
+    const size_t total = b_bytes + 2 * w_bytes + p_bytes + 16;
+    if (cudaMalloc(&fe->d_blob, total) != cudaSuccess) return bail(fail(ACB_ERR_CUDA, "acb_dftgemm_create: cudaMalloc failed"));
+    uint8_t* d = static_cast<uint8_t*>(fe->d_blob);
+    fe->d_b = d;
+    fe->d_wf = reinterpret_cast<const float*>(d + b_bytes);
+    fe->d_wr = reinterpret_cast<const float*>(d + b_bytes + w_bytes);
+    fe->d_prog = reinterpret_cast<const float4*>(d + b_bytes + 2 * w_bytes);
+    fe->d_err = reinterpret_cast<int*>(d + b_bytes + 2 * w_bytes + p_bytes);
+    bool good = cudaMemcpy(d, bsl.data(), b_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+                cudaMemcpy(d + b_bytes, wf.data(), w_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+                cudaMemcpy(d + b_bytes + w_bytes, wr.data(), w_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+                cudaMemcpy(d + b_bytes + 2 * w_bytes, prog.data(), p_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+                cudaMemset(fe->d_err, 0, 16) == cudaSuccess &&
+                cudaFuncSetAttribute(dftgemm_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess;
+    if (!good) {
+        cudaFree(fe->d_blob);
+        return bail(fail(ACB_ERR_CUDA, std::string("acb_dftgemm_create: table upload failed: ") + cudaGetErrorString(cudaGetLastError())));
+    }
+    cudaSetDevice(prev);
+    *out = fe;
+    return ACB_OK;
+}
+
+int acb_dftgemm_destroy(acb_dftgemm* fe) {
+    if (!fe) return ACB_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(fe->device);
+    if (fe->d_blob) cudaFree(fe->d_blob);
+    cudaSetDevice(prev);
+    delete fe;
+    return ACB_OK;
+}
+
+int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* stream) {
+    if (!fe || !a) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: null argument");
+    if (!a->wav || !a->out) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: wav and out must be device pointers");
+    if (a->n_clips <= 0) return ACB_OK;
+    const int64_t T = acb_dftgemm_frames(a->length, a->drop_last_frame);
+    if (T < 0) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: clips of " + std::to_string(a->length) + " samples; reflect padding needs more than " + std::to_string(kNfft / 2));
+    if (T == 0) return ACB_OK;
+    if (a->frame_capacity < T) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: frame_capacity " + std::to_string(a->frame_capacity) + " < frames " + std::to_string(T));
+    if (a->clip_stride < a->length) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: clip_stride < length");
+    if (a->out_clip_stride < (int64_t)fe->n_mels * a->frame_capacity) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: out_clip_stride too small");
+    if (a->dyn_range > 0.f && !a->clip_max) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: dyn_range needs the clip_max workspace");
+    if (a->affine && !(a->affine_std != 0.f)) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: affine_std must be non-zero");
+    const int64_t tiles_per_clip = (T + kTileFrames - 1) / kTileFrames;
+    if (tiles_per_clip * a->n_clips > INT32_MAX) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: more than 2^31 tiles in one call");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+
+    Params p{};
+    p.b_slices = fe->d_b;
+    p.win_fwd = fe->d_wf;
+    p.win_rev = fe->d_wr;
+    p.prog = fe->d_prog;
+    p.band_split = fe->band_split;
+    p.n_mels = fe->n_mels;
+    p.clamp_min = fe->clamp_min;
+    p.log_scale = fe->log_kind == ACB_LOG_10 ? 0.30102999566398120f : 0.69314718055994531f;
+    p.log_floor = fe->log_kind == ACB_LOG_10 ? (float)std::log10((double)fe->clamp_min) : (float)std::log((double)fe->clamp_min);
+    p.wav = a->wav;
+    p.clip_stride = a->clip_stride;
+    p.length = a->length;
+    p.n_clips = a->n_clips;
+    p.tiles_per_clip = (int)tiles_per_clip;
+    p.frames_out = (int)T;
+    p.out = a->out;
+    p.out_clip_stride = a->out_clip_stride;
+    p.frame_capacity = a->frame_capacity;
+    p.clip_max = a->dyn_range > 0.f ? a->clip_max : nullptr;
+    p.error_flag = fe->d_err;
+    if (p.clip_max) ACBG_CUDA(cudaMemsetAsync(p.clip_max, 0x80, sizeof(int) * (size_t)a->n_clips, s));   // keys below every float
+    const int64_t n_tiles = tiles_per_clip * a->n_clips;
+    const int grid = (int)std::min<int64_t>(n_tiles, fe->num_sms);
+    dftgemm_logmel_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
+    ACBG_CUDA(cudaGetLastError());
+    if (p.clip_max || a->affine) {
+        const float scale = a->affine ? 1.f / a->affine_std : 1.f;
+        const float shift = a->affine ? -a->affine_mean / a->affine_std : 0.f;
+        const long long per_clip = (long long)fe->n_mels * T;
+        const int bx = (int)std::min<long long>((per_clip + 255) / 256, 64);
+        dftgemm_finalize_kernel<<<dim3(bx, a->n_clips), 256, 0, s>>>(a->out, a->out_clip_stride, a->frame_capacity, fe->n_mels, (int)T,
+                                                                     p.clip_max, a->dyn_range, scale, shift);
+        ACBG_CUDA(cudaGetLastError());
+    }
+    return ACB_OK;
+}
+
+int acb_dftgemm_check(const acb_dftgemm* fe, void* stream) {
+    if (!fe) return fail(ACB_ERR_INVALID, "acb_dftgemm_check: null handle");
+    int flag = 0;
+    ACBG_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    ACBG_CUDA(cudaMemcpy(&flag, fe->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(fe->d_err, 0, sizeof(int));
+        return fail(ACB_ERR_CUDA, "acb_dftgemm_check: a tensor-core pipeline barrier timed out inside the kernel (results are invalid)");
+    }
+    return ACB_OK;
+}
+
+}  // extern "C"

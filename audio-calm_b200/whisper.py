@@ -1,0 +1,143 @@
+"""Whisper-style log-mel features on the tensor-core route (DFT-as-GEMM on tcgen05; csrc/acb_dftgemm.cu).
+
+BASELINE.json's north star words the front-end as "Whisper-style": n_fft 400, hop 160, the 80-band bank of
+``models/mel_filters.npz``, ``log10(clamp(., 1e-10))``, the ``max - 8`` dynamic-range floor and ``(x + 4) / 4``.  In the reference
+that computation runs inside the Hugging Face ASR pipeline that scores generated speech (eval/eval_calm.py:548-552 ->
+``transformers.WhisperFeatureExtractor``); ``WhisperLogMel`` reproduces ``WhisperFeatureExtractor.__call__`` for fp32 waveforms
+on a CUDA device.  The reference's own extractor (``MelExtractor``, n_fft 1024) is ``LogMelFrontend``.
+
+There is no CPU fallback: construction needs a CUDA device and the built C-ABI library.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence, Union
+
+import torch
+
+from . import _lib
+from ._lib import ACB_LOG_10, ACB_LOG_NATURAL, DftGemmArgs
+from .tables import hann_window, slaney_fbanks
+
+WHISPER_N_FFT = 400
+WHISPER_HOP = 160
+WHISPER_N_MELS = 80
+WHISPER_CHUNK_SAMPLES = 480000      # 30 s at 16 kHz: WhisperFeatureExtractor pads / trims every clip to this
+MAX_ABS_SAMPLE = 4096.0             # fp16 operand range of the split-precision GEMM (audio is in [-1, 1])
+
+
+def whisper_tables(n_mels: int = WHISPER_N_MELS, sample_rate: int = 16000):
+    """(window ``[400]``, filterbank ``[201, n_mels]``) fp32: periodic Hann and the slaney-scale, slaney-normalised
+    triangular bank over 0-8000 Hz -- the published construction of ``models/mel_filters.npz`` (``mel_80``, stored
+    transposed there; tests compare the two to 1e-7)."""
+    return hann_window(WHISPER_N_FFT), slaney_fbanks(WHISPER_N_FFT // 2 + 1, 0.0, sample_rate / 2.0, n_mels, sample_rate)
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class WhisperLogMel:
+    """Device tables + launches of the tcgen05 DFT-GEMM front-end for one device.
+
+    ``forward(wav[B, L])`` -> ``[B, n_mels, L // 160]`` fp32, the ``input_features`` of ``WhisperFeatureExtractor`` for clips
+    already padded / trimmed to ``L`` samples; ``extract(clips)`` pads or trims to 30 s first, like ``__call__`` does.
+    """
+
+    def __init__(self, device: Union[str, torch.device, int] = "cuda", n_mels: int = WHISPER_N_MELS, clamp_min: float = 1e-10,
+                 log: str = "log10", dyn_range: float = 8.0, affine_mean: Optional[float] = -4.0, affine_std: float = 4.0,
+                 drop_last_frame: bool = True, window: Optional[torch.Tensor] = None, fb: Optional[torch.Tensor] = None):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("WhisperLogMel runs on a CUDA device (sm_100a, tcgen05); there is no CPU fallback")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
+        self.n_fft, self.hop, self.n_mels = WHISPER_N_FFT, WHISPER_HOP, n_mels
+        self.clamp_min, self.dyn_range = float(clamp_min), float(dyn_range)
+        self.affine_mean, self.affine_std = affine_mean, float(affine_std)
+        self.drop_last_frame = bool(drop_last_frame)
+        self.log_kind = {"ln": ACB_LOG_NATURAL, "log10": ACB_LOG_10}[log]
+        w0, f0 = whisper_tables(n_mels)
+        self.window = (w0 if window is None else window).detach().to("cpu", torch.float32).contiguous()
+        self.fb = (f0 if fb is None else fb).detach().to("cpu", torch.float32).contiguous()
+        if tuple(self.window.shape) != (self.n_fft,) or tuple(self.fb.shape) != (self.n_fft // 2 + 1, n_mels):
+            raise ValueError("window must be [400] and fb [201, n_mels]")
+        self._lib = _lib.load()
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self._lib.acb_dftgemm_create(ctypes.byref(handle), device.index, self.n_fft, self.hop, n_mels,
+                                                    self.window.data_ptr(), self.fb.data_ptr(), self.clamp_min, self.log_kind),
+                       "acb_dftgemm_create")
+        self._handle = handle
+        self._clip_max: Optional[torch.Tensor] = None
+        self.launches = 0
+
+    def __del__(self):
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                self._lib.acb_dftgemm_destroy(h)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+            self._handle = None
+
+    def frames_for_length(self, length: int) -> int:
+        t = int(self._lib.acb_dftgemm_frames(int(length), int(self.drop_last_frame)))
+        if t < 0:
+            raise RuntimeError(f"Argument #4: Padding size should be less than the corresponding input dimension, but got: "
+                               f"padding ({self.n_fft // 2}, {self.n_fft // 2}) at dimension 2 of input of length {length}")
+        return t
+
+    def forward(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None, check: bool = False) -> torch.Tensor:
+        """``wav`` fp32 CUDA ``[B, L]`` (rows may be strided) -> ``[B, n_mels, frames]`` fp32."""
+        if not wav.is_cuda or wav.device != self.device:
+            raise RuntimeError(f"expected a CUDA tensor on {self.device}, got {wav.device} (no CPU fallback)")
+        if wav.dtype != torch.float32:
+            raise RuntimeError(f"expected float32 samples, got {wav.dtype}")
+        if wav.dim() != 2 or wav.stride(1) != 1:
+            raise ValueError("wav must be [B, L] with unit stride along time")
+        n_clips, length = int(wav.shape[0]), int(wav.shape[1])
+        frames = self.frames_for_length(length)
+        if out is None:
+            out = torch.empty((n_clips, self.n_mels, frames), dtype=torch.float32, device=self.device)
+        if out.dtype != torch.float32 or out.device != self.device or tuple(out.shape[:2]) != (n_clips, self.n_mels) \
+                or out.shape[2] < frames or out.stride(2) != 1 or out.stride(1) != out.shape[2]:
+            raise ValueError("out must be a float32 [B, n_mels, >= frames] tensor with contiguous rows on the same device")
+        if n_clips == 0 or frames == 0:
+            return out[:, :, :frames]
+        a = DftGemmArgs()
+        a.wav = wav.data_ptr()
+        a.clip_stride = int(wav.stride(0)) if n_clips > 1 else length
+        a.length = length
+        a.n_clips = n_clips
+        a.drop_last_frame = int(self.drop_last_frame)
+        a.out = out.data_ptr()
+        a.out_clip_stride = int(out.stride(0)) if n_clips > 1 else self.n_mels * int(out.shape[2])
+        a.frame_capacity = int(out.shape[2])
+        a.dyn_range = self.dyn_range
+        a.affine = int(self.affine_mean is not None)
+        a.affine_mean = float(self.affine_mean or 0.0)
+        a.affine_std = self.affine_std
+        if self.dyn_range > 0:
+            if self._clip_max is None or self._clip_max.numel() < n_clips:
+                self._clip_max = torch.empty(max(n_clips, 256), dtype=torch.int32, device=self.device)
+            a.clip_max = self._clip_max.data_ptr()
+        stream = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.acb_dftgemm_forward(self._handle, ctypes.byref(a), stream), "acb_dftgemm_forward")
+            self.launches += 1 + int(self.dyn_range > 0 or self.affine_mean is not None)
+            if check:
+                _lib.check(self._lib.acb_dftgemm_check(self._handle, stream), "acb_dftgemm_check")
+        return out[:, :, :frames]
+
+    __call__ = forward
+
+    def extract(self, clips: Sequence[torch.Tensor], n_samples: int = WHISPER_CHUNK_SAMPLES, check: bool = False) -> torch.Tensor:
+        """``WhisperFeatureExtractor.__call__`` semantics: every clip is zero-padded or trimmed to ``n_samples`` (30 s) before the
+        STFT, so the result is ``[len(clips), n_mels, n_samples // 160]``."""
+        batch = torch.zeros((len(clips), n_samples), dtype=torch.float32, device=self.device)
+        for i, c in enumerate(clips):
+            c = c.reshape(-1)[:n_samples]
+            batch[i, : c.numel()] = c.to(self.device, torch.float32)
+        return self.forward(batch, check=check)

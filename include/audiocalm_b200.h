@@ -176,6 +176,47 @@ int acb_logmel_forward_host_pcm16(const acb_frontend* fe, const int16_t* pcm_hos
                                   void* out_host, acb_logmel_args* args_template, int16_t* dev_pcm, float* dev_in,
                                   void* dev_out, int32_t n_chunks, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Tensor-core route (DFT-as-GEMM on tcgen05, split-fp16 operands, fp32 accumulation in TMEM) for the "Whisper-style"
+ * preset BASELINE.json's north star names: n_fft 400, hop 160, reflect-padded centred frames, periodic Hann window,
+ * the 80-band bank of models/mel_filters.npz, log10(clamp(., 1e-10)), max - 8 dynamic-range floor, (x + 4) / 4.
+ * Replaces transformers.WhisperFeatureExtractor._np_extract_fbank_features, which the reference reaches through the
+ * Hugging Face ASR pipeline it scores generated speech with (eval/eval_calm.py:548-552); the reference's own extractor
+ * (preprocess/core.py, n_fft 1024) stays on acb_logmel_forward.  Input domain: |x| <= 4096 (fp16 operand range).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct acb_dftgemm acb_dftgemm; /* opaque: DFT matrices, window halves and the streaming mel program */
+
+/* Frames of one clip: 1 + L / 160 (torch.stft center=True), minus the last one when drop_last_frame (Whisper drops it:
+ * stft[..., :-1]); -1 when L <= 200 (reflect padding needs a longer input). */
+int64_t acb_dftgemm_frames(int64_t length, int drop_last_frame);
+
+/* window_host[400] (must be symmetric: w[n] == w[400 - n]) and fb_host[201 * n_mels] (row-major [freq][mel]; every bin may
+ * feed at most two consecutive bands, i.e. a triangular bank) as fp32.  Only n_fft = 400, hop = 160 is built. */
+int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_mels, const float* window_host,
+                       const float* fb_host, float clamp_min, int log_kind);
+int acb_dftgemm_destroy(acb_dftgemm* fe);
+
+typedef struct acb_dftgemm_args {
+    const float* wav;          /* device: n_clips uniform clips, clip i at wav + i * clip_stride (16-byte aligned rows take the bulk-copy path) */
+    int64_t clip_stride;       /* samples */
+    int64_t length;            /* samples per clip (Whisper pads / trims to 480000 on the host side) */
+    int32_t n_clips;
+    int32_t drop_last_frame;   /* !=0: store frames [0, L / 160) */
+    float* out;                /* device fp32 [n_clips][n_mels][frame_capacity] */
+    int64_t out_clip_stride;   /* elements */
+    int64_t frame_capacity;    /* >= frames */
+    float dyn_range;           /* > 0: out = max(out, max over the clip - dyn_range) (Whisper: 8.0); <= 0: none */
+    int32_t affine;            /* !=0: out = (out - affine_mean) / affine_std afterwards (Whisper: mean -4, std 4) */
+    float affine_mean;
+    float affine_std;
+    int32_t* clip_max;         /* device [n_clips] workspace, needed when dyn_range > 0 */
+} acb_dftgemm_args;
+
+/* One persistent tcgen05 launch (+ one elementwise launch when dyn_range / affine are set) on `stream`. */
+int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* args, void* stream);
+/* Synchronises `stream` and reports whether any in-kernel pipeline barrier timed out since the last check. */
+int acb_dftgemm_check(const acb_dftgemm* fe, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,115 @@
+"""GPU parity of the tensor-core route (tcgen05 DFT-GEMM, csrc/acb_dftgemm.cu) through the C ABI: against golden vectors minted
+from transformers.WhisperFeatureExtractor, against the fp64 oracle on seeded inputs, and size-independent properties at the
+benchmark size.  Tolerance (BASELINE.json north star): 1e-4 absolute in fp32; frame counts bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import audio_calm_b200 as acb
+from oracle import logmel_oracle as o
+from oracle import whisper_oracle as wo
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+EXPECT = 2e-5
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "whisper_cases.npz")
+
+
+@pytest.fixture(scope="module")
+def gw():
+    return np.load(GOLDEN)
+
+
+@pytest.fixture(scope="module")
+def fe():
+    return acb.WhisperLogMel("cuda")
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("name,x", [("noise_1s_s1", lambda: o.hash_noise(16000, 1)), ("synth_2s_s3", lambda: o.synth_clip(32000, 3)),
+                                    ("noise_odd_s4", lambda: o.hash_noise(20011, 4))])
+def test_golden_unpadded(fe, gw, name, x):
+    y = fe.forward(dev(x())[None], check=True)[0].cpu().numpy()
+    ref = gw[f"raw_{name}"]
+    assert y.shape == ref.shape
+    assert np.abs(y - ref).max() < EXPECT
+
+
+@pytest.mark.parametrize("name,x", [("noise_3s_s5", lambda: o.hash_noise(48000, 5)), ("synth_10s_s7", lambda: o.synth_clip(160000, 7)),
+                                    ("synth_30s_s9", lambda: o.synth_clip(480000, 9))])
+def test_golden_extract_30s(fe, gw, name, x):
+    y = fe.extract([dev(x())], check=True)[0].cpu().numpy()
+    assert y.shape == (80, 3000)
+    assert np.abs(y[:, ::7] - gw[f"full_{name}_sub7"]).max() < EXPECT
+    mn, mx, mean = gw[f"full_{name}_minmax"]
+    assert abs(y.min() - mn) < EXPECT and abs(y.max() - mx) < EXPECT and abs(float(y.astype(np.float64).mean()) - mean) < EXPECT
+
+
+def test_oracle_batch_mixed(fe):
+    """A batch whose clips differ (each has its own dynamic-range floor), rows strided, every edge/interior tile kind."""
+    L = 70000
+    xs = np.stack([o.synth_clip(L, 20 + i) * (0.02 if i == 2 else 1.0) for i in range(5)])
+    xs[3] = 0.0                                                     # an all-zero clip: every value on the clamp floor
+    big = torch.zeros((5, L + 24), device="cuda")
+    big[:, :L] = dev(xs)
+    y = fe.forward(big[:, :L], check=True).cpu().numpy()
+    assert y.shape == (5, 80, L // 160)
+    for i in range(5):
+        ref = wo.whisper_logmel(xs[i], fe.window.numpy(), fe.fb.numpy())
+        assert np.abs(y[i] - ref).max() < EXPECT, i
+    assert np.all(y[3] == np.float32((-10.0 + 4.0) / 4.0))
+
+
+@pytest.mark.parametrize("L", [201, 202, 359, 360, 400, 20479, 20480, 20481, 20640, 40961])
+def test_lengths_and_frame_counts(fe, L):
+    x = o.hash_noise(L, 100 + L % 97)
+    y = fe.forward(dev(x)[None], check=True)[0].cpu().numpy()
+    assert y.shape == (80, L // 160)
+    if y.shape[1]:
+        ref = wo.whisper_logmel(x, fe.window.numpy(), fe.fb.numpy())
+        assert np.abs(y - ref).max() < EXPECT
+
+
+def test_unaligned_rows_take_gather_path(fe):
+    L = 33333                                                       # odd row pitch: no 16-byte aligned bulk copies
+    xs = np.stack([o.hash_noise(L, 7), o.hash_noise(L, 8)])
+    y = fe.forward(dev(xs), check=True).cpu().numpy()
+    for i in range(2):
+        assert np.abs(y[i] - wo.whisper_logmel(xs[i], fe.window.numpy(), fe.fb.numpy())).max() < EXPECT
+
+
+def test_raw_log10_without_floor_or_affine():
+    fe2 = acb.WhisperLogMel("cuda", dyn_range=0.0, affine_mean=None, drop_last_frame=False)
+    x = o.synth_clip(48000, 31)
+    y = fe2.forward(dev(x)[None], check=True)[0].cpu().numpy()
+    ref = wo.whisper_logmel(x, fe2.window.numpy(), fe2.fb.numpy(), drop_last=False, dyn_range=None, affine=False)
+    assert y.shape == ref.shape == (80, 301)
+    assert np.abs(y - ref).max() < 4 * EXPECT          # un-normalised log10 units are 4x the feature units
+    assert y.min() == np.float32(-10.0)                 # the zero tail sits exactly on log10(1e-10)
+
+
+def test_too_short_raises(fe):
+    with pytest.raises(RuntimeError):
+        fe.forward(torch.zeros((1, 200), device="cuda"))
+    with pytest.raises(RuntimeError):
+        fe.forward(torch.zeros((1, 4000)))              # CPU tensor: no fallback
+
+
+def test_benchmark_size_properties(fe):
+    """64 x 30 s: shift invariance along the batch (same clip -> same features wherever it sits), agreement of a sampled clip with
+    the oracle, and determinism across launches."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn((64, 480000), device="cuda", generator=g) * 0.1
+    x[17] = x[3]
+    y1 = fe.forward(x, check=True)
+    y2 = fe.forward(x, check=True)
+    assert torch.equal(y1, y2)
+    assert torch.equal(y1[17], y1[3])
+    ref = wo.whisper_logmel(x[41].cpu().numpy(), fe.window.numpy(), fe.fb.numpy())
+    assert np.abs(y1[41].cpu().numpy() - ref).max() < EXPECT
+    assert y1.shape == (64, 80, 3000) and torch.isfinite(y1).all()
