@@ -65,6 +65,7 @@ constexpr int kProgBins = 224;                   // 7 chunks of 32 bins
 constexpr int kSplitChunk = 3;                   // lower half: chunks [0, 3) = bins [0, 96); upper half: chunks [3, 7)
 constexpr int kTmemCols = 512;
 constexpr int kMaxMels = 128;
+constexpr float kPrescale = 4096.f;                // power-of-two scale of the A operands (see acb_dftgemm_create)
 
 // shared memory carve-up (bytes)
 constexpr int kOffSamples = 0;
@@ -558,7 +559,10 @@ int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_
 
     // ---- window halves ----
     std::vector<float> wf(kKpad, 0.f), wr(kKpad, 0.f);
-    for (int n = 0; n <= 100; ++n) { wf[n] = window_host[n]; wr[n] = window_host[200 - n]; }
+    // The window carries a power-of-two pre-scale (exact): fp16's narrow exponent would push the lo halves of quiet audio into the
+    // subnormal range (absolute precision 2^-24); with x 4096 the split keeps 22 bits for amplitudes down to ~3e-5.  The
+    // 2^-24 on the power spectrum is folded into the mel weights (exact).  Operand range: 4 |x| 4096 < 65504, i.e. |x| < 3.99.
+    for (int n = 0; n <= 100; ++n) { wf[n] = window_host[n] * kPrescale; wr[n] = window_host[200 - n] * kPrescale; }
 
     // ---- streaming mel program: every bin feeds at most the two bands (j0, j0 + 1); bands are emitted in order ----
     std::vector<int> last(n_mels, -1);
@@ -593,8 +597,8 @@ int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_
             ++n_emit;
         }
         code |= n_emit;
-        prog[(size_t)k * 4 + 0] = w0;
-        prog[(size_t)k * 4 + 1] = w1;
+        prog[(size_t)k * 4 + 0] = w0 / (kPrescale * kPrescale);
+        prog[(size_t)k * 4 + 1] = w1 / (kPrescale * kPrescale);
         std::memcpy(&prog[(size_t)k * 4 + 2], &code, 4);
     }
     if (j0 != n_mels) return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: filterbank does not fit the streaming mel program");

@@ -23,7 +23,7 @@ WHISPER_N_FFT = 400
 WHISPER_HOP = 160
 WHISPER_N_MELS = 80
 WHISPER_CHUNK_SAMPLES = 480000      # 30 s at 16 kHz: WhisperFeatureExtractor pads / trims every clip to this
-MAX_ABS_SAMPLE = 4096.0             # fp16 operand range of the split-precision GEMM (audio is in [-1, 1])
+MAX_ABS_SAMPLE = 2.0                # fp16 operand range of the split-precision GEMM after its 2^12 pre-scale (audio is in [-1, 1])
 
 
 def whisper_tables(n_mels: int = WHISPER_N_MELS, sample_rate: int = 16000):

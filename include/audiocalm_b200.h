@@ -182,7 +182,8 @@ int acb_logmel_forward_host_pcm16(const acb_frontend* fe, const int16_t* pcm_hos
  * the 80-band bank of models/mel_filters.npz, log10(clamp(., 1e-10)), max - 8 dynamic-range floor, (x + 4) / 4.
  * Replaces transformers.WhisperFeatureExtractor._np_extract_fbank_features, which the reference reaches through the
  * Hugging Face ASR pipeline it scores generated speech with (eval/eval_calm.py:548-552); the reference's own extractor
- * (preprocess/core.py, n_fft 1024) stays on acb_logmel_forward.  Input domain: |x| <= 4096 (fp16 operand range).
+ * (preprocess/core.py, n_fft 1024) stays on acb_logmel_forward.  Input domain: |x| <= 2 (fp16 operand range after the
+ * internal 2^12 pre-scale; audio is in [-1, 1]).
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct acb_dftgemm acb_dftgemm; /* opaque: DFT matrices, window halves and the streaming mel program */
 
