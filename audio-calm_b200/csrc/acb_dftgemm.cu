@@ -49,7 +49,9 @@ constexpr int kNfft = 400;
 constexpr int kHop = 160;
 constexpr int kBinsAll = 201;
 constexpr int kTileFrames = 128;
-constexpr int kThreads = 256;
+constexpr int kWorkerWarps = 8;
+constexpr int kWorkerThreads = kWorkerWarps * 32;   // thread = (frame row, k-half)
+constexpr int kThreads = kWorkerThreads + 32;      // + one MMA / bulk-copy issuer warp
 constexpr int kKpad = 112;                       // K of every GEMM (n = 0..100 used)
 constexpr int kNpad = 112;                       // N of every GEMM (m = 0..100 used)
 constexpr int kKsteps = kKpad / 16;              // 7
@@ -75,7 +77,7 @@ constexpr int kOffWin = kOffB + 2 * kBStageBytes;             // +57344
 constexpr int kOffProg = kOffWin + 2 * kKpad * 4;
 constexpr int kOffXchg = kOffProg + kProgBins * 16;
 constexpr int kOffBar = kOffXchg + 2 * kTileFrames * 4;
-constexpr int kSmemBytes = kOffBar + 64;
+constexpr int kSmemBytes = kOffBar + 96;
 static_assert(kOffWin % 16 == 0 && kOffProg % 16 == 0 && kOffBar % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
@@ -99,6 +101,12 @@ static int cuda_fail(cudaError_t e, const char* what) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void worker_sync() {   // named barrier of the 8 worker warps (barrier 0 is __syncthreads, 1 the band exchange)
+    asm volatile("bar.sync 2, %0;" ::"n"(256) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -206,15 +214,16 @@ __device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
     return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
 }
 
-// split 8 fp32 values into fp16 (hi, lo) and store them as one 16-byte core-matrix row each
+// split 8 fp32 values into fp16 (hi, lo) and store them as one 16-byte core-matrix row each (packed conversions: F2FP / HADD2.F32)
 __device__ __forceinline__ void split_store(const float (&v)[8], uint8_t* dst_hi, uint8_t* dst_lo) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-        const __half l0 = __float2half_rn(v[2 * i] - __half2float(h0)), l1 = __float2half_rn(v[2 * i + 1] - __half2float(h1));
-        hi[i] = pack_half2(h0, h1);
-        lo[i] = pack_half2(l0, l1);
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
     }
     *reinterpret_cast<uint4*>(dst_hi) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(dst_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -226,6 +235,54 @@ __device__ __forceinline__ int staged_index(int lin) {
     return blk * kPitch + (lin - blk * kHop);
 }
 
+// One K step of A-operand construction for one thread: 8 consecutive n (n0 .. n0 + 7) of its frame row, for the 4 GEMMs.
+// `srow` = the staged samples, `base` = 160 * row + 120 (linear staged position of the frame's sample 0).
+__device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, int base, int n0, const float* __restrict__ s_wf,
+                                               const float* __restrict__ s_wr, uint8_t* dst) {
+    float xa[8], xc[8], xb[8], xe[8];
+    {
+        const float* pa = srow + staged_index(base + n0);              // x[n0 .. n0+7]
+        const float* pc = srow + staged_index(base + 200 + n0);        // x[200+n0 .. 200+n0+7]
+        const float4 a0 = *reinterpret_cast<const float4*>(pa), a1 = *reinterpret_cast<const float4*>(pa + 4);
+        const float4 c0 = *reinterpret_cast<const float4*>(pc), c1 = *reinterpret_cast<const float4*>(pc + 4);
+        xa[0] = a0.x; xa[1] = a0.y; xa[2] = a0.z; xa[3] = a0.w; xa[4] = a1.x; xa[5] = a1.y; xa[6] = a1.z; xa[7] = a1.w;
+        xc[0] = c0.x; xc[1] = c0.y; xc[2] = c0.z; xc[3] = c0.w; xc[4] = c1.x; xc[5] = c1.y; xc[6] = c1.z; xc[7] = c1.w;
+        // x[200 - n0 - i] and x[400 - n0 - i], i = 0..7: the aligned group of 8 below plus one element above
+        const float* pb = srow + staged_index(base + 192 - n0);        // x[192-n0 .. 199-n0]
+        const float* pb8 = srow + staged_index(base + 200 - n0);       // x[200-n0]
+        const float4 b0 = *reinterpret_cast<const float4*>(pb), b1 = *reinterpret_cast<const float4*>(pb + 4);
+        xb[0] = *pb8; xb[1] = b1.w; xb[2] = b1.z; xb[3] = b1.y; xb[4] = b1.x; xb[5] = b0.w; xb[6] = b0.z; xb[7] = b0.y;
+        const float* pe = srow + staged_index(base + 392 - n0);        // x[392-n0 .. 399-n0]
+        const float* pe8 = srow + staged_index(base + (n0 == 0 ? 0 : 400 - n0));   // x[400-n0], index taken mod 400
+        const float4 e0 = *reinterpret_cast<const float4*>(pe), e1 = *reinterpret_cast<const float4*>(pe + 4);
+        xe[0] = *pe8; xe[1] = e1.w; xe[2] = e1.z; xe[3] = e1.y; xe[4] = e1.x; xe[5] = e0.w; xe[6] = e0.z; xe[7] = e0.y;
+    }
+    Fold8 f;
+    {
+        const float4 wf0 = *reinterpret_cast<const float4*>(s_wf + n0), wf1 = *reinterpret_cast<const float4*>(s_wf + n0 + 4);
+        const float4 wr0 = *reinterpret_cast<const float4*>(s_wr + n0), wr1 = *reinterpret_cast<const float4*>(s_wr + n0 + 4);
+        const float wa[8] = {wf0.x, wf0.y, wf0.z, wf0.w, wf1.x, wf1.y, wf1.z, wf1.w};
+        const float wb[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float pa = wa[i] * xa[i], pe = wa[i] * xe[i];      // w[400-n] = w[n]
+            const float pb = wb[i] * xb[i], pc = wb[i] * xc[i];      // w[200+n] = w[200-n]
+            const float sn = pa + pc, sr = pb + pe, dn = pa - pc, dr = pb - pe;
+            f.se[i] = sn + sr;
+            f.so[i] = sn - sr;
+            f.de[i] = dn - dr;
+            f.dd[i] = dn + dr;
+        }
+    }
+    split_store(f.se, dst + 0 * kASliceBytes, dst + 1 * kASliceBytes);
+    split_store(f.so, dst + 2 * kASliceBytes, dst + 3 * kASliceBytes);
+    split_store(f.de, dst + 4 * kASliceBytes, dst + 5 * kASliceBytes);
+    split_store(f.dd, dst + 6 * kASliceBytes, dst + 7 * kASliceBytes);
+}
+
+// Warp roles: warps 0-7 ("workers", thread = frame row x k-half) stage samples, build the A slices and run the epilogue;
+// warp 8 (one elected lane) streams the B slices and issues the MMAs.  All hand-offs are mbarriers: no CTA-wide barrier sits
+// inside the K loop.
 __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* s_samples = reinterpret_cast<float*>(smem + kOffSamples);
@@ -236,12 +293,17 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
     const float4* s_prog = reinterpret_cast<const float4*>(smem + kOffProg);
     float* s_xchg = reinterpret_cast<float*>(smem + kOffXchg);
     const uint32_t bar_base = smem_u32(smem + kOffBar);
-    const uint32_t bar_smp = bar_base, bar_bfull0 = bar_base + 8, bar_mma0 = bar_base + 24, bar_tile = bar_base + 40;
-    uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 48);
+    const uint32_t bar_smp = bar_base;              // sample tile landed (bulk copies, tx count)
+    const uint32_t bar_bfull0 = bar_base + 8;       // [2] B slices of a stage landed (tx count)
+    const uint32_t bar_afull0 = bar_base + 24;      // [2] A slices of a stage written (8 worker warps)
+    const uint32_t bar_mma0 = bar_base + 40;        // [2] the MMAs reading a stage are complete (tcgen05.commit)
+    const uint32_t bar_tile = bar_base + 56;        // all MMAs of the tile complete: accumulators ready
+    const uint32_t bar_tfree = bar_base + 64;       // accumulators drained by the epilogue (8 worker warps)
+    uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 72);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int row = ((warp & 3) << 5) | lane;     // frame row of the tile = TMEM lane
-    const int hsel = warp >> 2;                   // prep: k-half of the K step; epilogue: bin range
+    const int row = ((warp & 3) << 5) | lane;     // frame row of the tile = TMEM lane (workers)
+    const int hsel = (warp >> 2) & 1;             // prep: k-half of the K step; epilogue: bin range
 
     // ---- one-time setup ----
     for (int i = tid; i < kKpad; i += kThreads) { s_wf[i] = p.win_fwd[i]; s_wr[i] = p.win_rev[i]; }
@@ -250,9 +312,12 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
         mbar_init(bar_smp, 1);
         mbar_init(bar_bfull0, 1);
         mbar_init(bar_bfull0 + 8, 1);
+        mbar_init(bar_afull0, kWorkerWarps);
+        mbar_init(bar_afull0 + 8, kWorkerWarps);
         mbar_init(bar_mma0, 1);
         mbar_init(bar_mma0 + 8, 1);
         mbar_init(bar_tile, 1);
+        mbar_init(bar_tfree, kWorkerWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -263,200 +328,179 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem_slot;
-    const uint32_t idesc = make_idesc_f16(kTileFrames, kNpad);
-
     const int n_tiles = p.n_clips * p.tiles_per_clip;
-    uint32_t gs = 0;            // global K-step counter (stage = gs & 1, use = gs >> 1)
-    uint32_t smp_uses = 0;      // completed phases of bar_smp
-    uint32_t tile_iter = 0;
     bool ok = true;
 
-    // sample staging of one tile; returns true when the bulk-copy path was taken (then bar_smp completes a phase)
-    auto stage_samples = [&](int tile) -> bool {
-        const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
-        const float* src = p.wav + (long long)clip * p.clip_stride;
-        const long long g0 = (long long)(tic * kTileFrames - 2) * kHop;     // clip sample held by staged block 0, offset 0
-        const bool interior = g0 >= 0 && g0 + (long long)kBlocks * kHop <= p.length && ((reinterpret_cast<uintptr_t>(src + g0) & 15) == 0);
-        if (interior) {
-            if (warp == 0) {
-                if (lane == 0) mbar_arrive_expect_tx(bar_smp, kBlocks * kHop * 4);
-                __syncwarp();
-                for (int j = lane; j < kBlocks; j += 32)
-                    bulk_copy_g2s(smem_u32(s_samples + j * kPitch), src + g0 + (long long)j * kHop, kHop * 4, bar_smp);
+    if (warp == kWorkerWarps) {
+        // ======================================= MMA / B-slice issuer =======================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(kTileFrames, kNpad);
+            uint32_t gs = 0, tile_iter = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+                for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
+                    const uint32_t st = gs & 1u, use = gs >> 1;
+                    if (gs >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;      // the stage's previous MMAs are complete
+                    mbar_arrive_expect_tx(bar_bfull0 + 8 * st, kBStageBytes);
+                    bulk_copy_g2s(smem_u32(s_b + st * kBStageBytes), p.b_slices + (size_t)ks * kBStageBytes, kBStageBytes, bar_bfull0 + 8 * st);
+                    if (ks == 0 && tile_iter > 0) ok = mbar_wait(bar_tfree, (tile_iter - 1) & 1u) && ok;   // accumulators drained
+                    ok = mbar_wait(bar_afull0 + 8 * st, use & 1u) && ok;
+                    ok = mbar_wait(bar_bfull0 + 8 * st, use & 1u) && ok;
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(s_a + st * kAStageBytes), b_base = smem_u32(s_b + st * kBStageBytes);
+#pragma unroll
+                    for (int g = 0; g < kGemms; ++g) {
+                        const uint64_t a_hi = make_desc(a_base + (2 * g) * kASliceBytes, kTileFrames * 16, 128);
+                        const uint64_t a_lo = make_desc(a_base + (2 * g + 1) * kASliceBytes, kTileFrames * 16, 128);
+                        const uint64_t b_hi = make_desc(b_base + (2 * g) * kBSliceBytes, 128, 256);
+                        const uint64_t b_lo = make_desc(b_base + (2 * g + 1) * kBSliceBytes, 128, 256);
+                        const uint32_t d = tmem + (uint32_t)(g * kNpad);
+                        mma_f16_ss(d, a_hi, b_hi, idesc, ks > 0);
+                        mma_f16_ss(d, a_lo, b_hi, idesc, 1);
+                        mma_f16_ss(d, a_hi, b_lo, idesc, 1);
+                    }
+                    mma_commit(bar_mma0 + 8 * st);
+                    if (ks == kKsteps - 1) mma_commit(bar_tile);
+                }
             }
-            return true;
         }
-        const long long L = p.length;
-        for (int i = tid; i < kBlocks * kHop; i += kThreads) {
-            const int j = i / kHop, o = i - j * kHop;
-            long long idx = g0 + i;
-            if (idx < 0) idx = -idx;                       // reflection about sample 0 (torch.stft center=True, pad_mode="reflect")
-            if (idx >= L) idx = 2 * (L - 1) - idx;         // and about sample L - 1
-            float v = 0.f;
-            if (idx >= 0 && idx < L) v = __ldg(src + idx);
-            s_samples[j * kPitch + o] = v;
-        }
-        return false;
-    };
+    } else {
+        // ================================================ workers ================================================
+        const int wtid = tid;                       // 0..255
+        uint32_t gs = 0, smp_uses = 0, tile_iter = 0;
+        const float clamp_min = p.clamp_min, log_scale = p.log_scale, log_floor = p.log_floor;
+        const long long cap = p.frame_capacity;
 
-    int tile = blockIdx.x;
-    bool smp_async = false;
-    if (tile < n_tiles) smp_async = stage_samples(tile);
-
-    for (; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-        const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
-        if (smp_async) {
-            ok = mbar_wait(bar_smp, smp_uses & 1) && ok;
-            ++smp_uses;
-        } else {
-            __syncthreads();   // gathered samples visible
-        }
-
-        // ================= K loop: build A slices, stream B slices, issue MMAs =================
-        const float* srow = s_samples;   // + staged_index(160 * row + 120 + n)
-        for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
-            const uint32_t st = gs & 1u, use = gs >> 1;
-            if (gs >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;   // MMAs that read this stage are complete
-            if (tid == 0) {
-                mbar_arrive_expect_tx(bar_bfull0 + 8 * st, kBStageBytes);
-                bulk_copy_g2s(smem_u32(s_b + st * kBStageBytes), p.b_slices + (size_t)ks * kBStageBytes, kBStageBytes, bar_bfull0 + 8 * st);
+        // sample staging of one tile; returns true when the bulk-copy path was taken (then bar_smp completes a phase)
+        auto stage_samples = [&](int tile) -> bool {
+            const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
+            const float* src = p.wav + (long long)clip * p.clip_stride;
+            const long long g0 = (long long)(tic * kTileFrames - 2) * kHop;     // clip sample held by staged block 0, offset 0
+            const bool interior = g0 >= 0 && g0 + (long long)kBlocks * kHop <= p.length && ((reinterpret_cast<uintptr_t>(src + g0) & 15) == 0);
+            if (interior) {
+                if (warp == 0) {
+                    if (lane == 0) mbar_arrive_expect_tx(bar_smp, kBlocks * kHop * 4);
+                    __syncwarp();
+                    for (int j = lane; j < kBlocks; j += 32)
+                        bulk_copy_g2s(smem_u32(s_samples + j * kPitch), src + g0 + (long long)j * kHop, kHop * 4, bar_smp);
+                }
+                return true;
             }
-            // ---- this thread's 8 values of n: n0 .. n0 + 7 ----
-            const int n0 = 16 * ks + 8 * hsel;
+            const long long L = p.length;
+            for (int i = wtid; i < kBlocks * kHop; i += kWorkerThreads) {
+                const int j = i / kHop, o = i - j * kHop;
+                long long idx = g0 + i;
+                if (idx < 0) idx = -idx;                       // reflection about sample 0 (torch.stft center=True, pad_mode="reflect")
+                if (idx >= L) idx = 2 * (L - 1) - idx;         // and about sample L - 1
+                float v = 0.f;
+                if (idx >= 0 && idx < L) v = __ldg(src + idx);
+                s_samples[j * kPitch + o] = v;
+            }
+            return false;
+        };
+
+        int tile = blockIdx.x;
+        bool smp_async = false;
+        if (tile < n_tiles) smp_async = stage_samples(tile);
+
+        for (; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+            const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
+            if (smp_async) {
+                ok = mbar_wait(bar_smp, smp_uses & 1) && ok;
+                ++smp_uses;
+            } else {
+                worker_sync();   // gathered samples visible
+            }
+
+            // ---------------- K loop: build the A slices of each step ----------------
             const int base = kHop * row + 120;
-            float xa[8], xc[8], xb[8], xe[8];
-            {
-                const float* pa = srow + staged_index(base + n0);              // x[n0 .. n0+7]
-                const float* pc = srow + staged_index(base + 200 + n0);        // x[200+n0 .. 200+n0+7]
-                const float4 a0 = *reinterpret_cast<const float4*>(pa), a1 = *reinterpret_cast<const float4*>(pa + 4);
-                const float4 c0 = *reinterpret_cast<const float4*>(pc), c1 = *reinterpret_cast<const float4*>(pc + 4);
-                xa[0] = a0.x; xa[1] = a0.y; xa[2] = a0.z; xa[3] = a0.w; xa[4] = a1.x; xa[5] = a1.y; xa[6] = a1.z; xa[7] = a1.w;
-                xc[0] = c0.x; xc[1] = c0.y; xc[2] = c0.z; xc[3] = c0.w; xc[4] = c1.x; xc[5] = c1.y; xc[6] = c1.z; xc[7] = c1.w;
-                // x[200 - n0 - i] and x[400 - n0 - i], i = 0..7: the aligned group of 8 below plus one element above
-                const float* pb = srow + staged_index(base + 192 - n0);        // x[192-n0 .. 199-n0]
-                const float* pb8 = srow + staged_index(base + 200 - n0);       // x[200-n0]
-                const float4 b0 = *reinterpret_cast<const float4*>(pb), b1 = *reinterpret_cast<const float4*>(pb + 4);
-                xb[0] = *pb8; xb[1] = b1.w; xb[2] = b1.z; xb[3] = b1.y; xb[4] = b1.x; xb[5] = b0.w; xb[6] = b0.z; xb[7] = b0.y;
-                const float* pe = srow + staged_index(base + 392 - n0);        // x[392-n0 .. 399-n0]
-                const float* pe8 = srow + staged_index(base + (n0 == 0 ? 0 : 400 - n0));   // x[400-n0], index taken mod 400
-                const float4 e0 = *reinterpret_cast<const float4*>(pe), e1 = *reinterpret_cast<const float4*>(pe + 4);
-                xe[0] = *pe8; xe[1] = e1.w; xe[2] = e1.z; xe[3] = e1.y; xe[4] = e1.x; xe[5] = e0.w; xe[6] = e0.z; xe[7] = e0.y;
+#pragma unroll 1
+            for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
+                const uint32_t st = gs & 1u, use = gs >> 1;
+                if (gs >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;   // MMAs that read this stage are complete
+                build_a_slices(s_samples, base, 16 * ks + 8 * hsel, s_wf, s_wr,
+                               s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16);
+                fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_afull0 + 8 * st);
             }
-            Fold8 f;
-            {
-                const float4 wf0 = *reinterpret_cast<const float4*>(s_wf + n0), wf1 = *reinterpret_cast<const float4*>(s_wf + n0 + 4);
-                const float4 wr0 = *reinterpret_cast<const float4*>(s_wr + n0), wr1 = *reinterpret_cast<const float4*>(s_wr + n0 + 4);
-                const float wa[8] = {wf0.x, wf0.y, wf0.z, wf0.w, wf1.x, wf1.y, wf1.z, wf1.w};
-                const float wb[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float pa = wa[i] * xa[i], pe = wa[i] * xe[i];      // w[400-n] = w[n]
-                    const float pb = wb[i] * xb[i], pc = wb[i] * xc[i];      // w[200+n] = w[200-n]
-                    const float sn = pa + pc, sr = pb + pe, dn = pa - pc, dr = pb - pe;
-                    f.se[i] = sn + sr;
-                    f.so[i] = sn - sr;
-                    f.de[i] = dn - dr;
-                    f.dd[i] = dn + dr;
-                }
-            }
-            {
-                uint8_t* dst = s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16;
-                split_store(f.se, dst + 0 * kASliceBytes, dst + 1 * kASliceBytes);
-                split_store(f.so, dst + 2 * kASliceBytes, dst + 3 * kASliceBytes);
-                split_store(f.de, dst + 4 * kASliceBytes, dst + 5 * kASliceBytes);
-                split_store(f.dd, dst + 6 * kASliceBytes, dst + 7 * kASliceBytes);
-            }
-            fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
-            __syncthreads();
-            if (tid == 0) {
-                ok = mbar_wait(bar_bfull0 + 8 * st, use & 1u) && ok;   // B slices of this step have landed
-                tc_fence_after();
-                const uint32_t a_base = smem_u32(s_a + st * kAStageBytes), b_base = smem_u32(s_b + st * kBStageBytes);
-#pragma unroll
-                for (int g = 0; g < kGemms; ++g) {
-                    const uint64_t a_hi = make_desc(a_base + (2 * g) * kASliceBytes, kTileFrames * 16, 128);
-                    const uint64_t a_lo = make_desc(a_base + (2 * g + 1) * kASliceBytes, kTileFrames * 16, 128);
-                    const uint64_t b_hi = make_desc(b_base + (2 * g) * kBSliceBytes, 128, 256);
-                    const uint64_t b_lo = make_desc(b_base + (2 * g + 1) * kBSliceBytes, 128, 256);
-                    const uint32_t d = tmem + (uint32_t)(g * kNpad);
-                    mma_f16_ss(d, a_hi, b_hi, idesc, ks > 0);
-                    mma_f16_ss(d, a_lo, b_hi, idesc, 1);
-                    mma_f16_ss(d, a_hi, b_lo, idesc, 1);
-                }
-                mma_commit(bar_mma0 + 8 * st);
-                if (ks == kKsteps - 1) mma_commit(bar_tile);
-            }
-        }
-        // every thread is past its last read of the sample tile (the barrier of the last K step): prefetch the next tile
-        const int next_tile = tile + gridDim.x;
-        const bool next_async = next_tile < n_tiles ? stage_samples(next_tile) : false;
+            // every worker is past its last read of the sample tile: prefetch the next tile's samples
+            worker_sync();
+            const int next_tile = tile + gridDim.x;
+            const bool next_async = next_tile < n_tiles ? stage_samples(next_tile) : false;
 
-        // ================= epilogue: |X|^2, streaming banded mel, log, store =================
-        ok = mbar_wait(bar_tile, tile_iter & 1u) && ok;
-        tc_fence_after();
-        {
-            const int frame = tic * kTileFrames + row;
-            const bool valid = frame < p.frames_out;
-            float* out_col = p.out + (long long)clip * p.out_clip_stride + frame;
-            const uint32_t t_row = tmem + ((uint32_t)((warp & 3) << 5) << 16);
-            float acc0 = 0.f, acc1 = 0.f, vmax = -3.0e38f;
-            int band = hsel ? p.band_split : 0;
-            int xslot = 0;
-            const int c_begin = hsel ? kSplitChunk : 0, c_end = hsel ? kKsteps : kSplitChunk;
-            auto emit_global = [&](float m, int b) {
-                const float v = (m > p.clamp_min) ? lg2_normal(m) * p.log_scale : p.log_floor;
-                if (valid) {
-                    out_col[(long long)b * p.frame_capacity] = v;
-                    vmax = fmaxf(vmax, v);
-                }
-            };
-            for (int c = c_begin; c < c_end; ++c) {
-                float d0[16], d1[16], d2[16], d3[16];
-                tmem_ld16(t_row + (uint32_t)(0 * kNpad + 16 * c), d0);
-                tmem_ld16(t_row + (uint32_t)(1 * kNpad + 16 * c), d1);
-                tmem_ld16(t_row + (uint32_t)(2 * kNpad + 16 * c), d2);
-                tmem_ld16(t_row + (uint32_t)(3 * kNpad + 16 * c), d3);
-                tmem_ld_wait();
+            // ---------------- epilogue: |X|^2, streaming banded mel, log, store ----------------
+            ok = mbar_wait(bar_tile, tile_iter & 1u) && ok;
+            tc_fence_after();
+            {
+                const int frame = tic * kTileFrames + row;
+                const bool valid = frame < p.frames_out;
+                float* out_col = p.out + (long long)clip * p.out_clip_stride + frame;
+                const uint32_t t_row = tmem + ((uint32_t)((warp & 3) << 5) << 16);
+                float acc0 = 0.f, acc1 = 0.f, vmax = -3.0e38f;
+                int xslot = 0;
+                if (hsel) out_col += (long long)p.band_split * cap;     // out_col always points at the next band to emit
+                const int c_begin = hsel ? kSplitChunk : 0, c_end = hsel ? kKsteps : kSplitChunk;
+                auto emit = [&](float m, int to_xchg) {
+                    if (to_xchg) {   // a band that straddles the cut: hand the partial sum to the lower half
+                        s_xchg[xslot * kTileFrames + row] = m;
+                        if (++xslot == 2) asm volatile("bar.arrive 1, %0;" ::"n"(kWorkerThreads) : "memory");
+                    } else {
+                        const float v = (m > clamp_min) ? lg2_normal(m) * log_scale : log_floor;
+                        if (valid) *out_col = v;
+                        vmax = fmaxf(vmax, v);
+                    }
+                    out_col += cap;
+                };
+                for (int c = c_begin; c < c_end; ++c) {
+                    float d0[16], d1[16], d2[16], d3[16];
+                    tmem_ld16(t_row + (uint32_t)(0 * kNpad + 16 * c), d0);
+                    tmem_ld16(t_row + (uint32_t)(1 * kNpad + 16 * c), d1);
+                    tmem_ld16(t_row + (uint32_t)(2 * kNpad + 16 * c), d2);
+                    tmem_ld16(t_row + (uint32_t)(3 * kNpad + 16 * c), d3);
+                    tmem_ld_wait();
+                    if (c == c_end - 1) {          // last accumulator read of this warp: hand TMEM back to the issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tfree);
+                    }
+                    const float4* prog = s_prog + 32 * c;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float re = (i & 1) ? d2[i >> 1] : d0[i >> 1];
-                    const float im = (i & 1) ? d3[i >> 1] : d1[i >> 1];
-                    const float pw = fmaf(re, re, im * im);
-                    const float4 pg = s_prog[32 * c + i];
-                    acc0 = fmaf(pg.x, pw, acc0);
-                    acc1 = fmaf(pg.y, pw, acc1);
-                    const int code = __float_as_int(pg.z);
-                    if (code != 0) {     // uniform over the CTA half
-                        const int n_emit = code & 3;
-                        for (int e = 0; e < n_emit; ++e) {
-                            if (code & (4 << e)) {       // a band that straddles the cut: hand the partial sum to the lower half
-                                s_xchg[xslot * kTileFrames + row] = acc0;
-                                if (++xslot == 2) asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
-                            } else {
-                                emit_global(acc0, band);
-                            }
+                    for (int i = 0; i < 32; ++i) {
+                        const float re = (i & 1) ? d2[i >> 1] : d0[i >> 1];
+                        const float im = (i & 1) ? d3[i >> 1] : d1[i >> 1];
+                        const float pw = fmaf(re, re, im * im);
+                        const float4 pg = prog[i];
+                        acc0 = fmaf(pg.x, pw, acc0);
+                        acc1 = fmaf(pg.y, pw, acc1);
+                        const int code = __float_as_int(pg.z);
+                        if (code != 0) {     // uniform over the CTA half: the band in acc0 is complete
+                            emit(acc0, code & 4);
                             acc0 = acc1;
                             acc1 = 0.f;
-                            ++band;
+                            if (code & 2) {  // rare: the next band ends on the same bin
+                                emit(acc0, code & 8);
+                                acc0 = 0.f;
+                            }
                         }
                     }
                 }
-            }
-            if (hsel == 0) {   // the two bands open at the cut: add the upper half's partial sums and emit them
-                asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
-                emit_global(acc0 + s_xchg[row], band);
-                if (band + 1 < p.n_mels) emit_global(acc1 + s_xchg[kTileFrames + row], band + 1);
-            }
-            if (p.clip_max) {
+                if (hsel == 0) {   // the two bands open at the cut: add the upper half's partial sums and emit them
+                    asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory");
+                    const float m0 = acc0 + s_xchg[row], m1 = acc1 + s_xchg[kTileFrames + row];
+                    const float v0 = (m0 > clamp_min) ? lg2_normal(m0) * log_scale : log_floor;
+                    const float v1 = (m1 > clamp_min) ? lg2_normal(m1) * log_scale : log_floor;
+                    if (valid) { out_col[0] = v0; out_col[cap] = v1; }
+                    vmax = fmaxf(vmax, fmaxf(v0, v1));
+                }
+                if (p.clip_max) {
+                    if (!valid) vmax = -3.0e38f;
 #pragma unroll
-                for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-                if (lane == 0 && vmax > -3.0e38f) atomicMax(p.clip_max + clip, float_key(vmax));
+                    for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+                    if (lane == 0 && vmax > -3.0e38f) atomicMax(p.clip_max + clip, float_key(vmax));
+                }
             }
+            smp_async = next_async;
         }
-        tc_fence_before();
-        __syncthreads();      // TMEM and the exchange buffer are free for the next tile
-        tc_fence_after();
-        smp_async = next_async;
     }
 
     if (!ok && p.error_flag) atomicExch(p.error_flag, 1);
@@ -590,13 +634,13 @@ int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_
             }
         }
         int n_emit = 0, code = 0;
-        while (j0 < n_mels && n_emit < 2 && (last[j0] <= k || k == kProgBins - 1)) {
+        while (j0 < n_mels && n_emit < 2 && (last[j0] <= k || k >= kBinsAll)) {
             // the first two bands finished by the upper half are the ones open at the cut: they go through the exchange buffer
             if (k >= split_bin && band_split >= 0 && j0 < band_split + 2) code |= 4 << n_emit;
             ++j0;
             ++n_emit;
         }
-        code |= n_emit;
+        code |= (n_emit >= 1 ? 1 : 0) | (n_emit >= 2 ? 2 : 0);
         prog[(size_t)k * 4 + 0] = w0 / (kPrescale * kPrescale);
         prog[(size_t)k * 4 + 1] = w1 / (kPrescale * kPrescale);
         std::memcpy(&prog[(size_t)k * 4 + 2], &code, 4);
