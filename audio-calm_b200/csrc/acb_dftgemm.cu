@@ -63,8 +63,9 @@ constexpr int kASliceBytes = 2 * kTileFrames * 16;            // two k-halves x 
 constexpr int kAStageBytes = kGemms * 2 * kASliceBytes;       // 32768
 constexpr int kBSliceBytes = kNpad * 16 * 2;                  // 3584
 constexpr int kBStageBytes = kGemms * 2 * kBSliceBytes;       // 28672
-constexpr int kProgBins = 224;                   // 7 chunks of 32 bins
-constexpr int kSplitChunk = 3;                   // lower half: chunks [0, 3) = bins [0, 96); upper half: chunks [3, 7)
+constexpr int kPowBins = 224;                    // 7 chunks of 32 bins of |X|^2 staged per frame (bins 201.. are padding)
+constexpr int kSplitChunk = 4;                   // power pass: k-half 0 converts chunks [0, 4), k-half 1 chunks [4, 7)
+constexpr int kMaxWeights = 3072;                // packed non-zero filterbank weights (banded form)
 constexpr int kTmemCols = 512;
 constexpr int kMaxMels = 128;
 constexpr float kPrescale = 4096.f;                // power-of-two scale of the A operands (see acb_dftgemm_create)
@@ -74,11 +75,13 @@ constexpr int kOffSamples = 0;
 constexpr int kOffA = (kSampleFloats * 4 + 127) & ~127;       // 85952
 constexpr int kOffB = kOffA + 2 * kAStageBytes;               // +65536
 constexpr int kOffWin = kOffB + 2 * kBStageBytes;             // +57344
-constexpr int kOffProg = kOffWin + 2 * kKpad * 4;
-constexpr int kOffXchg = kOffProg + kProgBins * 16;
-constexpr int kOffBar = kOffXchg + 2 * kTileFrames * 4;
+constexpr int kOffBand = kOffWin + 2 * kKpad * 4;            // int4 per band: first bin, bins, weight offset
+constexpr int kOffMelW = kOffBand + kMaxMels * 16;
+constexpr int kOffBar = kOffMelW + kMaxWeights * 4;
+constexpr int kOffPow = kOffA;                                // |X|^2 [224 bins][128 rows] fp32 reuses the A/B stages during the epilogue
+static_assert(kPowBins * kTileFrames * 4 <= 2 * kAStageBytes + 2 * kBStageBytes, "power tile must fit the operand stages");
 constexpr int kSmemBytes = kOffBar + 96;
-static_assert(kOffWin % 16 == 0 && kOffProg % 16 == 0 && kOffBar % 8 == 0, "alignment");
+static_assert(kOffWin % 16 == 0 && kOffBand % 16 == 0 && kOffBar % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 static int fail(int code, const std::string& msg) {
@@ -186,8 +189,10 @@ struct Params {
     const uint8_t* b_slices;   // [kKsteps][kGemms][2][kBSliceBytes] fp16 DFT matrices, core-matrix layout
     const float* win_fwd;      // [112] w[n] (0 beyond n = 100)
     const float* win_rev;      // [112] w[200 - n] (0 beyond n = 100)
-    const float4* prog;        // [224] per bin: (w0, w1, emit code, 0)
-    int band_split;            // first unfinished band at the cut between the two epilogue halves
+    const int4* bands;         // [n_mels] (first bin, bins, offset into mel_w, 0): the filterbank in banded form
+    const float* mel_w;        // [n_mel_w] packed weights (with the 2^-24 of the pre-scale folded in)
+    int n_mel_w;
+    int band_split;            // bands [0, band_split) go to k-half 0, the rest to k-half 1 (balanced by weight count)
     int n_mels;
     float clamp_min, log_scale, log_floor;
     // batch
@@ -290,8 +295,9 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
     uint8_t* s_b = smem + kOffB;
     float* s_wf = reinterpret_cast<float*>(smem + kOffWin);
     float* s_wr = s_wf + kKpad;
-    const float4* s_prog = reinterpret_cast<const float4*>(smem + kOffProg);
-    float* s_xchg = reinterpret_cast<float*>(smem + kOffXchg);
+    int4* s_band = reinterpret_cast<int4*>(smem + kOffBand);
+    float* s_melw = reinterpret_cast<float*>(smem + kOffMelW);
+    float* s_pow = reinterpret_cast<float*>(smem + kOffPow);
     const uint32_t bar_base = smem_u32(smem + kOffBar);
     const uint32_t bar_smp = bar_base;              // sample tile landed (bulk copies, tx count)
     const uint32_t bar_bfull0 = bar_base + 8;       // [2] B slices of a stage landed (tx count)
@@ -307,7 +313,8 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
 
     // ---- one-time setup ----
     for (int i = tid; i < kKpad; i += kThreads) { s_wf[i] = p.win_fwd[i]; s_wr[i] = p.win_rev[i]; }
-    for (int i = tid; i < kProgBins; i += kThreads) reinterpret_cast<float4*>(smem + kOffProg)[i] = p.prog[i];
+    for (int i = tid; i < p.n_mels; i += kThreads) s_band[i] = p.bands[i];
+    for (int i = tid; i < p.n_mel_w; i += kThreads) s_melw[i] = p.mel_w[i];
     if (tid == 0) {
         mbar_init(bar_smp, 1);
         mbar_init(bar_bfull0, 1);
@@ -340,9 +347,10 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
                     const uint32_t st = gs & 1u, use = gs >> 1;
                     if (gs >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;      // the stage's previous MMAs are complete
+                    // the epilogue of the previous tile reads the accumulators and keeps |X|^2 in the operand stages: wait for it
+                    if (ks == 0 && tile_iter > 0) ok = mbar_wait(bar_tfree, (tile_iter - 1) & 1u) && ok;
                     mbar_arrive_expect_tx(bar_bfull0 + 8 * st, kBStageBytes);
                     bulk_copy_g2s(smem_u32(s_b + st * kBStageBytes), p.b_slices + (size_t)ks * kBStageBytes, kBStageBytes, bar_bfull0 + 8 * st);
-                    if (ks == 0 && tile_iter > 0) ok = mbar_wait(bar_tfree, (tile_iter - 1) & 1u) && ok;   // accumulators drained
                     ok = mbar_wait(bar_afull0 + 8 * st, use & 1u) && ok;
                     ok = mbar_wait(bar_bfull0 + 8 * st, use & 1u) && ok;
                     tc_fence_after();
@@ -428,29 +436,13 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
             const int next_tile = tile + gridDim.x;
             const bool next_async = next_tile < n_tiles ? stage_samples(next_tile) : false;
 
-            // ---------------- epilogue: |X|^2, streaming banded mel, log, store ----------------
-            ok = mbar_wait(bar_tile, tile_iter & 1u) && ok;
+            // ---------------- epilogue: |X|^2 -> shared memory, banded mel, log, store ----------------
+            ok = mbar_wait(bar_tile, tile_iter & 1u) && ok;      // every MMA of the tile is complete: accumulators ready, stages idle
             tc_fence_after();
             {
-                const int frame = tic * kTileFrames + row;
-                const bool valid = frame < p.frames_out;
-                float* out_col = p.out + (long long)clip * p.out_clip_stride + frame;
+                // power pass: thread (row, k-half) converts its chunks of 32 bins; s_pow[bin][row] (a warp writes 32 consecutive rows)
                 const uint32_t t_row = tmem + ((uint32_t)((warp & 3) << 5) << 16);
-                float acc0 = 0.f, acc1 = 0.f, vmax = -3.0e38f;
-                int xslot = 0;
-                if (hsel) out_col += (long long)p.band_split * cap;     // out_col always points at the next band to emit
                 const int c_begin = hsel ? kSplitChunk : 0, c_end = hsel ? kKsteps : kSplitChunk;
-                auto emit = [&](float m, int to_xchg) {
-                    if (to_xchg) {   // a band that straddles the cut: hand the partial sum to the lower half
-                        s_xchg[xslot * kTileFrames + row] = m;
-                        if (++xslot == 2) asm volatile("bar.arrive 1, %0;" ::"n"(kWorkerThreads) : "memory");
-                    } else {
-                        const float v = (m > clamp_min) ? lg2_normal(m) * log_scale : log_floor;
-                        if (valid) *out_col = v;
-                        vmax = fmaxf(vmax, v);
-                    }
-                    out_col += cap;
-                };
                 for (int c = c_begin; c < c_end; ++c) {
                     float d0[16], d1[16], d2[16], d3[16];
                     tmem_ld16(t_row + (uint32_t)(0 * kNpad + 16 * c), d0);
@@ -458,39 +450,38 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     tmem_ld16(t_row + (uint32_t)(2 * kNpad + 16 * c), d2);
                     tmem_ld16(t_row + (uint32_t)(3 * kNpad + 16 * c), d3);
                     tmem_ld_wait();
-                    if (c == c_end - 1) {          // last accumulator read of this warp: hand TMEM back to the issuer
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tfree);
-                    }
-                    const float4* prog = s_prog + 32 * c;
+                    float* dst = s_pow + (32 * c) * kTileFrames + row;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const float re = (i & 1) ? d2[i >> 1] : d0[i >> 1];
-                        const float im = (i & 1) ? d3[i >> 1] : d1[i >> 1];
-                        const float pw = fmaf(re, re, im * im);
-                        const float4 pg = prog[i];
-                        acc0 = fmaf(pg.x, pw, acc0);
-                        acc1 = fmaf(pg.y, pw, acc1);
-                        const int code = __float_as_int(pg.z);
-                        if (code != 0) {     // uniform over the CTA half: the band in acc0 is complete
-                            emit(acc0, code & 4);
-                            acc0 = acc1;
-                            acc1 = 0.f;
-                            if (code & 2) {  // rare: the next band ends on the same bin
-                                emit(acc0, code & 8);
-                                acc0 = 0.f;
-                            }
-                        }
+                    for (int i = 0; i < 16; ++i) {
+                        dst[(2 * i) * kTileFrames] = fmaf(d0[i], d0[i], d1[i] * d1[i]);          // even bin 2m
+                        dst[(2 * i + 1) * kTileFrames] = fmaf(d2[i], d2[i], d3[i] * d3[i]);      // odd bin 2m + 1
                     }
                 }
-                if (hsel == 0) {   // the two bands open at the cut: add the upper half's partial sums and emit them
-                    asm volatile("bar.sync 1, %0;" ::"n"(kWorkerThreads) : "memory");
-                    const float m0 = acc0 + s_xchg[row], m1 = acc1 + s_xchg[kTileFrames + row];
-                    const float v0 = (m0 > clamp_min) ? lg2_normal(m0) * log_scale : log_floor;
-                    const float v1 = (m1 > clamp_min) ? lg2_normal(m1) * log_scale : log_floor;
-                    if (valid) { out_col[0] = v0; out_col[cap] = v1; }
-                    vmax = fmaxf(vmax, fmaxf(v0, v1));
+                tc_fence_before();
+                worker_sync();       // the whole power tile is in shared memory; the accumulators are drained
+
+                // mel pass: thread (row, k-half) takes a contiguous range of bands; weights are warp-uniform (broadcast loads)
+                const int frame = tic * kTileFrames + row;
+                const bool valid = frame < p.frames_out;
+                const int b_begin = hsel ? p.band_split : 0, b_end = hsel ? p.n_mels : p.band_split;
+                float* out_col = p.out + (long long)clip * p.out_clip_stride + (long long)b_begin * cap + frame;
+                float vmax = -3.0e38f;
+                for (int b = b_begin; b < b_end; ++b, out_col += cap) {
+                    const int4 bd = s_band[b];
+                    const float* pp = s_pow + bd.x * kTileFrames + row;
+                    const float* ww = s_melw + bd.z;
+                    float a0 = 0.f, a1 = 0.f;
+                    int i = 0;
+#pragma unroll 2
+                    for (; i + 1 < bd.y; i += 2) {
+                        a0 = fmaf(ww[i], pp[i * kTileFrames], a0);
+                        a1 = fmaf(ww[i + 1], pp[(i + 1) * kTileFrames], a1);
+                    }
+                    if (i < bd.y) a0 = fmaf(ww[i], pp[i * kTileFrames], a0);
+                    const float m = a0 + a1;
+                    const float v = (m > clamp_min) ? lg2_normal(m) * log_scale : log_floor;
+                    if (valid) *out_col = v;
+                    vmax = fmaxf(vmax, v);
                 }
                 if (p.clip_max) {
                     if (!valid) vmax = -3.0e38f;
@@ -498,6 +489,8 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
                     if (lane == 0 && vmax > -3.0e38f) atomicMax(p.clip_max + clip, float_key(vmax));
                 }
+                worker_sync();       // nobody reads the power tile any more: the operand stages may be refilled
+                if (lane == 0) mbar_arrive(bar_tfree);
             }
             smp_async = next_async;
         }
@@ -540,7 +533,9 @@ struct acb_dftgemm {
     const uint8_t* d_b = nullptr;
     const float* d_wf = nullptr;
     const float* d_wr = nullptr;
-    const float4* d_prog = nullptr;
+    const int4* d_bands = nullptr;
+    const float* d_melw = nullptr;
+    int n_mel_w = 0;
     int* d_err = nullptr;
 };
 
@@ -608,48 +603,33 @@ int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_
     // 2^-24 on the power spectrum is folded into the mel weights (exact).  Operand range: 4 |x| 4096 < 65504, i.e. |x| < 3.99.
     for (int n = 0; n <= 100; ++n) { wf[n] = window_host[n] * kPrescale; wr[n] = window_host[200 - n] * kPrescale; }
 
-    // ---- streaming mel program: every bin feeds at most the two bands (j0, j0 + 1); bands are emitted in order ----
-    std::vector<int> last(n_mels, -1);
-    for (int b = 0; b < n_mels; ++b)
+    // ---- filterbank in banded form: band b = one contiguous run of bins [start, start + len) with packed weights.  The 2^-24 of
+    // the pre-scaled power spectrum is folded into the weights (exact).  Bands are split between the two k-halves of the CTA so
+    // that both get about the same number of multiply-adds.
+    std::vector<int> bands((size_t)n_mels * 4, 0);
+    std::vector<float> melw;
+    for (int b = 0; b < n_mels; ++b) {
+        int lo = -1, hi = -1;
         for (int k = 0; k < kBinsAll; ++k)
-            if (fb_host[(size_t)k * n_mels + b] != 0.f) last[b] = k;
-    for (int b = 0; b < n_mels; ++b)
-        if (last[b] < 0) last[b] = b ? last[b - 1] : 0;      // an all-zero band is emitted right after its predecessor
-    for (int b = 1; b < n_mels; ++b)
-        if (last[b] < last[b - 1]) return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: filterbank bands are not ordered by frequency");
-    std::vector<float> prog((size_t)kProgBins * 4, 0.f);
-    int j0 = 0, band_split = -1;
-    const int split_bin = kSplitChunk * 32;
-    for (int k = 0; k < kProgBins; ++k) {
-        if (k == split_bin) band_split = j0;
-        float w0 = 0.f, w1 = 0.f;
-        if (k < kBinsAll) {
-            for (int b = 0; b < n_mels; ++b) {
-                const float w = fb_host[(size_t)k * n_mels + b];
-                if (w == 0.f) continue;
-                if (b == j0) w0 = w;
-                else if (b == j0 + 1) w1 = w;
-                else return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: filterbank bin " + std::to_string(k) +
-                                                          " feeds bands other than two consecutive ones (band " + std::to_string(b) + ")");
-            }
-        }
-        int n_emit = 0, code = 0;
-        while (j0 < n_mels && n_emit < 2 && (last[j0] <= k || k >= kBinsAll)) {
-            // the first two bands finished by the upper half are the ones open at the cut: they go through the exchange buffer
-            if (k >= split_bin && band_split >= 0 && j0 < band_split + 2) code |= 4 << n_emit;
-            ++j0;
-            ++n_emit;
-        }
-        code |= (n_emit >= 1 ? 1 : 0) | (n_emit >= 2 ? 2 : 0);
-        prog[(size_t)k * 4 + 0] = w0 / (kPrescale * kPrescale);
-        prog[(size_t)k * 4 + 1] = w1 / (kPrescale * kPrescale);
-        std::memcpy(&prog[(size_t)k * 4 + 2], &code, 4);
+            if (fb_host[(size_t)k * n_mels + b] != 0.f) { if (lo < 0) lo = k; hi = k; }
+        bands[(size_t)b * 4 + 0] = lo < 0 ? 0 : lo;
+        bands[(size_t)b * 4 + 1] = lo < 0 ? 0 : hi - lo + 1;
+        bands[(size_t)b * 4 + 2] = (int)melw.size();
+        for (int k = lo; lo >= 0 && k <= hi; ++k) melw.push_back(fb_host[(size_t)k * n_mels + b] / (kPrescale * kPrescale));
     }
-    if (j0 != n_mels) return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: filterbank does not fit the streaming mel program");
-    if (band_split < 0 || band_split + 2 > n_mels)
-        return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: fewer than two bands above bin 96");
-    // the lower half must not have emitted past band_split + 0 before the cut, and the exchange needs both bands finished above it
-    // (guaranteed by construction: band_split is the first unfinished band at bin 96).
+    if ((int)melw.size() > kMaxWeights)
+        return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: filterbank too dense (" + std::to_string(melw.size()) + " banded weights, limit " +
+                                             std::to_string(kMaxWeights) + ")");
+    int band_split = n_mels / 2;
+    {
+        long long total = 0, run = 0;
+        for (int b = 0; b < n_mels; ++b) total += bands[(size_t)b * 4 + 1] + 6;
+        for (int b = 0; b < n_mels; ++b) {
+            run += bands[(size_t)b * 4 + 1] + 6;
+            if (2 * run >= total) { band_split = b + 1; break; }
+        }
+    }
+    melw.resize((melw.size() + 3) & ~(size_t)3, 0.f);
 
     acb_dftgemm* fe = new acb_dftgemm();
     fe->device = device;
@@ -665,19 +645,22 @@ int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(ACB_ERR_CUDA, "acb_dftgemm_create: cudaGetDeviceProperties failed"));
     if (prop.major != 10) return bail(fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: needs an sm_100 device (tcgen05)"));
     fe->num_sms = prop.multiProcessorCount;
-    const size_t b_bytes = bsl.size(), w_bytes = kKpad * 4, p_bytes = prog.size() * 4;
+    const size_t b_bytes = bsl.size(), w_bytes = kKpad * 4, bd_bytes = bands.size() * 4, mw_bytes = melw.size() * 4, p_bytes = bd_bytes + mw_bytes;
+    fe->n_mel_w = (int)melw.size();
     const size_t total = b_bytes + 2 * w_bytes + p_bytes + 16;
     if (cudaMalloc(&fe->d_blob, total) != cudaSuccess) return bail(fail(ACB_ERR_CUDA, "acb_dftgemm_create: cudaMalloc failed"));
     uint8_t* d = static_cast<uint8_t*>(fe->d_blob);
     fe->d_b = d;
     fe->d_wf = reinterpret_cast<const float*>(d + b_bytes);
     fe->d_wr = reinterpret_cast<const float*>(d + b_bytes + w_bytes);
-    fe->d_prog = reinterpret_cast<const float4*>(d + b_bytes + 2 * w_bytes);
+    fe->d_bands = reinterpret_cast<const int4*>(d + b_bytes + 2 * w_bytes);
+    fe->d_melw = reinterpret_cast<const float*>(d + b_bytes + 2 * w_bytes + bd_bytes);
     fe->d_err = reinterpret_cast<int*>(d + b_bytes + 2 * w_bytes + p_bytes);
     bool good = cudaMemcpy(d, bsl.data(), b_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
                 cudaMemcpy(d + b_bytes, wf.data(), w_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
                 cudaMemcpy(d + b_bytes + w_bytes, wr.data(), w_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
-                cudaMemcpy(d + b_bytes + 2 * w_bytes, prog.data(), p_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+                cudaMemcpy(d + b_bytes + 2 * w_bytes, bands.data(), bd_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
+                cudaMemcpy(d + b_bytes + 2 * w_bytes + bd_bytes, melw.data(), mw_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
                 cudaMemset(fe->d_err, 0, 16) == cudaSuccess &&
                 cudaFuncSetAttribute(dftgemm_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess;
     if (!good) {
@@ -720,7 +703,9 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     p.b_slices = fe->d_b;
     p.win_fwd = fe->d_wf;
     p.win_rev = fe->d_wr;
-    p.prog = fe->d_prog;
+    p.bands = fe->d_bands;
+    p.mel_w = fe->d_melw;
+    p.n_mel_w = fe->n_mel_w;
     p.band_split = fe->band_split;
     p.n_mels = fe->n_mels;
     p.clamp_min = fe->clamp_min;

@@ -191,8 +191,8 @@ typedef struct acb_dftgemm acb_dftgemm; /* opaque: DFT matrices, window halves a
  * stft[..., :-1]); -1 when L <= 200 (reflect padding needs a longer input). */
 int64_t acb_dftgemm_frames(int64_t length, int drop_last_frame);
 
-/* window_host[400] (must be symmetric: w[n] == w[400 - n]) and fb_host[201 * n_mels] (row-major [freq][mel]; every bin may
- * feed at most two consecutive bands, i.e. a triangular bank) as fp32.  Only n_fft = 400, hop = 160 is built. */
+/* window_host[400] (must be symmetric: w[n] == w[400 - n]) and fb_host[201 * n_mels] (row-major [freq][mel]; used in banded
+ * form: at most 3072 weights between the first and last non-zero bin of every band) as fp32.  Only n_fft = 400, hop = 160 is built. */
 int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_mels, const float* window_host,
                        const float* fb_host, float clamp_min, int log_kind);
 int acb_dftgemm_destroy(acb_dftgemm* fe);

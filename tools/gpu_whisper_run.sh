@@ -1,3 +1,2 @@
-python -m pytest tests/test_whisper_gpu.py -q 2>&1 | tail -12
-ncu --set full --clock-control none --import-source on -k regex:dftgemm_logmel -c 1 -s 2 -o gpurun_out/r01_w1_dftgemm -f python tools/whisper_bench_step.py > gpurun_out/ncu_w1.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dftgemm --csv python tools/whisper_bench_step.py 2>&1 | grep dftgemm | cut -d, -f5,15 | tail -4
+ncu --set full --clock-control none --import-source on -k regex:dftgemm_logmel -c 1 -s 2 -o gpurun_out/r01_w2_dftgemm -f python tools/whisper_bench_step.py > gpurun_out/ncu_w2.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dftgemm --csv python tools/whisper_bench_step.py 2>&1 | grep dftgemm | cut -d, -f5,15 | tail -2
