@@ -64,7 +64,6 @@ constexpr int kAStageBytes = kGemms * 2 * kASliceBytes;       // 32768
 constexpr int kBSliceBytes = kNpad * 16 * 2;                  // 3584
 constexpr int kBStageBytes = kGemms * 2 * kBSliceBytes;       // 28672
 constexpr int kPowBins = 224;                    // 7 chunks of 32 bins of |X|^2 staged per frame (bins 201.. are padding)
-constexpr int kSplitChunk = 4;                   // power pass: k-half 0 converts chunks [0, 4), k-half 1 chunks [4, 7)
 constexpr int kMaxWeights = 3072;                // packed non-zero filterbank weights (banded form)
 constexpr int kTmemCols = 512;
 constexpr int kMaxMels = 128;
@@ -158,6 +157,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&r)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
+    uint32_t u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];\n"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(u[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -192,7 +199,7 @@ struct Params {
     const int4* bands;         // [n_mels] (first bin, bins, offset into mel_w, 0): the filterbank in banded form
     const float* mel_w;        // [n_mel_w] packed weights (with the 2^-24 of the pre-scale folded in)
     int n_mel_w;
-    int band_split;            // bands [0, band_split) go to k-half 0, the rest to k-half 1 (balanced by weight count)
+    int band_group[kWorkerWarps + 1];   // worker warp w projects bands [band_group[w], band_group[w + 1]) (balanced by weight count)
     int n_mels;
     float clamp_min, log_scale, log_floor;
     // batch
@@ -440,19 +447,20 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
             ok = mbar_wait(bar_tile, tile_iter & 1u) && ok;      // every MMA of the tile is complete: accumulators ready, stages idle
             tc_fence_after();
             {
-                // power pass: thread (row, k-half) converts its chunks of 32 bins; s_pow[bin][row] (a warp writes 32 consecutive rows)
+                // power pass: thread (row, k-half) converts 7 units of 8 accumulator columns (16 bins); s_pow[bin][row]
+                // (a warp writes 32 consecutive rows: conflict-free)
                 const uint32_t t_row = tmem + ((uint32_t)((warp & 3) << 5) << 16);
-                const int c_begin = hsel ? kSplitChunk : 0, c_end = hsel ? kKsteps : kSplitChunk;
-                for (int c = c_begin; c < c_end; ++c) {
-                    float d0[16], d1[16], d2[16], d3[16];
-                    tmem_ld16(t_row + (uint32_t)(0 * kNpad + 16 * c), d0);
-                    tmem_ld16(t_row + (uint32_t)(1 * kNpad + 16 * c), d1);
-                    tmem_ld16(t_row + (uint32_t)(2 * kNpad + 16 * c), d2);
-                    tmem_ld16(t_row + (uint32_t)(3 * kNpad + 16 * c), d3);
+#pragma unroll 1
+                for (int u = 7 * hsel; u < 7 * hsel + 7; ++u) {
+                    float d0[8], d1[8], d2[8], d3[8];
+                    tmem_ld8(t_row + (uint32_t)(0 * kNpad + 8 * u), d0);
+                    tmem_ld8(t_row + (uint32_t)(1 * kNpad + 8 * u), d1);
+                    tmem_ld8(t_row + (uint32_t)(2 * kNpad + 8 * u), d2);
+                    tmem_ld8(t_row + (uint32_t)(3 * kNpad + 8 * u), d3);
                     tmem_ld_wait();
-                    float* dst = s_pow + (32 * c) * kTileFrames + row;
+                    float* dst = s_pow + (16 * u) * kTileFrames + row;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
+                    for (int i = 0; i < 8; ++i) {
                         dst[(2 * i) * kTileFrames] = fmaf(d0[i], d0[i], d1[i] * d1[i]);          // even bin 2m
                         dst[(2 * i + 1) * kTileFrames] = fmaf(d2[i], d2[i], d3[i] * d3[i]);      // odd bin 2m + 1
                     }
@@ -460,31 +468,45 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 tc_fence_before();
                 worker_sync();       // the whole power tile is in shared memory; the accumulators are drained
 
-                // mel pass: thread (row, k-half) takes a contiguous range of bands; weights are warp-uniform (broadcast loads)
-                const int frame = tic * kTileFrames + row;
-                const bool valid = frame < p.frames_out;
-                const int b_begin = hsel ? p.band_split : 0, b_end = hsel ? p.n_mels : p.band_split;
-                float* out_col = p.out + (long long)clip * p.out_clip_stride + (long long)b_begin * cap + frame;
+                // mel pass: lane = 4 consecutive frames (one 16-byte load per bin), warp = one group of bands (weights are
+                // warp-uniform broadcast loads); a warp stores 32 x 4 consecutive frames of one band = 512 contiguous bytes
+                const int frame0 = tic * kTileFrames + 4 * lane;
+                const int n_valid = p.frames_out - frame0;            // frames of this lane that exist (<= 0: none)
+                const int b_begin = p.band_group[warp], b_end = p.band_group[warp + 1];
+                float* out_col = p.out + (long long)clip * p.out_clip_stride + (long long)b_begin * cap + frame0;
+                const bool vec_store = n_valid >= 4 && ((reinterpret_cast<uintptr_t>(p.out) | (uintptr_t)(p.out_clip_stride * 4) | (uintptr_t)(cap * 4)) & 15) == 0;
                 float vmax = -3.0e38f;
+                const float4* pow4 = reinterpret_cast<const float4*>(s_pow) + lane;
                 for (int b = b_begin; b < b_end; ++b, out_col += cap) {
                     const int4 bd = s_band[b];
-                    const float* pp = s_pow + bd.x * kTileFrames + row;
+                    const float4* pp = pow4 + bd.x * (kTileFrames / 4);
                     const float* ww = s_melw + bd.z;
-                    float a0 = 0.f, a1 = 0.f;
-                    int i = 0;
-#pragma unroll 2
-                    for (; i + 1 < bd.y; i += 2) {
-                        a0 = fmaf(ww[i], pp[i * kTileFrames], a0);
-                        a1 = fmaf(ww[i + 1], pp[(i + 1) * kTileFrames], a1);
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+                    for (int i = 0; i < bd.y; ++i) {
+                        const float w = ww[i];
+                        const float4 q = pp[i * (kTileFrames / 4)];
+                        a.x = fmaf(w, q.x, a.x);
+                        a.y = fmaf(w, q.y, a.y);
+                        a.z = fmaf(w, q.z, a.z);
+                        a.w = fmaf(w, q.w, a.w);
                     }
-                    if (i < bd.y) a0 = fmaf(ww[i], pp[i * kTileFrames], a0);
-                    const float m = a0 + a1;
-                    const float v = (m > clamp_min) ? lg2_normal(m) * log_scale : log_floor;
-                    if (valid) *out_col = v;
-                    vmax = fmaxf(vmax, v);
+                    float4 v;
+                    v.x = (a.x > clamp_min) ? lg2_normal(a.x) * log_scale : log_floor;
+                    v.y = (a.y > clamp_min) ? lg2_normal(a.y) * log_scale : log_floor;
+                    v.z = (a.z > clamp_min) ? lg2_normal(a.z) * log_scale : log_floor;
+                    v.w = (a.w > clamp_min) ? lg2_normal(a.w) * log_scale : log_floor;
+                    if (vec_store) {
+                        *reinterpret_cast<float4*>(out_col) = v;
+                        vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                    } else {
+                        if (n_valid > 0) { out_col[0] = v.x; vmax = fmaxf(vmax, v.x); }
+                        if (n_valid > 1) { out_col[1] = v.y; vmax = fmaxf(vmax, v.y); }
+                        if (n_valid > 2) { out_col[2] = v.z; vmax = fmaxf(vmax, v.z); }
+                        if (n_valid > 3) { out_col[3] = v.w; vmax = fmaxf(vmax, v.w); }
+                    }
                 }
                 if (p.clip_max) {
-                    if (!valid) vmax = -3.0e38f;
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
                     if (lane == 0 && vmax > -3.0e38f) atomicMax(p.clip_max + clip, float_key(vmax));
@@ -528,7 +550,7 @@ struct acb_dftgemm {
     int log_kind = 0;
     float clamp_min = 0.f;
     int num_sms = 0;
-    int band_split = 0;
+    int band_group[acbg::kWorkerWarps + 1] = {0};
     void* d_blob = nullptr;
     const uint8_t* d_b = nullptr;
     const float* d_wf = nullptr;
@@ -620,14 +642,17 @@ int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_
     if ((int)melw.size() > kMaxWeights)
         return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_create: filterbank too dense (" + std::to_string(melw.size()) + " banded weights, limit " +
                                              std::to_string(kMaxWeights) + ")");
-    int band_split = n_mels / 2;
+    int band_group[kWorkerWarps + 1];
     {
         long long total = 0, run = 0;
-        for (int b = 0; b < n_mels; ++b) total += bands[(size_t)b * 4 + 1] + 6;
-        for (int b = 0; b < n_mels; ++b) {
-            run += bands[(size_t)b * 4 + 1] + 6;
-            if (2 * run >= total) { band_split = b + 1; break; }
+        for (int b = 0; b < n_mels; ++b) total += bands[(size_t)b * 4 + 1] + 8;
+        int g = 0;
+        band_group[0] = 0;
+        for (int b = 0; b < n_mels; ++b) {      // cut after the band that reaches the next multiple of total / 8
+            run += bands[(size_t)b * 4 + 1] + 8;
+            while (g + 1 < kWorkerWarps && run * kWorkerWarps >= total * (g + 1)) band_group[++g] = b + 1;
         }
+        while (g < kWorkerWarps) band_group[++g] = n_mels;
     }
     melw.resize((melw.size() + 3) & ~(size_t)3, 0.f);
 
@@ -636,7 +661,7 @@ int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_
     fe->n_mels = n_mels;
     fe->log_kind = log_kind;
     fe->clamp_min = clamp_min;
-    fe->band_split = band_split;
+    for (int g = 0; g <= kWorkerWarps; ++g) fe->band_group[g] = band_group[g];
     int prev = 0;
     cudaGetDevice(&prev);
     auto bail = [&](int rc) { cudaSetDevice(prev); delete fe; return rc; };
@@ -706,7 +731,7 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     p.bands = fe->d_bands;
     p.mel_w = fe->d_melw;
     p.n_mel_w = fe->n_mel_w;
-    p.band_split = fe->band_split;
+    for (int g = 0; g <= kWorkerWarps; ++g) p.band_group[g] = fe->band_group[g];
     p.n_mels = fe->n_mels;
     p.clamp_min = fe->clamp_min;
     p.log_scale = fe->log_kind == ACB_LOG_10 ? 0.30102999566398120f : 0.69314718055994531f;
