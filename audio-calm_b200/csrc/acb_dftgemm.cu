@@ -33,6 +33,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -51,7 +52,7 @@ constexpr int kBinsAll = 201;
 constexpr int kTileFrames = 128;
 constexpr int kWorkerWarps = 8;
 constexpr int kWorkerThreads = kWorkerWarps * 32;   // thread = (frame row, k-half)
-constexpr int kThreads = kWorkerThreads + 32;      // + one MMA / bulk-copy issuer warp
+constexpr int kThreads = kWorkerThreads + 64;      // + one MMA issuer warp + one B-slice loader warp (one elected lane each)
 constexpr int kKpad = 112;                       // K of every GEMM (n = 0..100 used)
 constexpr int kNpad = 112;                       // N of every GEMM (m = 0..100 used)
 constexpr int kKsteps = kKpad / 16;              // 7
@@ -293,8 +294,8 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
 }
 
 // Warp roles: warps 0-7 ("workers", thread = frame row x k-half) stage samples, build the A slices and run the epilogue;
-// warp 8 (one elected lane) streams the B slices and issues the MMAs.  All hand-offs are mbarriers: no CTA-wide barrier sits
-// inside the K loop.
+// warp 8 (one elected lane) issues the MMAs, warp 9 (one elected lane) streams the B slices.  All hand-offs are mbarriers: no
+// CTA-wide barrier sits inside the K loop.
 __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Params p) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* s_samples = reinterpret_cast<float*>(smem + kOffSamples);
@@ -345,21 +346,33 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
     const int n_tiles = p.n_clips * p.tiles_per_clip;
     bool ok = true;
 
-    if (warp == kWorkerWarps) {
-        // ======================================= MMA / B-slice issuer =======================================
+    if (warp == kWorkerWarps + 1) {
+        // ======================================= B-slice loader =======================================
+        // Streams the 28 KB of DFT-matrix slices of every K step from L2 as soon as the stage's previous MMAs have completed,
+        // independently of the issuer, so the copy of step k+1 overlaps the MMAs of step k.
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16(kTileFrames, kNpad);
             uint32_t gs = 0, tile_iter = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
                 for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
                     const uint32_t st = gs & 1u, use = gs >> 1;
                     if (gs >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;      // the stage's previous MMAs are complete
-                    // the epilogue of the previous tile reads the accumulators and keeps |X|^2 in the operand stages: wait for it
+                    // the epilogue of the previous tile keeps |X|^2 in the operand stages: wait until it is done with them
                     if (ks == 0 && tile_iter > 0) ok = mbar_wait(bar_tfree, (tile_iter - 1) & 1u) && ok;
                     mbar_arrive_expect_tx(bar_bfull0 + 8 * st, kBStageBytes);
                     bulk_copy_g2s(smem_u32(s_b + st * kBStageBytes), p.b_slices + (size_t)ks * kBStageBytes, kBStageBytes, bar_bfull0 + 8 * st);
-                    ok = mbar_wait(bar_afull0 + 8 * st, use & 1u) && ok;
-                    ok = mbar_wait(bar_bfull0 + 8 * st, use & 1u) && ok;
+                }
+            }
+        }
+    } else if (warp == kWorkerWarps) {
+        // ======================================= MMA issuer =======================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_f16(kTileFrames, kNpad);
+            uint32_t gs = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
+                    const uint32_t st = gs & 1u, use = gs >> 1;
+                    ok = mbar_wait(bar_afull0 + 8 * st, use & 1u) && ok;      // A slices written by the 8 worker warps
+                    ok = mbar_wait(bar_bfull0 + 8 * st, use & 1u) && ok;      // B slices landed (implies: accumulators drained, see the loader)
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(s_a + st * kAStageBytes), b_base = smem_u32(s_b + st * kBStageBytes);
 #pragma unroll
@@ -525,17 +538,29 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
 }
 
 // Dynamic-range floor and affine of the stored features (WhisperFeatureExtractor: maximum(x, max - 8), then (x + 4) / 4).
+// One CTA row per (band, clip); 16-byte accesses when the rows are aligned.  HBM-bound: one read and one write of the features.
 __global__ void __launch_bounds__(256) dftgemm_finalize_kernel(float* __restrict__ out, long long out_clip_stride, long long frame_capacity,
                                                                int n_mels, int frames, const int* __restrict__ clip_max, float dyn_range,
                                                                float scale, float shift) {
     const int clip = blockIdx.y;
-    float* base = out + (long long)clip * out_clip_stride;
-    const float floor_v = clip_max ? key_float(clip_max[clip]) - dyn_range : -3.0e38f;
-    const long long n = (long long)n_mels * frames;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const long long b = i / frames, t = i - b * frames;
-        float* q = base + b * frame_capacity + t;
-        *q = fmaf(fmaxf(*q, floor_v), scale, shift);
+    const float floor_v = clip_max ? key_float(__ldg(clip_max + clip)) - dyn_range : -3.0e38f;
+    for (int b = blockIdx.x; b < n_mels; b += gridDim.x) {
+        float* row = out + (long long)clip * out_clip_stride + (long long)b * frame_capacity;
+        if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+            float4* row4 = reinterpret_cast<float4*>(row);
+            const int n4 = frames >> 2;
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+                float4 v = row4[i];
+                v.x = fmaf(fmaxf(v.x, floor_v), scale, shift);
+                v.y = fmaf(fmaxf(v.y, floor_v), scale, shift);
+                v.z = fmaf(fmaxf(v.z, floor_v), scale, shift);
+                v.w = fmaf(fmaxf(v.w, floor_v), scale, shift);
+                row4[i] = v;
+            }
+            for (int t = (n4 << 2) + threadIdx.x; t < frames; t += blockDim.x) row[t] = fmaf(fmaxf(row[t], floor_v), scale, shift);
+        } else {
+            for (int t = threadIdx.x; t < frames; t += blockDim.x) row[t] = fmaf(fmaxf(row[t], floor_v), scale, shift);
+        }
     }
 }
 
@@ -755,8 +780,7 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     if (p.clip_max || a->affine) {
         const float scale = a->affine ? 1.f / a->affine_std : 1.f;
         const float shift = a->affine ? -a->affine_mean / a->affine_std : 0.f;
-        const long long per_clip = (long long)fe->n_mels * T;
-        const int bx = (int)std::min<long long>((per_clip + 255) / 256, 64);
+        const int bx = T >= 1024 ? fe->n_mels : std::max(1, fe->n_mels / 8);     // short rows: several bands per CTA
         dftgemm_finalize_kernel<<<dim3(bx, a->n_clips), 256, 0, s>>>(a->out, a->out_clip_stride, a->frame_capacity, fe->n_mels, (int)T,
                                                                      p.clip_max, a->dyn_range, scale, shift);
         ACBG_CUDA(cudaGetLastError());
