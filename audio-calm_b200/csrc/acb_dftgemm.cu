@@ -293,6 +293,15 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
     split_store(f.dd, dst + 6 * kASliceBytes, dst + 7 * kASliceBytes);
 }
 
+// Where a tile's samples come from: clip pointer, the clip sample held by staged block 0 / offset 0, and whether the whole staged
+// range lies inside the clip on 16-byte aligned addresses (then it is fetched by bulk copies, otherwise gathered with reflection).
+__device__ __forceinline__ bool tile_source(const Params& p, int tile, const float*& src, long long& g0) {
+    const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
+    src = p.wav + (long long)clip * p.clip_stride;
+    g0 = (long long)(tic * kTileFrames - 2) * kHop;
+    return g0 >= 0 && g0 + (long long)kBlocks * kHop <= p.length && ((reinterpret_cast<uintptr_t>(src + g0) & 15) == 0);
+}
+
 // Warp roles: warps 0-7 ("workers", thread = frame row x k-half) stage samples, build the A slices and run the epilogue;
 // warp 8 (one elected lane) issues the MMAs, warp 9 (one elected lane) streams the B slices.  All hand-offs are mbarriers: no
 // CTA-wide barrier sits inside the K loop.
@@ -313,7 +322,8 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
     const uint32_t bar_mma0 = bar_base + 40;        // [2] the MMAs reading a stage are complete (tcgen05.commit)
     const uint32_t bar_tile = bar_base + 56;        // all MMAs of the tile complete: accumulators ready
     const uint32_t bar_tfree = bar_base + 64;       // accumulators drained by the epilogue (8 worker warps)
-    uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 72);
+    const uint32_t bar_sfree = bar_base + 72;       // sample tile no longer read (8 worker warps)
+    uint32_t* s_tmem_slot = reinterpret_cast<uint32_t*>(smem + kOffBar + 80);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = ((warp & 3) << 5) | lane;     // frame row of the tile = TMEM lane (workers)
@@ -333,6 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
         mbar_init(bar_mma0 + 8, 1);
         mbar_init(bar_tile, 1);
         mbar_init(bar_tfree, kWorkerWarps);
+        mbar_init(bar_sfree, kWorkerWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -350,18 +361,34 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
         // ======================================= B-slice loader =======================================
         // Streams the 28 KB of DFT-matrix slices of every K step from L2 as soon as the stage's previous MMAs have completed,
         // independently of the issuer, so the copy of step k+1 overlaps the MMAs of step k.
-        if (lane == 0) {
-            uint32_t gs = 0, tile_iter = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
-                for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
-                    const uint32_t st = gs & 1u, use = gs >> 1;
-                    if (gs >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;      // the stage's previous MMAs are complete
+        // The same warp (all lanes, one 640-byte hop block each per round) fetches the next tile's samples as soon as the workers
+        // have left the K loop, so no worker warp spends its time issuing copies.
+        auto fetch_samples = [&](int tile) {
+            const float* src;
+            long long g0;
+            if (!tile_source(p, tile, src, g0)) return;     // edge tile: the workers gather it themselves
+            if (lane == 0) mbar_arrive_expect_tx(bar_smp, kBlocks * kHop * 4);
+            __syncwarp();
+            for (int j = lane; j < kBlocks; j += 32)
+                bulk_copy_g2s(smem_u32(s_samples + j * kPitch), src + g0 + (long long)j * kHop, kHop * 4, bar_smp);
+        };
+        uint32_t gs = 0, tile_iter = 0;
+        if ((int)blockIdx.x < n_tiles) fetch_samples(blockIdx.x);
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
+            if (lane == 0) {
+                for (int ks = 0; ks < kKsteps; ++ks) {
+                    const uint32_t st = (gs + ks) & 1u, use = (gs + ks) >> 1;
+                    if (gs + ks >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;      // the stage's previous MMAs are complete
                     // the epilogue of the previous tile keeps |X|^2 in the operand stages: wait until it is done with them
                     if (ks == 0 && tile_iter > 0) ok = mbar_wait(bar_tfree, (tile_iter - 1) & 1u) && ok;
                     mbar_arrive_expect_tx(bar_bfull0 + 8 * st, kBStageBytes);
                     bulk_copy_g2s(smem_u32(s_b + st * kBStageBytes), p.b_slices + (size_t)ks * kBStageBytes, kBStageBytes, bar_bfull0 + 8 * st);
                 }
             }
+            gs += kKsteps;
+            __syncwarp();
+            ok = mbar_wait(bar_sfree, tile_iter & 1u) && ok;      // every worker is past its last read of the sample tile
+            if (tile + (int)gridDim.x < n_tiles) fetch_samples(tile + gridDim.x);
         }
     } else if (warp == kWorkerWarps) {
         // ======================================= MMA issuer =======================================
@@ -398,21 +425,12 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
         const float clamp_min = p.clamp_min, log_scale = p.log_scale, log_floor = p.log_floor;
         const long long cap = p.frame_capacity;
 
-        // sample staging of one tile; returns true when the bulk-copy path was taken (then bar_smp completes a phase)
+        // sample staging of one tile: interior tiles arrive by the loader warp's bulk copies (bar_smp completes a phase, returns
+        // true); edge tiles are gathered here with reflection by all workers
         auto stage_samples = [&](int tile) -> bool {
-            const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
-            const float* src = p.wav + (long long)clip * p.clip_stride;
-            const long long g0 = (long long)(tic * kTileFrames - 2) * kHop;     // clip sample held by staged block 0, offset 0
-            const bool interior = g0 >= 0 && g0 + (long long)kBlocks * kHop <= p.length && ((reinterpret_cast<uintptr_t>(src + g0) & 15) == 0);
-            if (interior) {
-                if (warp == 0) {
-                    if (lane == 0) mbar_arrive_expect_tx(bar_smp, kBlocks * kHop * 4);
-                    __syncwarp();
-                    for (int j = lane; j < kBlocks; j += 32)
-                        bulk_copy_g2s(smem_u32(s_samples + j * kPitch), src + g0 + (long long)j * kHop, kHop * 4, bar_smp);
-                }
-                return true;
-            }
+            const float* src;
+            long long g0;
+            if (tile_source(p, tile, src, g0)) return true;
             const long long L = p.length;
             for (int i = wtid; i < kBlocks * kHop; i += kWorkerThreads) {
                 const int j = i / kHop, o = i - j * kHop;
@@ -451,10 +469,21 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_afull0 + 8 * st);
             }
-            // every worker is past its last read of the sample tile: prefetch the next tile's samples
-            worker_sync();
+            // this warp is past its last read of the sample tile: tell the loader, which prefetches an interior next tile; an edge
+            // next tile is gathered here once every worker has left the K loop
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sfree);
             const int next_tile = tile + gridDim.x;
-            const bool next_async = next_tile < n_tiles ? stage_samples(next_tile) : false;
+            bool next_async = false;
+            if (next_tile < n_tiles) {
+                const float* nsrc;
+                long long ng0;
+                next_async = tile_source(p, next_tile, nsrc, ng0);
+                if (!next_async) {
+                    worker_sync();
+                    stage_samples(next_tile);
+                }
+            }
 
             // ---------------- epilogue: |X|^2 -> shared memory, banded mel, log, store ----------------
             ok = mbar_wait(bar_tile, tile_iter & 1u) && ok;      // every MMA of the tile is complete: accumulators ready, stages idle
