@@ -16,17 +16,19 @@
 // fp32 accuracy from fp16 tensor cores: A = A_hi + A_lo, B = B_hi + B_lo (fp16 pairs, 22 significant bits),
 // D = A_hi B_hi + A_lo B_hi + A_hi B_lo accumulated in fp32 in TMEM (measured 2e-6 on the final features).
 //
-// Kernel (persistent, one CTA of 256 threads per SM, tiles of 128 frames of one clip):
-//   1. the tile's samples are staged in shared memory by bulk async copies (one per 160-sample hop block, rows padded to 164
-//      floats so a warp's 16-byte loads of 32 different frames are conflict-free); edge tiles are gathered with reflection;
-//   2. K loop, 7 steps of 16: all threads build the step's A slices (window, folds, fp16 hi/lo split) in the canonical
-//      K-major no-swizzle core-matrix layout, the step's B slices (28 KB) arrive by one bulk copy from L2, one thread issues
-//      12 tcgen05.mma (M 128, N 112, K 16) and commits to an mbarrier; A/B are double-buffered so the MMAs of step k run under
-//      the CUDA-core work of step k+1;
-//   3. epilogue: thread = frame row; tcgen05.ld 16 columns of each accumulator, |X|^2 in registers, a streaming banded mel
-//      projection (every bin feeds at most two consecutive bands: two running accumulators, bands are emitted in order),
-//      clamp, log, coalesced stores (32 consecutive frames of one band per warp), per-clip max by atomicMax.  The two halves
-//      of the CTA take bins [0, 96) and [96, 201); the two bands that straddle the cut are exchanged through shared memory.
+// Kernel (persistent, one CTA per SM, tiles of 128 frames of one clip; 8 worker warps + 1 MMA issuer warp + 1 loader warp, every
+// hand-off an mbarrier):
+//   1. loader warp: the tile's samples are staged in shared memory by bulk async copies (one per 160-sample hop block, rows padded
+//      to 164 floats so a warp's 16-byte loads of 32 different frames are conflict-free) while the previous tile's epilogue runs;
+//      edge tiles (reflection about sample 0 / L-1) are gathered by the workers;
+//   2. K loop, 7 steps of 16: the workers (thread = frame row x k-half) build the step's A slices (window, folds, fp16 hi/lo split
+//      with packed conversions) in the canonical K-major no-swizzle core-matrix layout; the loader streams the step's B slices
+//      (28 KB of the 200 KB DFT matrices, L2-resident) with one bulk copy; the issuer's elected lane issues 12 tcgen05.mma
+//      (M 128, N 112, K 16, kind::f16) and commits to mbarriers.  A and B are double-buffered: the MMAs of step k run under the
+//      CUDA-core work of step k+1;
+//   3. epilogue: tcgen05.ld of the four accumulators, |X|^2 into shared memory as [bin][frame] (the operand stages are idle),
+//      then the banded mel projection with lane = 4 consecutive frames (one 16-byte load per bin) and warp = a group of bands
+//      (warp-uniform weights), clamp, log, 512-byte band stores, per-clip max by atomicMax;
 //   4. a second, HBM-bound kernel applies the dynamic-range floor (per-clip max - 8) and the affine (x + 4) / 4.
 #include "audiocalm_b200.h"
 
