@@ -32,6 +32,7 @@
 //   4. a second, HBM-bound kernel applies the dynamic-range floor (per-clip max - 8) and the affine (x + 4) / 4.
 #include "audiocalm_b200.h"
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -52,16 +53,18 @@ constexpr int kNfft = 400;
 constexpr int kHop = 160;
 constexpr int kBinsAll = 201;
 constexpr int kTileFrames = 128;
-constexpr int kWorkerWarps = 8;
-constexpr int kWorkerThreads = kWorkerWarps * 32;   // thread = (frame row, k-half)
+constexpr int kWorkerWarps = 16;                    // all of them run the epilogue (4 per TMEM lane quarter)
+constexpr int kPrepWarps = 8;                       // the first 8 also build the A slices: thread = (frame row, k-half), 16-byte stores
+constexpr int kWorkerThreads = kWorkerWarps * 32;
 constexpr int kThreads = kWorkerThreads + 64;      // + one MMA issuer warp + one B-slice loader warp (one elected lane each)
 constexpr int kKpad = 112;                       // K of every GEMM (n = 0..100 used)
 constexpr int kNpad = 112;                       // N of every GEMM (m = 0..100 used)
 constexpr int kKsteps = kKpad / 16;              // 7
 constexpr int kGemms = 4;
 constexpr int kBlocks = kTileFrames + 3;         // hop blocks staged per tile
-constexpr int kPitch = 164;                      // floats per staged hop block
-constexpr int kSampleFloats = kBlocks * kPitch;  // 21484
+constexpr int kStageRows = 656;                  // staged sample tile: rows of 32 floats (128 B); 131 * 160 = 20960 samples = 655 rows
+constexpr int kBoxRows = 128;                    // TMA box: 128 rows (16 KB, a multiple of the 1 KB swizzle atom); 5 of them + one of 16 rows
+constexpr int kSampleFloats = kStageRows * 32;   // 20992
 constexpr int kASliceBytes = 2 * kTileFrames * 16;            // two k-halves x 128 rows x 8 halves
 constexpr int kAStageBytes = kGemms * 2 * kASliceBytes;       // 32768
 constexpr int kBSliceBytes = kNpad * 16 * 2;                  // 3584
@@ -70,11 +73,15 @@ constexpr int kPowBins = 224;                    // 7 chunks of 32 bins of |X|^2
 constexpr int kMaxWeights = 3072;                // packed non-zero filterbank weights (banded form)
 constexpr int kTmemCols = 512;
 constexpr int kMaxMels = 128;
+#ifndef ACBG_BAND_COST
+#define ACBG_BAND_COST 16
+#endif
+constexpr int kBandCost = ACBG_BAND_COST;          // fixed cost of a band (logs, stores) in units of one weight, for balancing the band groups
 constexpr float kPrescale = 4096.f;                // power-of-two scale of the A operands (see acb_dftgemm_create)
 
 // shared memory carve-up (bytes)
 constexpr int kOffSamples = 0;
-constexpr int kOffA = (kSampleFloats * 4 + 127) & ~127;       // 85952
+constexpr int kOffA = (kSampleFloats * 4 + 1023) & ~1023;     // 83968
 constexpr int kOffB = kOffA + 2 * kAStageBytes;               // +65536
 constexpr int kOffWin = kOffB + 2 * kBStageBytes;             // +57344
 constexpr int kOffBand = kOffWin + 2 * kKpad * 4;            // int4 per band: first bin, bins, weight offset
@@ -110,8 +117,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void worker_sync() {   // named barrier of the 8 worker warps (barrier 0 is __syncthreads, 1 the band exchange)
-    asm volatile("bar.sync 2, %0;" ::"n"(256) : "memory");
+__device__ __forceinline__ void worker_sync() {   // named barrier of the worker warps (barrier 0 is __syncthreads, 1 the band exchange)
+    asm volatile("bar.sync 2, %0;" ::"n"(kWorkerThreads) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -128,6 +135,10 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tensor_copy_2d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor: 8-row x 16-byte core matrices (rows 16 bytes apart);
 // lbo = byte distance between core matrices adjacent in K, sbo = between 8-row groups (validated on B200 by
@@ -218,6 +229,8 @@ struct Params {
     long long frame_capacity;
     int* clip_max;             // [n_clips] ordered-int keys, or nullptr
     int* error_flag;           // set to 1 when a barrier wait timed out
+    int use_tma;               // the batch is 128-byte row addressable (16-byte aligned base, clip_stride % 32 == 0): tensor copies
+    long long* trace;          // development: clock64 stamps of CTA 0 ([role][tile < 8][event < 16]), or nullptr
 };
 
 // A-operand values of one thread for one K step: 8 consecutive n of its frame row, for the 4 GEMMs
@@ -244,11 +257,11 @@ __device__ __forceinline__ void split_store(const float (&v)[8], uint8_t* dst_hi
     *reinterpret_cast<uint4*>(dst_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
-// staged float index of linear position `lin` (= 160 * row + 120 + n) with padded hop blocks
-__device__ __forceinline__ int staged_index(int lin) {
-    const int blk = lin / kHop;
-    return blk * kPitch + (lin - blk * kHop);
-}
+// Staged float index of linear position `lin` (= 160 * row + 120 + n).  The tile is staged as rows of 32 floats in the TMA
+// SWIZZLE_128B layout (the 16-byte chunk index within a 128-byte row is XORed with the row index mod 8): frames are 160 floats
+// = 5 rows apart, so the 8 threads of a 16-byte load phase (8 consecutive frames) hit 8 different chunk positions -- no bank
+// conflicts, and the whole tile arrives with 6 tensor copies instead of one copy per hop block.
+__device__ __forceinline__ int staged_index(int lin) { return lin ^ (((lin >> 5) & 7) << 2); }
 
 // One K step of A-operand construction for one thread: 8 consecutive n (n0 .. n0 + 7) of its frame row, for the 4 GEMMs.
 // `srow` = the staged samples, `base` = 160 * row + 120 (linear staged position of the frame's sample 0).
@@ -258,18 +271,19 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
     {
         const float* pa = srow + staged_index(base + n0);              // x[n0 .. n0+7]
         const float* pc = srow + staged_index(base + 200 + n0);        // x[200+n0 .. 200+n0+7]
-        const float4 a0 = *reinterpret_cast<const float4*>(pa), a1 = *reinterpret_cast<const float4*>(pa + 4);
-        const float4 c0 = *reinterpret_cast<const float4*>(pc), c1 = *reinterpret_cast<const float4*>(pc + 4);
+        // the second 16-byte chunk of an aligned group of 8 sits at the swizzled index ^ 4
+        const float4 a0 = *reinterpret_cast<const float4*>(pa), a1 = *reinterpret_cast<const float4*>(srow + (staged_index(base + n0) ^ 4));
+        const float4 c0 = *reinterpret_cast<const float4*>(pc), c1 = *reinterpret_cast<const float4*>(srow + (staged_index(base + 200 + n0) ^ 4));
         xa[0] = a0.x; xa[1] = a0.y; xa[2] = a0.z; xa[3] = a0.w; xa[4] = a1.x; xa[5] = a1.y; xa[6] = a1.z; xa[7] = a1.w;
         xc[0] = c0.x; xc[1] = c0.y; xc[2] = c0.z; xc[3] = c0.w; xc[4] = c1.x; xc[5] = c1.y; xc[6] = c1.z; xc[7] = c1.w;
         // x[200 - n0 - i] and x[400 - n0 - i], i = 0..7: the aligned group of 8 below plus one element above
         const float* pb = srow + staged_index(base + 192 - n0);        // x[192-n0 .. 199-n0]
         const float* pb8 = srow + staged_index(base + 200 - n0);       // x[200-n0]
-        const float4 b0 = *reinterpret_cast<const float4*>(pb), b1 = *reinterpret_cast<const float4*>(pb + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(pb), b1 = *reinterpret_cast<const float4*>(srow + (staged_index(base + 192 - n0) ^ 4));
         xb[0] = *pb8; xb[1] = b1.w; xb[2] = b1.z; xb[3] = b1.y; xb[4] = b1.x; xb[5] = b0.w; xb[6] = b0.z; xb[7] = b0.y;
         const float* pe = srow + staged_index(base + 392 - n0);        // x[392-n0 .. 399-n0]
         const float* pe8 = srow + staged_index(base + (n0 == 0 ? 0 : 400 - n0));   // x[400-n0], index taken mod 400
-        const float4 e0 = *reinterpret_cast<const float4*>(pe), e1 = *reinterpret_cast<const float4*>(pe + 4);
+        const float4 e0 = *reinterpret_cast<const float4*>(pe), e1 = *reinterpret_cast<const float4*>(srow + (staged_index(base + 392 - n0) ^ 4));
         xe[0] = *pe8; xe[1] = e1.w; xe[2] = e1.z; xe[3] = e1.y; xe[4] = e1.x; xe[5] = e0.w; xe[6] = e0.z; xe[7] = e0.y;
     }
     Fold8 f;
@@ -296,19 +310,20 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
 }
 
 // Where a tile's samples come from: clip pointer, the clip sample held by staged block 0 / offset 0, and whether the whole staged
-// range lies inside the clip on 16-byte aligned addresses (then it is fetched by bulk copies, otherwise gathered with reflection).
+// range lies inside the clip (then it is fetched by TMA tensor copies when the batch layout allows, otherwise gathered with reflection).
 __device__ __forceinline__ bool tile_source(const Params& p, int tile, const float*& src, long long& g0) {
     const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
     src = p.wav + (long long)clip * p.clip_stride;
     g0 = (long long)(tic * kTileFrames - 2) * kHop;
-    return g0 >= 0 && g0 + (long long)kBlocks * kHop <= p.length && ((reinterpret_cast<uintptr_t>(src + g0) & 15) == 0);
+    return p.use_tma && g0 >= 0 && g0 + (long long)kBlocks * kHop <= p.length;
 }
 
-// Warp roles: warps 0-7 ("workers", thread = frame row x k-half) stage samples, build the A slices and run the epilogue;
-// warp 8 (one elected lane) issues the MMAs, warp 9 (one elected lane) streams the B slices.  All hand-offs are mbarriers: no
+// Warp roles: 16 worker warps run the epilogue and gather edge tiles, the first 8 of them (thread = frame row x k-half) also build
+// the A slices; warp 16 (one elected lane) issues the MMAs, warp 17 streams the B slices and prefetches sample tiles.  All hand-offs are mbarriers: no
 // CTA-wide barrier sits inside the K loop.
-__global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Params p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+__global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Params p, const __grid_constant__ CUtensorMap tm_box128,
+                                                                     const __grid_constant__ CUtensorMap tm_box16) {
+    extern __shared__ __align__(1024) uint8_t smem[];
     float* s_samples = reinterpret_cast<float*>(smem + kOffSamples);
     uint8_t* s_a = smem + kOffA;
     uint8_t* s_b = smem + kOffB;
@@ -329,7 +344,8 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row = ((warp & 3) << 5) | lane;     // frame row of the tile = TMEM lane (workers)
-    const int hsel = (warp >> 2) & 1;             // prep: k-half of the K step; epilogue: bin range
+    const int hsel = (warp >> 2) & 1;             // prep warps: k-half of the K step
+    const int qsel = (warp >> 2) & 3;             // power pass: which quarter of the accumulator columns of the row
 
     // ---- one-time setup ----
     for (int i = tid; i < kKpad; i += kThreads) { s_wf[i] = p.win_fwd[i]; s_wr[i] = p.win_rev[i]; }
@@ -339,13 +355,13 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
         mbar_init(bar_smp, 1);
         mbar_init(bar_bfull0, 1);
         mbar_init(bar_bfull0 + 8, 1);
-        mbar_init(bar_afull0, kWorkerWarps);
-        mbar_init(bar_afull0 + 8, kWorkerWarps);
+        mbar_init(bar_afull0, kPrepWarps);
+        mbar_init(bar_afull0 + 8, kPrepWarps);
         mbar_init(bar_mma0, 1);
         mbar_init(bar_mma0 + 8, 1);
         mbar_init(bar_tile, 1);
         mbar_init(bar_tfree, kWorkerWarps);
-        mbar_init(bar_sfree, kWorkerWarps);
+        mbar_init(bar_sfree, kPrepWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -357,7 +373,12 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
     tc_fence_after();
     const uint32_t tmem = *s_tmem_slot;
     const int n_tiles = p.n_clips * p.tiles_per_clip;
-    bool ok = true;
+    bool ok = (smem_u32(smem) & 1023u) == 0;       // the swizzled sample tile needs a 1 KB aligned base
+
+    // development timeline (acb_dftgemm_set_trace): role 0 = worker warp 0, 1 = issuer, 2 = loader; CTA 0, first 8 tiles
+    auto stamp = [&](int role, uint32_t tile_iter, int event) {
+        if (p.trace && blockIdx.x == 0 && lane == 0 && tile_iter < 8 && event < 16) p.trace[(role * 8 + tile_iter) * 16 + event] = clock64();
+    };
 
     if (warp == kWorkerWarps + 1) {
         // ======================================= B-slice loader =======================================
@@ -369,10 +390,13 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
             const float* src;
             long long g0;
             if (!tile_source(p, tile, src, g0)) return;     // edge tile: the workers gather it themselves
-            if (lane == 0) mbar_arrive_expect_tx(bar_smp, kBlocks * kHop * 4);
+            const long long row0 = ((src - p.wav) + g0) >> 5;       // first 128-byte row of the tile in the batch buffer
+            if (lane == 0) mbar_arrive_expect_tx(bar_smp, kStageRows * 128);
             __syncwarp();
-            for (int j = lane; j < kBlocks; j += 32)
-                bulk_copy_g2s(smem_u32(s_samples + j * kPitch), src + g0 + (long long)j * kHop, kHop * 4, bar_smp);
+            if (lane < 6) {
+                const CUtensorMap* tm = lane < 5 ? &tm_box128 : &tm_box16;
+                tensor_copy_2d(smem_u32(s_samples) + lane * (kBoxRows * 128), tm, 0, (int)(row0 + lane * kBoxRows), bar_smp);
+            }
         };
         uint32_t gs = 0, tile_iter = 0;
         if ((int)blockIdx.x < n_tiles) fetch_samples(blockIdx.x);
@@ -383,6 +407,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     if (gs + ks >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;      // the stage's previous MMAs are complete
                     // the epilogue of the previous tile keeps |X|^2 in the operand stages: wait until it is done with them
                     if (ks == 0 && tile_iter > 0) ok = mbar_wait(bar_tfree, (tile_iter - 1) & 1u) && ok;
+                    stamp(2, tile_iter, ks);        // B copy of step ks issued
                     mbar_arrive_expect_tx(bar_bfull0 + 8 * st, kBStageBytes);
                     bulk_copy_g2s(smem_u32(s_b + st * kBStageBytes), p.b_slices + (size_t)ks * kBStageBytes, kBStageBytes, bar_bfull0 + 8 * st);
                 }
@@ -390,18 +415,21 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
             gs += kKsteps;
             __syncwarp();
             ok = mbar_wait(bar_sfree, tile_iter & 1u) && ok;      // every worker is past its last read of the sample tile
+            stamp(2, tile_iter, 8);
             if (tile + (int)gridDim.x < n_tiles) fetch_samples(tile + gridDim.x);
         }
     } else if (warp == kWorkerWarps) {
         // ======================================= MMA issuer =======================================
         if (lane == 0) {
             const uint32_t idesc = make_idesc_f16(kTileFrames, kNpad);
-            uint32_t gs = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            uint32_t gs = 0, tile_iter = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
                 for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
                     const uint32_t st = gs & 1u, use = gs >> 1;
-                    ok = mbar_wait(bar_afull0 + 8 * st, use & 1u) && ok;      // A slices written by the 8 worker warps
+                    ok = mbar_wait(bar_afull0 + 8 * st, use & 1u) && ok;      // A slices written by the worker warps
+                    stamp(1, tile_iter, 2 * ks);
                     ok = mbar_wait(bar_bfull0 + 8 * st, use & 1u) && ok;      // B slices landed (implies: accumulators drained, see the loader)
+                    stamp(1, tile_iter, 2 * ks + 1);
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(s_a + st * kAStageBytes), b_base = smem_u32(s_b + st * kBStageBytes);
 #pragma unroll
@@ -435,13 +463,12 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
             if (tile_source(p, tile, src, g0)) return true;
             const long long L = p.length;
             for (int i = wtid; i < kBlocks * kHop; i += kWorkerThreads) {
-                const int j = i / kHop, o = i - j * kHop;
                 long long idx = g0 + i;
                 if (idx < 0) idx = -idx;                       // reflection about sample 0 (torch.stft center=True, pad_mode="reflect")
                 if (idx >= L) idx = 2 * (L - 1) - idx;         // and about sample L - 1
                 float v = 0.f;
                 if (idx >= 0 && idx < L) v = __ldg(src + idx);
-                s_samples[j * kPitch + o] = v;
+                s_samples[staged_index(i)] = v;
             }
             return false;
         };
@@ -459,22 +486,27 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 worker_sync();   // gathered samples visible
             }
 
+            if (warp == 0) stamp(0, tile_iter, 0);      // samples ready
             // ---------------- K loop: build the A slices of each step ----------------
             const int base = kHop * row + 120;
+            if (warp < kPrepWarps) {
 #pragma unroll 1
-            for (int ks = 0; ks < kKsteps; ++ks, ++gs) {
-                const uint32_t st = gs & 1u, use = gs >> 1;
-                if (gs >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;   // MMAs that read this stage are complete
-                build_a_slices(s_samples, base, 16 * ks + 8 * hsel, s_wf, s_wr,
-                               s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16);
-                fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
+                for (int ks = 0; ks < kKsteps; ++ks) {
+                    const uint32_t st = (gs + ks) & 1u, use = (gs + ks) >> 1;
+                    if (gs + ks >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;   // MMAs that read this stage are complete
+                    build_a_slices(s_samples, base, 16 * ks + 8 * hsel, s_wf, s_wr,
+                                   s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16);
+                    fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_afull0 + 8 * st);
+                    if (warp == 0) stamp(0, tile_iter, 1 + ks);
+                }
+                // this warp is past its last read of the sample tile: tell the loader, which prefetches an interior next tile
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_afull0 + 8 * st);
+                if (lane == 0) mbar_arrive(bar_sfree);
             }
-            // this warp is past its last read of the sample tile: tell the loader, which prefetches an interior next tile; an edge
-            // next tile is gathered here once every worker has left the K loop
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_sfree);
+            gs += kKsteps;
+            // an edge next tile is gathered here by all workers once every prep warp has left the K loop
             const int next_tile = tile + gridDim.x;
             bool next_async = false;
             if (next_tile < n_tiles) {
@@ -490,12 +522,13 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
             // ---------------- epilogue: |X|^2 -> shared memory, banded mel, log, store ----------------
             ok = mbar_wait(bar_tile, tile_iter & 1u) && ok;      // every MMA of the tile is complete: accumulators ready, stages idle
             tc_fence_after();
+            if (warp == 0) stamp(0, tile_iter, 8);
             {
-                // power pass: thread (row, k-half) converts 7 units of 8 accumulator columns (16 bins); s_pow[bin][row]
+                // power pass: the 4 warps of a lane quarter share the 14 units of 8 accumulator columns (16 bins); s_pow[bin][row]
                 // (a warp writes 32 consecutive rows: conflict-free)
                 const uint32_t t_row = tmem + ((uint32_t)((warp & 3) << 5) << 16);
 #pragma unroll 1
-                for (int u = 7 * hsel; u < 7 * hsel + 7; ++u) {
+                for (int u = (14 * qsel) / 4; u < (14 * (qsel + 1)) / 4; ++u) {
                     float d0[8], d1[8], d2[8], d3[8];
                     tmem_ld8(t_row + (uint32_t)(0 * kNpad + 8 * u), d0);
                     tmem_ld8(t_row + (uint32_t)(1 * kNpad + 8 * u), d1);
@@ -511,6 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 }
                 tc_fence_before();
                 worker_sync();       // the whole power tile is in shared memory; the accumulators are drained
+                if (warp == 0) stamp(0, tile_iter, 9);
 
                 // mel pass: lane = 4 consecutive frames (one 16-byte load per bin), warp = one group of bands (weights are
                 // warp-uniform broadcast loads); a warp stores 32 x 4 consecutive frames of one band = 512 contiguous bytes
@@ -555,7 +589,9 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
                     if (lane == 0 && vmax > -3.0e38f) atomicMax(p.clip_max + clip, float_key(vmax));
                 }
+                if (warp == 0) stamp(0, tile_iter, 10);
                 worker_sync();       // nobody reads the power tile any more: the operand stages may be refilled
+                if (warp == 0) stamp(0, tile_iter, 11);
                 if (lane == 0) mbar_arrive(bar_tfree);
             }
             smp_async = next_async;
@@ -615,6 +651,7 @@ struct acb_dftgemm {
     const float* d_melw = nullptr;
     int n_mel_w = 0;
     int* d_err = nullptr;
+    long long* d_trace = nullptr;   // development timeline buffer (acb_dftgemm_set_trace)
 };
 
 using namespace acbg;
@@ -701,11 +738,11 @@ int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_
     int band_group[kWorkerWarps + 1];
     {
         long long total = 0, run = 0;
-        for (int b = 0; b < n_mels; ++b) total += bands[(size_t)b * 4 + 1] + 8;
+        for (int b = 0; b < n_mels; ++b) total += bands[(size_t)b * 4 + 1] + kBandCost;
         int g = 0;
         band_group[0] = 0;
         for (int b = 0; b < n_mels; ++b) {      // cut after the band that reaches the next multiple of total / 8
-            run += bands[(size_t)b * 4 + 1] + 8;
+            run += bands[(size_t)b * 4 + 1] + kBandCost;
             while (g + 1 < kWorkerWarps && run * kWorkerWarps >= total * (g + 1)) band_group[++g] = b + 1;
         }
         while (g < kWorkerWarps) band_group[++g] = n_mels;
@@ -764,6 +801,30 @@ int acb_dftgemm_destroy(acb_dftgemm* fe) {
     return ACB_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+// The batch buffer as rows of 32 floats: [rows][32], boxes of `box_rows` rows, 128-byte swizzle
+static bool make_sample_map(CUtensorMap* tm, const float* base, long long rows, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* stream) {
     if (!fe || !a) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: null argument");
     if (!a->wav || !a->out) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: wav and out must be device pointers");
@@ -803,10 +864,20 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     p.frame_capacity = a->frame_capacity;
     p.clip_max = a->dyn_range > 0.f ? a->clip_max : nullptr;
     p.error_flag = fe->d_err;
+    p.trace = fe->d_trace;
     if (p.clip_max) ACBG_CUDA(cudaMemsetAsync(p.clip_max, 0x80, sizeof(int) * (size_t)a->n_clips, s));   // keys below every float
     const int64_t n_tiles = tiles_per_clip * a->n_clips;
     const int grid = (int)std::min<int64_t>(n_tiles, fe->num_sms);
-    dftgemm_logmel_kernel<<<grid, kThreads, kSmemBytes, s>>>(p);
+    // tensor maps of the sample buffer: usable when every tile start is a whole 128-byte row of a 16-byte aligned buffer
+    CUtensorMap tm128, tm16;
+    std::memset(&tm128, 0, sizeof(tm128));
+    std::memset(&tm16, 0, sizeof(tm16));
+    const bool row_addressable = (reinterpret_cast<uintptr_t>(a->wav) & 15) == 0 && (a->n_clips == 1 || a->clip_stride % 32 == 0);
+    if (row_addressable) {
+        const long long rows = ((long long)(a->n_clips - 1) * a->clip_stride + a->length) / 32;    // whole rows inside the buffer
+        p.use_tma = rows > 0 && make_sample_map(&tm128, a->wav, rows, kBoxRows) && make_sample_map(&tm16, a->wav, rows, 16);
+    }
+    dftgemm_logmel_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, tm128, tm16);
     ACBG_CUDA(cudaGetLastError());
     if (p.clip_max || a->affine) {
         const float scale = a->affine ? 1.f / a->affine_std : 1.f;
@@ -816,6 +887,13 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
                                                                      p.clip_max, a->dyn_range, scale, shift);
         ACBG_CUDA(cudaGetLastError());
     }
+    return ACB_OK;
+}
+
+/* development only (not in the public header): device buffer of 3 * 8 * 16 int64 clock stamps written by CTA 0, or NULL */
+int acb_dftgemm_set_trace(acb_dftgemm* fe, long long* device_buffer) {
+    if (!fe) return fail(ACB_ERR_INVALID, "acb_dftgemm_set_trace: null handle");
+    fe->d_trace = device_buffer;
     return ACB_OK;
 }
 
