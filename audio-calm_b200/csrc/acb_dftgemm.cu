@@ -230,7 +230,7 @@ struct Params {
     int* clip_max;             // [n_clips] ordered-int keys, or nullptr
     int* error_flag;           // set to 1 when a barrier wait timed out
     int use_tma;               // the batch is 128-byte row addressable (16-byte aligned base, clip_stride % 32 == 0): tensor copies
-    long long* trace;          // development: clock64 stamps of CTA 0 ([role][tile < 8][event < 16]), or nullptr
+    long long* trace;          // development: clock64 stamps of CTA 0 ([role][tile < 48][event < 16]), or nullptr
 };
 
 // A-operand values of one thread for one K step: 8 consecutive n of its frame row, for the 4 GEMMs
@@ -309,13 +309,14 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
     split_store(f.dd, dst + 6 * kASliceBytes, dst + 7 * kASliceBytes);
 }
 
-// Where a tile's samples come from: clip pointer, the clip sample held by staged block 0 / offset 0, and whether the whole staged
-// range lies inside the clip (then it is fetched by TMA tensor copies when the batch layout allows, otherwise gathered with reflection).
+// Where a tile's samples come from: clip pointer and the clip sample held by staged position 0.  Returns whether the tile is fetched by
+// TMA tensor copies (the batch layout allows it; positions outside the clip are then patched with the reflection by the workers) or
+// gathered entirely by the workers.
 __device__ __forceinline__ bool tile_source(const Params& p, int tile, const float*& src, long long& g0) {
     const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
     src = p.wav + (long long)clip * p.clip_stride;
     g0 = (long long)(tic * kTileFrames - 2) * kHop;
-    return p.use_tma && g0 >= 0 && g0 + (long long)kBlocks * kHop <= p.length;
+    return p.use_tma != 0;
 }
 
 // Warp roles: 16 worker warps run the epilogue and gather edge tiles, the first 8 of them (thread = frame row x k-half) also build
@@ -377,7 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
 
     // development timeline (acb_dftgemm_set_trace): role 0 = worker warp 0, 1 = issuer, 2 = loader; CTA 0, first 8 tiles
     auto stamp = [&](int role, uint32_t tile_iter, int event) {
-        if (p.trace && blockIdx.x == 0 && lane == 0 && tile_iter < 8 && event < 16) p.trace[(role * 8 + tile_iter) * 16 + event] = clock64();
+        if (p.trace && blockIdx.x == 0 && lane == 0 && tile_iter < 48 && event < 16) p.trace[(role * 48 + tile_iter) * 16 + event] = clock64();
     };
 
     if (warp == kWorkerWarps + 1) {
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
         auto fetch_samples = [&](int tile) {
             const float* src;
             long long g0;
-            if (!tile_source(p, tile, src, g0)) return;     // edge tile: the workers gather it themselves
+            if (!tile_source(p, tile, src, g0)) return;     // not row addressable: the workers gather the tile themselves
             const long long row0 = ((src - p.wav) + g0) >> 5;       // first 128-byte row of the tile in the batch buffer
             if (lane == 0) mbar_arrive_expect_tx(bar_smp, kStageRows * 128);
             __syncwarp();
@@ -455,13 +456,14 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
         const float clamp_min = p.clamp_min, log_scale = p.log_scale, log_floor = p.log_floor;
         const long long cap = p.frame_capacity;
 
-        // sample staging of one tile: interior tiles arrive by the loader warp's bulk copies (bar_smp completes a phase, returns
-        // true); edge tiles are gathered here with reflection by all workers
+        // sample staging of one tile: with a row-addressable batch every tile arrives by the loader warp's tensor copies (bar_smp
+        // completes a phase, returns true); otherwise the workers gather it here with reflection
         auto stage_samples = [&](int tile) -> bool {
             const float* src;
             long long g0;
             if (tile_source(p, tile, src, g0)) return true;
             const long long L = p.length;
+#pragma unroll 8
             for (int i = wtid; i < kBlocks * kHop; i += kWorkerThreads) {
                 long long idx = g0 + i;
                 if (idx < 0) idx = -idx;                       // reflection about sample 0 (torch.stft center=True, pad_mode="reflect")
@@ -482,10 +484,29 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
             if (smp_async) {
                 ok = mbar_wait(bar_smp, smp_uses & 1) && ok;
                 ++smp_uses;
+                // positions outside the clip (reflection about sample 0 / L - 1: torch.stft center=True, pad_mode="reflect") are
+                // patched over what the tensor copy brought in; only the first and the last tiles of a clip have any
+                const float* src = p.wav + (long long)clip * p.clip_stride;
+                const long long g0 = (long long)(tic * kTileFrames - 2) * kHop, L = p.length;
+                const long long e0 = L - g0;                        // first staged position beyond the clip
+                if (g0 < 0 || e0 < kBlocks * kHop) {                // CTA-uniform
+                    if (g0 < 0)
+                        for (int i = wtid; i < (int)-g0; i += kWorkerThreads) {
+                            const long long idx = -(g0 + i);
+                            s_samples[staged_index(i)] = idx < L ? __ldg(src + idx) : 0.f;
+                        }
+                    if (e0 < kBlocks * kHop) {                      // the 200 reflected samples the last frame needs (and a margin)
+                        const int i = (int)e0 + wtid;
+                        if (wtid < 256 && i < kBlocks * kHop) {
+                            const long long idx = 2 * (L - 1) - (g0 + i);
+                            s_samples[staged_index(i)] = idx >= 0 ? __ldg(src + idx) : 0.f;
+                        }
+                    }
+                    worker_sync();
+                }
             } else {
                 worker_sync();   // gathered samples visible
             }
-
             if (warp == 0) stamp(0, tile_iter, 0);      // samples ready
             // ---------------- K loop: build the A slices of each step ----------------
             const int base = kHop * row + 120;
@@ -874,7 +895,8 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     std::memset(&tm16, 0, sizeof(tm16));
     const bool row_addressable = (reinterpret_cast<uintptr_t>(a->wav) & 15) == 0 && (a->n_clips == 1 || a->clip_stride % 32 == 0);
     if (row_addressable) {
-        const long long rows = ((long long)(a->n_clips - 1) * a->clip_stride + a->length) / 32;    // whole rows inside the buffer
+        // rows that hold samples of the batch (a partial last row is read whole: allocations are 256-byte granular)
+        const long long rows = ((long long)(a->n_clips - 1) * a->clip_stride + a->length + 31) / 32;
         p.use_tma = rows > 0 && make_sample_map(&tm128, a->wav, rows, kBoxRows) && make_sample_map(&tm16, a->wav, rows, 16);
     }
     dftgemm_logmel_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, tm128, tm16);
@@ -890,7 +912,7 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     return ACB_OK;
 }
 
-/* development only (not in the public header): device buffer of 3 * 8 * 16 int64 clock stamps written by CTA 0, or NULL */
+/* development only (not in the public header): device buffer of 3 * 48 * 16 int64 clock stamps written by CTA 0, or NULL */
 int acb_dftgemm_set_trace(acb_dftgemm* fe, long long* device_buffer) {
     if (!fe) return fail(ACB_ERR_INVALID, "acb_dftgemm_set_trace: null handle");
     fe->d_trace = device_buffer;
