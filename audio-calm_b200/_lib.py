@@ -38,7 +38,7 @@ EXPORTED_SYMBOLS = [
     "acb_logmel_forward", "acb_peak_abs", "acb_process_audio_chunk", "acb_moments_accumulate",
     "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host", "acb_crop_pad", "acb_pad_transpose",
     "acb_moments_accumulate_workspace_bytes", "acb_pcm16_to_float", "acb_logmel_forward_host_pcm16",
-    "acb_dftgemm_frames", "acb_dftgemm_create", "acb_dftgemm_destroy", "acb_dftgemm_forward", "acb_dftgemm_check",
+    "acb_dftgemm_frames", "acb_dftgemm_workspace_ints", "acb_dftgemm_create", "acb_dftgemm_destroy", "acb_dftgemm_forward", "acb_dftgemm_check",
 ]
 
 
@@ -188,6 +188,8 @@ def load() -> ctypes.CDLL:
         lib.acb_logmel_forward_host_pcm16.argtypes = [vp, vp, i32, i64, vp, ctypes.POINTER(LogmelArgs), vp, vp, vp, i32, vp]
         lib.acb_dftgemm_frames.restype = i64
         lib.acb_dftgemm_frames.argtypes = [i64, ctypes.c_int]
+        lib.acb_dftgemm_workspace_ints.restype = i64
+        lib.acb_dftgemm_workspace_ints.argtypes = [i64, ctypes.c_int, i32]
         lib.acb_dftgemm_create.restype = ctypes.c_int
         lib.acb_dftgemm_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            vp, vp, f32, ctypes.c_int]

@@ -29,7 +29,8 @@
 //   3. epilogue: tcgen05.ld of the four accumulators, |X|^2 into shared memory as [bin][frame] (the operand stages are idle),
 //      then the banded mel projection with lane = 4 consecutive frames (one 16-byte load per bin) and warp = a group of bands
 //      (warp-uniform weights), clamp, log, 512-byte band stores, per-clip max by atomicMax;
-//   4. a second, HBM-bound kernel applies the dynamic-range floor (per-clip max - 8) and the affine (x + 4) / 4.
+//   4. the affine (x + 4) / 4 is applied at the store (it commutes with the floor); the kernel also records the minimum of every tile,
+//      so the second kernel (dynamic-range floor, per-clip max - 8) only touches the tiles that hold values below the floor.
 #include "audiocalm_b200.h"
 
 #include <cuda.h>
@@ -227,7 +228,9 @@ struct Params {
     float* out;
     long long out_clip_stride;
     long long frame_capacity;
-    int* clip_max;             // [n_clips] ordered-int keys, or nullptr
+    int* clip_max;             // [n_clips] ordered-int keys of the per-clip maximum, or nullptr (no dynamic-range floor)
+    int* tile_min;             // [n_clips * tiles_per_clip] ordered-int keys of the per-tile minimum (tiles above the floor are skipped later)
+    float aff_scale, aff_shift;   // out = v * aff_scale + aff_shift (1, 0 when no affine)
     int* error_flag;           // set to 1 when a barrier wait timed out
     int use_tma;               // the batch is 128-byte row addressable (16-byte aligned base, clip_stride % 32 == 0): tensor copies
     long long* trace;          // development: clock64 stamps of CTA 0 ([role][tile < 48][event < 16]), or nullptr
@@ -574,7 +577,8 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 const int b_begin = p.band_group[warp], b_end = p.band_group[warp + 1];
                 float* out_col = p.out + (long long)clip * p.out_clip_stride + (long long)b_begin * cap + frame0;
                 const bool vec_store = n_valid >= 4 && ((reinterpret_cast<uintptr_t>(p.out) | (uintptr_t)(p.out_clip_stride * 4) | (uintptr_t)(cap * 4)) & 15) == 0;
-                float vmax = -3.0e38f;
+                float vmax = -3.0e38f, vmin = 3.0e38f;
+                const float aff_scale = p.aff_scale, aff_shift = p.aff_shift;
                 const float4* pow4 = reinterpret_cast<const float4*>(s_pow) + lane;
                 for (int b = b_begin; b < b_end; ++b, out_col += cap) {
                     const int4 bd = s_band[b];
@@ -595,20 +599,29 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     v.y = (a.y > clamp_min) ? lg2_normal(a.y) * log_scale : log_floor;
                     v.z = (a.z > clamp_min) ? lg2_normal(a.z) * log_scale : log_floor;
                     v.w = (a.w > clamp_min) ? lg2_normal(a.w) * log_scale : log_floor;
+                    // the affine is applied here; the dynamic-range floor commutes with it: max(v, M - r) * s + t = max(v s + t, (M s + t) - r s)
+                    v.x = fmaf(v.x, aff_scale, aff_shift);
+                    v.y = fmaf(v.y, aff_scale, aff_shift);
+                    v.z = fmaf(v.z, aff_scale, aff_shift);
+                    v.w = fmaf(v.w, aff_scale, aff_shift);
                     if (vec_store) {
                         *reinterpret_cast<float4*>(out_col) = v;
                         vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+                        vmin = fminf(fminf(vmin, fminf(v.x, v.y)), fminf(v.z, v.w));
                     } else {
-                        if (n_valid > 0) { out_col[0] = v.x; vmax = fmaxf(vmax, v.x); }
-                        if (n_valid > 1) { out_col[1] = v.y; vmax = fmaxf(vmax, v.y); }
-                        if (n_valid > 2) { out_col[2] = v.z; vmax = fmaxf(vmax, v.z); }
-                        if (n_valid > 3) { out_col[3] = v.w; vmax = fmaxf(vmax, v.w); }
+                        if (n_valid > 0) { out_col[0] = v.x; vmax = fmaxf(vmax, v.x); vmin = fminf(vmin, v.x); }
+                        if (n_valid > 1) { out_col[1] = v.y; vmax = fmaxf(vmax, v.y); vmin = fminf(vmin, v.y); }
+                        if (n_valid > 2) { out_col[2] = v.z; vmax = fmaxf(vmax, v.z); vmin = fminf(vmin, v.z); }
+                        if (n_valid > 3) { out_col[3] = v.w; vmax = fmaxf(vmax, v.w); vmin = fminf(vmin, v.w); }
                     }
                 }
                 if (p.clip_max) {
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
                     if (lane == 0 && vmax > -3.0e38f) atomicMax(p.clip_max + clip, float_key(vmax));
+#pragma unroll
+                    for (int o = 16; o >= 1; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+                    if (lane == 0 && vmin < 3.0e38f) atomicMin(p.tile_min + tile, float_key(vmin));
                 }
                 if (warp == 0) stamp(0, tile_iter, 10);
                 worker_sync();       // nobody reads the power tile any more: the operand stages may be refilled
@@ -625,29 +638,23 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
-// Dynamic-range floor and affine of the stored features (WhisperFeatureExtractor: maximum(x, max - 8), then (x + 4) / 4).
-// One CTA row per (band, clip); 16-byte accesses when the rows are aligned.  HBM-bound: one read and one write of the features.
-__global__ void __launch_bounds__(256) dftgemm_finalize_kernel(float* __restrict__ out, long long out_clip_stride, long long frame_capacity,
-                                                               int n_mels, int frames, const int* __restrict__ clip_max, float dyn_range,
-                                                               float scale, float shift) {
-    const int clip = blockIdx.y;
-    const float floor_v = clip_max ? key_float(__ldg(clip_max + clip)) - dyn_range : -3.0e38f;
-    for (int b = blockIdx.x; b < n_mels; b += gridDim.x) {
-        float* row = out + (long long)clip * out_clip_stride + (long long)b * frame_capacity;
-        if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
-            float4* row4 = reinterpret_cast<float4*>(row);
-            const int n4 = frames >> 2;
-            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-                float4 v = row4[i];
-                v.x = fmaf(fmaxf(v.x, floor_v), scale, shift);
-                v.y = fmaf(fmaxf(v.y, floor_v), scale, shift);
-                v.z = fmaf(fmaxf(v.z, floor_v), scale, shift);
-                v.w = fmaf(fmaxf(v.w, floor_v), scale, shift);
-                row4[i] = v;
-            }
-            for (int t = (n4 << 2) + threadIdx.x; t < frames; t += blockDim.x) row[t] = fmaf(fmaxf(row[t], floor_v), scale, shift);
-        } else {
-            for (int t = threadIdx.x; t < frames; t += blockDim.x) row[t] = fmaf(fmaxf(row[t], floor_v), scale, shift);
+// Dynamic-range floor of the stored features (WhisperFeatureExtractor: maximum(x, max - 8); the affine (x + 4) / 4 has already been
+// applied and commutes with it).  One CTA per tile of 128 frames; a tile whose minimum is not below its clip's floor -- the common
+// case -- is skipped after two loads, so the pass costs a fraction of a read + write of the features.
+__global__ void __launch_bounds__(256) dftgemm_floor_kernel(float* __restrict__ out, long long out_clip_stride, long long frame_capacity, int n_mels,
+                                                            int frames, int tiles_per_clip, const int* __restrict__ clip_max,
+                                                            const int* __restrict__ tile_min, float range) {
+    const int tic = blockIdx.x, clip = blockIdx.y;
+    const float floor_v = key_float(__ldg(clip_max + clip)) - range;
+    if (!(key_float(__ldg(tile_min + clip * tiles_per_clip + tic)) < floor_v)) return;
+    const int f0 = tic * kTileFrames, nf = min(kTileFrames, frames - f0);
+    float* base = out + (long long)clip * out_clip_stride + f0;
+    for (int i = threadIdx.x; i < n_mels * kTileFrames; i += blockDim.x) {
+        const int b = i / kTileFrames, f = i - b * kTileFrames;
+        if (f < nf) {
+            float* q = base + (long long)b * frame_capacity + f;
+            const float v = *q;
+            if (v < floor_v) *q = floor_v;
         }
     }
 }
@@ -690,6 +697,12 @@ static float half_value(uint16_t u) {
 }
 
 extern "C" {
+
+int64_t acb_dftgemm_workspace_ints(int64_t length, int drop_last_frame, int32_t n_clips) {
+    const int64_t T = 1 + length / kHop - (drop_last_frame ? 1 : 0);
+    if (length <= kNfft / 2 || n_clips < 0) return -1;
+    return (int64_t)n_clips * (1 + (T + kTileFrames - 1) / kTileFrames);
+}
 
 int64_t acb_dftgemm_frames(int64_t length, int drop_last_frame) {
     if (length <= kNfft / 2) return -1;
@@ -857,7 +870,7 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     if (a->clip_stride < a->length) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: clip_stride < length");
     if (a->out_clip_stride < (int64_t)fe->n_mels * a->frame_capacity) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: out_clip_stride too small");
     if (a->dyn_range > 0.f && !a->clip_max) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: dyn_range needs the clip_max workspace");
-    if (a->affine && !(a->affine_std != 0.f)) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: affine_std must be non-zero");
+    if (a->affine && !(a->affine_std > 0.f)) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: affine_std must be positive");
     const int64_t tiles_per_clip = (T + kTileFrames - 1) / kTileFrames;
     if (tiles_per_clip * a->n_clips > INT32_MAX) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: more than 2^31 tiles in one call");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -884,9 +897,15 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     p.out_clip_stride = a->out_clip_stride;
     p.frame_capacity = a->frame_capacity;
     p.clip_max = a->dyn_range > 0.f ? a->clip_max : nullptr;
+    p.tile_min = p.clip_max ? a->clip_max + a->n_clips : nullptr;
+    p.aff_scale = a->affine ? 1.f / a->affine_std : 1.f;
+    p.aff_shift = a->affine ? -a->affine_mean / a->affine_std : 0.f;
     p.error_flag = fe->d_err;
     p.trace = fe->d_trace;
-    if (p.clip_max) ACBG_CUDA(cudaMemsetAsync(p.clip_max, 0x80, sizeof(int) * (size_t)a->n_clips, s));   // keys below every float
+    if (p.clip_max) {
+        ACBG_CUDA(cudaMemsetAsync(p.clip_max, 0x80, sizeof(int) * (size_t)a->n_clips, s));   // keys below every float
+        ACBG_CUDA(cudaMemsetAsync(p.tile_min, 0x7f, sizeof(int) * (size_t)a->n_clips * (size_t)tiles_per_clip, s));   // keys above every float
+    }
     const int64_t n_tiles = tiles_per_clip * a->n_clips;
     const int grid = (int)std::min<int64_t>(n_tiles, fe->num_sms);
     // tensor maps of the sample buffer: usable when every tile start is a whole 128-byte row of a 16-byte aligned buffer
@@ -901,12 +920,9 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     }
     dftgemm_logmel_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, tm128, tm16);
     ACBG_CUDA(cudaGetLastError());
-    if (p.clip_max || a->affine) {
-        const float scale = a->affine ? 1.f / a->affine_std : 1.f;
-        const float shift = a->affine ? -a->affine_mean / a->affine_std : 0.f;
-        const int bx = T >= 1024 ? fe->n_mels : std::max(1, fe->n_mels / 8);     // short rows: several bands per CTA
-        dftgemm_finalize_kernel<<<dim3(bx, a->n_clips), 256, 0, s>>>(a->out, a->out_clip_stride, a->frame_capacity, fe->n_mels, (int)T,
-                                                                     p.clip_max, a->dyn_range, scale, shift);
+    if (p.clip_max) {
+        dftgemm_floor_kernel<<<dim3((unsigned)tiles_per_clip, (unsigned)a->n_clips), 256, 0, s>>>(a->out, a->out_clip_stride, a->frame_capacity, fe->n_mels, (int)T,
+                                                                                           (int)tiles_per_clip, p.clip_max, p.tile_min, a->dyn_range * p.aff_scale);
         ACBG_CUDA(cudaGetLastError());
     }
     return ACB_OK;

@@ -120,13 +120,14 @@ class WhisperLogMel:
         a.affine_mean = float(self.affine_mean or 0.0)
         a.affine_std = self.affine_std
         if self.dyn_range > 0:
-            if self._clip_max is None or self._clip_max.numel() < n_clips:
-                self._clip_max = torch.empty(max(n_clips, 256), dtype=torch.int32, device=self.device)
+            need = int(self._lib.acb_dftgemm_workspace_ints(length, int(self.drop_last_frame), n_clips))
+            if self._clip_max is None or self._clip_max.numel() < need:
+                self._clip_max = torch.empty(need, dtype=torch.int32, device=self.device)
             a.clip_max = self._clip_max.data_ptr()
         stream = _stream_ptr(self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.acb_dftgemm_forward(self._handle, ctypes.byref(a), stream), "acb_dftgemm_forward")
-            self.launches += 1 + int(self.dyn_range > 0 or self.affine_mean is not None)
+            self.launches += 1 + int(self.dyn_range > 0)
             if check:
                 _lib.check(self._lib.acb_dftgemm_check(self._handle, stream), "acb_dftgemm_check")
         return out[:, :, :frames]

@@ -196,6 +196,8 @@ int64_t acb_dftgemm_frames(int64_t length, int drop_last_frame);
 int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_mels, const float* window_host,
                        const float* fb_host, float clamp_min, int log_kind);
 int acb_dftgemm_destroy(acb_dftgemm* fe);
+/* int32 elements of the `clip_max` workspace for n_clips clips of `length` samples: n_clips * (1 + tiles per clip) */
+int64_t acb_dftgemm_workspace_ints(int64_t length, int drop_last_frame, int32_t n_clips);
 
 typedef struct acb_dftgemm_args {
     const float* wav;          /* device: n_clips uniform clips, clip i at wav + i * clip_stride (16-byte aligned rows take the bulk-copy path) */
@@ -210,10 +212,12 @@ typedef struct acb_dftgemm_args {
     int32_t affine;            /* !=0: out = (out - affine_mean) / affine_std afterwards (Whisper: mean -4, std 4) */
     float affine_mean;
     float affine_std;
-    int32_t* clip_max;         /* device [n_clips] workspace, needed when dyn_range > 0 */
+    int32_t* clip_max;         /* device workspace of acb_dftgemm_workspace_ints() int32 (per-clip maximum and per-tile minimum keys),
+                                * needed when dyn_range > 0 */
 } acb_dftgemm_args;
 
-/* One persistent tcgen05 launch (+ one elementwise launch when dyn_range / affine are set) on `stream`. */
+/* One persistent tcgen05 launch on `stream`, plus -- when dyn_range > 0 -- a pass that rewrites only the tiles holding values below
+ * their clip's floor (the kernel records every tile's minimum). */
 int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* args, void* stream);
 /* Synchronises `stream` and reports whether any in-kernel pipeline barrier timed out since the last check. */
 int acb_dftgemm_check(const acb_dftgemm* fe, void* stream);

@@ -75,6 +75,19 @@ def test_lengths_and_frame_counts(fe, L):
         assert np.abs(y - ref).max() < EXPECT
 
 
+def test_row_addressable_batch_with_poisoned_padding(fe):
+    """Row pitch a multiple of 32 samples -> every tile arrives by TMA tensor copies; the samples between a clip's end and the next
+    row (NaN here) are what the copy brings in beyond the clip and must be replaced by the reflection, never reach a valid frame."""
+    L, pitch = 70000, 70016
+    xs = np.stack([o.synth_clip(L, 40 + i) for i in range(3)])
+    big = torch.full((3, pitch), float("nan"), device="cuda")
+    big[:, :L] = dev(xs)
+    y = fe.forward(big[:, :L], check=True).cpu().numpy()
+    assert np.isfinite(y).all()
+    for i in range(3):
+        assert np.abs(y[i] - wo.whisper_logmel(xs[i], fe.window.numpy(), fe.fb.numpy())).max() < EXPECT, i
+
+
 def test_unaligned_rows_take_gather_path(fe):
     L = 33333                                                       # odd row pitch: no 16-byte aligned bulk copies
     xs = np.stack([o.hash_noise(L, 7), o.hash_noise(L, 8)])
