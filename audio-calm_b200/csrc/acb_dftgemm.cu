@@ -639,22 +639,39 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
 }
 
 // Dynamic-range floor of the stored features (WhisperFeatureExtractor: maximum(x, max - 8); the affine (x + 4) / 4 has already been
-// applied and commutes with it).  One CTA per tile of 128 frames; a tile whose minimum is not below its clip's floor -- the common
-// case -- is skipped after two loads, so the pass costs a fraction of a read + write of the features.
+// applied and commutes with it).  One CTA per 4 tiles of 128 frames; a tile whose minimum is not below the floor -- the common
+// case -- is skipped after one load, so the pass costs a fraction of a read + write of the features.
+constexpr int kFloorTilesPerCta = 4;
 __global__ void __launch_bounds__(256) dftgemm_floor_kernel(float* __restrict__ out, long long out_clip_stride, long long frame_capacity, int n_mels,
                                                             int frames, int tiles_per_clip, const int* __restrict__ clip_max,
                                                             const int* __restrict__ tile_min, float range) {
-    const int tic = blockIdx.x, clip = blockIdx.y;
+    const int clip = blockIdx.y;
     const float floor_v = key_float(__ldg(clip_max + clip)) - range;
-    if (!(key_float(__ldg(tile_min + clip * tiles_per_clip + tic)) < floor_v)) return;
-    const int f0 = tic * kTileFrames, nf = min(kTileFrames, frames - f0);
-    float* base = out + (long long)clip * out_clip_stride + f0;
-    for (int i = threadIdx.x; i < n_mels * kTileFrames; i += blockDim.x) {
-        const int b = i / kTileFrames, f = i - b * kTileFrames;
-        if (f < nf) {
-            float* q = base + (long long)b * frame_capacity + f;
-            const float v = *q;
-            if (v < floor_v) *q = floor_v;
+    const int t_end = min(tiles_per_clip, (int)(blockIdx.x + 1) * kFloorTilesPerCta);
+    for (int tic = blockIdx.x * kFloorTilesPerCta; tic < t_end; ++tic) {
+        if (!(key_float(__ldg(tile_min + clip * tiles_per_clip + tic)) < floor_v)) continue;      // CTA-uniform: nothing below the floor
+        const int f0 = tic * kTileFrames, nf = min(kTileFrames, frames - f0);
+        float* base = out + (long long)clip * out_clip_stride + f0;
+        if (nf == kTileFrames && ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(frame_capacity * 4)) & 15) == 0) {
+#pragma unroll 4
+            for (int i = threadIdx.x; i < n_mels * (kTileFrames / 4); i += blockDim.x) {
+                const int b = i / (kTileFrames / 4), f4 = i - b * (kTileFrames / 4);
+                float4* q = reinterpret_cast<float4*>(base + (long long)b * frame_capacity) + f4;
+                float4 v = *q;
+                if (fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < floor_v) {
+                    v.x = fmaxf(v.x, floor_v); v.y = fmaxf(v.y, floor_v); v.z = fmaxf(v.z, floor_v); v.w = fmaxf(v.w, floor_v);
+                    *q = v;
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < n_mels * kTileFrames; i += blockDim.x) {
+                const int b = i / kTileFrames, f = i - b * kTileFrames;
+                if (f < nf) {
+                    float* q = base + (long long)b * frame_capacity + f;
+                    const float v = *q;
+                    if (v < floor_v) *q = floor_v;
+                }
+            }
         }
     }
 }
@@ -921,7 +938,7 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     dftgemm_logmel_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, tm128, tm16);
     ACBG_CUDA(cudaGetLastError());
     if (p.clip_max) {
-        dftgemm_floor_kernel<<<dim3((unsigned)tiles_per_clip, (unsigned)a->n_clips), 256, 0, s>>>(a->out, a->out_clip_stride, a->frame_capacity, fe->n_mels, (int)T,
+        dftgemm_floor_kernel<<<dim3((unsigned)((tiles_per_clip + kFloorTilesPerCta - 1) / kFloorTilesPerCta), (unsigned)a->n_clips), 256, 0, s>>>(a->out, a->out_clip_stride, a->frame_capacity, fe->n_mels, (int)T,
                                                                                            (int)tiles_per_clip, p.clip_max, p.tile_min, a->dyn_range * p.aff_scale);
         ACBG_CUDA(cudaGetLastError());
     }

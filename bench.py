@@ -307,7 +307,7 @@ def main() -> None:
             walg = B * (4 * L + 4 * 80 * wout.shape[2])
             whisper = {"value": B * args.seconds / (wms * 1e-3) / 3600.0, "unit": UNIT, "ms_per_step": wms,
                        "frames_per_s": B * wout.shape[2] / (wms * 1e-3), "roofline_frac": walg / (wms * 1e-3) / 1e9 / peak,
-                       "kernel": "dftgemm_logmel_kernel (tcgen05 DFT-GEMM, n_fft 400 / hop 160; floor and affine fused)",
+                       "kernel": "dftgemm_logmel_kernel (tcgen05 DFT-GEMM, n_fft 400 / hop 160) + dftgemm_floor_kernel (tiles below the floor only)",
                        "note": "extension preset (north-star wording); tools/bench_whisper.py prints its full line"}
             del wfe, wout
         except Exception as e:  # noqa: BLE001

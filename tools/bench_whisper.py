@@ -3,7 +3,7 @@
     python tools/bench_whisper.py [--batch 256] [--steps 50] [--warmup 3] [--no-cpu-baseline]
 
 Workload: 256 x 30 s synthetic 16 kHz clips per GPU -> WhisperFeatureExtractor-compatible features fp32 [256, 80, 3000]
-(one launch: the dynamic-range floor and the affine are applied inside the tcgen05 kernel).  Prints ONE JSON line shaped like bench.py's.
+(both launches: the tcgen05 kernel and the sparse dynamic-range floor pass).  Prints ONE JSON line shaped like bench.py's.
 Algorithmic bytes per frame: 160 samples x 4 B + 80 x 4 B = 960 B; GEMM flops per frame: 4 GEMMs x 3 split terms x 2 x 112 x 112.
 The CPU baseline is the unmodified transformers.WhisperFeatureExtractor (numpy path) on the host cores, bounded sample.
 """
@@ -111,7 +111,7 @@ def main() -> None:
                    "l2": f"inputs {B * L * 4 / 1e6:.1f} MB + outputs {B * 80 * T * 4 / 1e6:.1f} MB per step exceed the 126 MB L2; no flush"},
         "frames_per_s": B * T / (ms * 1e-3), "clocks": clocks, "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "kernel": "dftgemm_logmel_kernel", "kernel_ms": ms, "algorithmic_bytes_per_launch": alg, "peak_source": src},
+                     "kernel": "dftgemm_logmel_kernel + dftgemm_floor_kernel", "kernel_ms": ms, "algorithmic_bytes_per_launch": alg, "peak_source": src},
         "tensor": {"achieved": flops / (ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / tpeak,
                    "flops_per_step": flops, "peak_source": tsrc},
         "cpu_baseline": cpu,
