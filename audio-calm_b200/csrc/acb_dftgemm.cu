@@ -54,6 +54,10 @@ constexpr int kNfft = 400;
 constexpr int kHop = 160;
 constexpr int kBinsAll = 201;
 constexpr int kTileFrames = 128;
+#ifndef ACBG_A_HI_TMEM
+#define ACBG_A_HI_TMEM 1        // 1: the A_hi slices live in the 64 TMEM columns the accumulators leave free (.ts MMAs); 0: all operands in shared memory
+#endif
+constexpr int kAhiCols = 448;                       // first TMEM column of the A_hi stages: [stage][gemm][8 columns = 16 fp16]
 constexpr int kWorkerWarps = 16;                    // all of them run the epilogue (4 per TMEM lane quarter)
 constexpr int kPrepWarps = 8;                       // the first 8 also build the A slices: thread = (frame row, k-half), 16-byte stores
 constexpr int kWorkerThreads = kWorkerWarps * 32;
@@ -160,6 +164,15 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand in tensor memory (M = 128 rows = lanes, K = 16 fp16 = 8 columns of two packed halves), B in shared memory
+__device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -260,6 +273,21 @@ __device__ __forceinline__ void split_store(const float (&v)[8], uint8_t* dst_hi
     *reinterpret_cast<uint4*>(dst_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
+// Same, with the hi halves going to tensor memory: 4 columns (8 packed halves) of this thread's lane at `t_hi`
+__device__ __forceinline__ void split_store_tmem(const float (&v)[8], uint32_t t_hi, uint8_t* dst_lo) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    tmem_st4(t_hi, hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
 // Staged float index of linear position `lin` (= 160 * row + 120 + n).  The tile is staged as rows of 32 floats in the TMA
 // SWIZZLE_128B layout (the 16-byte chunk index within a 128-byte row is XORed with the row index mod 8): frames are 160 floats
 // = 5 rows apart, so the 8 threads of a 16-byte load phase (8 consecutive frames) hit 8 different chunk positions -- no bank
@@ -269,7 +297,7 @@ __device__ __forceinline__ int staged_index(int lin) { return lin ^ (((lin >> 5)
 // One K step of A-operand construction for one thread: 8 consecutive n (n0 .. n0 + 7) of its frame row, for the 4 GEMMs.
 // `srow` = the staged samples, `base` = 160 * row + 120 (linear staged position of the frame's sample 0).
 __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, int base, int n0, const float* __restrict__ s_wf,
-                                               const float* __restrict__ s_wr, uint8_t* dst) {
+                                               const float* __restrict__ s_wr, uint8_t* dst, uint32_t t_hi) {
     float xa[8], xc[8], xb[8], xe[8];
     {
         const float* pa = srow + staged_index(base + n0);              // x[n0 .. n0+7]
@@ -306,10 +334,19 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
             f.dd[i] = dn + dr;
         }
     }
+#if ACBG_A_HI_TMEM
+    split_store_tmem(f.se, t_hi + 0, dst + 1 * kASliceBytes);
+    split_store_tmem(f.so, t_hi + 8, dst + 3 * kASliceBytes);
+    split_store_tmem(f.de, t_hi + 16, dst + 5 * kASliceBytes);
+    split_store_tmem(f.dd, t_hi + 24, dst + 7 * kASliceBytes);
+    tmem_st_wait();
+#else
+    (void)t_hi;
     split_store(f.se, dst + 0 * kASliceBytes, dst + 1 * kASliceBytes);
     split_store(f.so, dst + 2 * kASliceBytes, dst + 3 * kASliceBytes);
     split_store(f.de, dst + 4 * kASliceBytes, dst + 5 * kASliceBytes);
     split_store(f.dd, dst + 6 * kASliceBytes, dst + 7 * kASliceBytes);
+#endif
 }
 
 // Where a tile's samples come from: clip pointer and the clip sample held by staged position 0.  Returns whether the tile is fetched by
@@ -443,9 +480,17 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                         const uint64_t b_hi = make_desc(b_base + (2 * g) * kBSliceBytes, 128, 256);
                         const uint64_t b_lo = make_desc(b_base + (2 * g + 1) * kBSliceBytes, 128, 256);
                         const uint32_t d = tmem + (uint32_t)(g * kNpad);
+#if ACBG_A_HI_TMEM
+                        const uint32_t a_hi_t = tmem + (uint32_t)(kAhiCols + st * 32 + g * 8);
+                        (void)a_hi;
+                        mma_f16_ts(d, a_hi_t, b_hi, idesc, ks > 0);
+                        mma_f16_ss(d, a_lo, b_hi, idesc, 1);
+                        mma_f16_ts(d, a_hi_t, b_lo, idesc, 1);
+#else
                         mma_f16_ss(d, a_hi, b_hi, idesc, ks > 0);
                         mma_f16_ss(d, a_lo, b_hi, idesc, 1);
                         mma_f16_ss(d, a_hi, b_lo, idesc, 1);
+#endif
                     }
                     mma_commit(bar_mma0 + 8 * st);
                     if (ks == kKsteps - 1) mma_commit(bar_tile);
@@ -519,8 +564,10 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     const uint32_t st = (gs + ks) & 1u, use = (gs + ks) >> 1;
                     if (gs + ks >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;   // MMAs that read this stage are complete
                     build_a_slices(s_samples, base, 16 * ks + 8 * hsel, s_wf, s_wr,
-                                   s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16);
+                                   s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16,
+                                   tmem + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(kAhiCols + st * 32 + hsel * 4));
                     fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
+                    tc_fence_before();       // (and the tensor-memory stores of A_hi, completed by tcgen05.wait::st, ordered before the arrive)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_afull0 + 8 * st);
                     if (warp == 0) stamp(0, tile_iter, 1 + ks);
