@@ -54,6 +54,11 @@ constexpr int kNfft = 400;
 constexpr int kHop = 160;
 constexpr int kBinsAll = 201;
 constexpr int kTileFrames = 128;
+// Development-only ablation switch (tools/ablate_dftgemm.sh prices each part of the K loop in situ; results are wrong for n != 0).
+// The shipped library is always built with ACBG_ABLATE == 0.
+#ifndef ACBG_ABLATE
+#define ACBG_ABLATE 0
+#endif
 #ifndef ACBG_A_HI_TMEM
 #define ACBG_A_HI_TMEM 1        // 1: the A_hi slices live in the 64 TMEM columns the accumulators leave free (.ts MMAs); 0: all operands in shared memory
 #endif
@@ -278,11 +283,16 @@ __device__ __forceinline__ void split_store_tmem(const float (&v)[8], uint32_t t
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
+#if ACBG_ABLATE == 5   // byte permutes instead of the split conversions
+        hi[i] = __byte_perm(__float_as_uint(v[2 * i]), __float_as_uint(v[2 * i + 1]), 0x7632) & 0x3fff3fffu;
+        lo[i] = __byte_perm(__float_as_uint(v[2 * i]), __float_as_uint(v[2 * i + 1]), 0x5410) & 0x3fff3fffu;
+#else
         const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
         const float2 hf = __half22float2(h);
         const __half2 l = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
         hi[i] = *reinterpret_cast<const uint32_t*>(&h);
         lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+#endif
     }
     tmem_st4(t_hi, hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(dst_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -317,6 +327,10 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
         const float4 e0 = *reinterpret_cast<const float4*>(pe), e1 = *reinterpret_cast<const float4*>(srow + (staged_index(base + 392 - n0) ^ 4));
         xe[0] = *pe8; xe[1] = e1.w; xe[2] = e1.z; xe[3] = e1.y; xe[4] = e1.x; xe[5] = e0.w; xe[6] = e0.z; xe[7] = e0.y;
     }
+#if ACBG_ABLATE == 2   // no sample loads
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { xa[i] = 0.25f * i + n0; xb[i] = 0.5f; xc[i] = 1.f + n0; xe[i] = 0.125f * i; }
+#endif
     Fold8 f;
     {
         const float4 wf0 = *reinterpret_cast<const float4*>(s_wf + n0), wf1 = *reinterpret_cast<const float4*>(s_wf + n0 + 4);
@@ -334,7 +348,10 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
             f.dd[i] = dn + dr;
         }
     }
-#if ACBG_A_HI_TMEM
+#if ACBG_ABLATE == 3   // no operand stores (and, as dead code, no conversions)
+    if (f.se[0] == 1234.5f && f.so[1] == 3.25f && f.de[2] == 7.f && f.dd[3] == 1.f) dst[0] = 1;
+    (void)t_hi;
+#elif ACBG_A_HI_TMEM
     split_store_tmem(f.se, t_hi + 0, dst + 1 * kASliceBytes);
     split_store_tmem(f.so, t_hi + 8, dst + 3 * kASliceBytes);
     split_store_tmem(f.de, t_hi + 16, dst + 5 * kASliceBytes);
@@ -480,7 +497,9 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                         const uint64_t b_hi = make_desc(b_base + (2 * g) * kBSliceBytes, 128, 256);
                         const uint64_t b_lo = make_desc(b_base + (2 * g + 1) * kBSliceBytes, 128, 256);
                         const uint32_t d = tmem + (uint32_t)(g * kNpad);
-#if ACBG_A_HI_TMEM
+#if ACBG_ABLATE == 4   // no MMAs (the commits still arrive)
+                        (void)a_hi; (void)a_lo; (void)b_hi; (void)b_lo; (void)d;
+#elif ACBG_A_HI_TMEM
                         const uint32_t a_hi_t = tmem + (uint32_t)(kAhiCols + st * 32 + g * 8);
                         (void)a_hi;
                         mma_f16_ts(d, a_hi_t, b_hi, idesc, ks > 0);
@@ -566,7 +585,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     build_a_slices(s_samples, base, 16 * ks + 8 * hsel, s_wf, s_wr,
                                    s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16,
                                    tmem + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(kAhiCols + st * 32 + hsel * 4));
-                    fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
+                    if (ACBG_ABLATE != 1) fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
                     tc_fence_before();       // (and the tensor-memory stores of A_hi, completed by tcgen05.wait::st, ordered before the arrive)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_afull0 + 8 * st);

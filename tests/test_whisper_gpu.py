@@ -126,3 +126,17 @@ def test_benchmark_size_properties(fe):
     ref = wo.whisper_logmel(x[41].cpu().numpy(), fe.window.numpy(), fe.fb.numpy())
     assert np.abs(y1[41].cpu().numpy() - ref).max() < EXPECT
     assert y1.shape == (64, 80, 3000) and torch.isfinite(y1).all()
+
+
+@pytest.mark.parametrize("n_mels", [40, 128])
+def test_other_filterbanks(n_mels):
+    """The route takes any banded filterbank over the 201 bins: a 40-band and a 128-band slaney bank, natural log, no floor."""
+    from audio_calm_b200.tables import slaney_fbanks
+    fb = slaney_fbanks(201, 0.0, 8000.0, n_mels, 16000)
+    fe2 = acb.WhisperLogMel("cuda", n_mels=n_mels, fb=fb, log="ln", clamp_min=1e-5, dyn_range=0.0, affine_mean=None, drop_last_frame=False)
+    x = o.synth_clip(40000, 77)
+    y = fe2.forward(dev(x)[None], check=True)[0].cpu().numpy()
+    p = wo.power_spectrogram(x, fe2.window.numpy())
+    ref = np.log(np.maximum(p @ fb.numpy().astype(np.float64), 1e-5)).T
+    assert y.shape == ref.shape == (n_mels, 251)
+    assert np.abs(y - ref).max() < 1e-4
