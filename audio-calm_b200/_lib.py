@@ -94,6 +94,7 @@ class DftGemmArgs(ctypes.Structure):
         ("affine_mean", ctypes.c_float),
         ("affine_std", ctypes.c_float),
         ("clip_max", ctypes.c_void_p),
+        ("out_dtype", ctypes.c_int32),
     ]
 
 

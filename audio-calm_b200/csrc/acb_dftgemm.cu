@@ -34,6 +34,7 @@
 #include "audiocalm_b200.h"
 
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
@@ -243,7 +244,8 @@ struct Params {
     int tiles_per_clip;
     int frames_out;            // frames stored per clip
     // output
-    float* out;
+    void* out;                 // fp32 or bf16 [n_clips][n_mels][frame_capacity]
+    int out_bf16;
     long long out_clip_stride;
     long long frame_capacity;
     int* clip_max;             // [n_clips] ordered-int keys of the per-clip maximum, or nullptr (no dynamic-range floor)
@@ -641,8 +643,10 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 const int frame0 = tic * kTileFrames + 4 * lane;
                 const int n_valid = p.frames_out - frame0;            // frames of this lane that exist (<= 0: none)
                 const int b_begin = p.band_group[warp], b_end = p.band_group[warp + 1];
-                float* out_col = p.out + (long long)clip * p.out_clip_stride + (long long)b_begin * cap + frame0;
-                const bool vec_store = n_valid >= 4 && ((reinterpret_cast<uintptr_t>(p.out) | (uintptr_t)(p.out_clip_stride * 4) | (uintptr_t)(cap * 4)) & 15) == 0;
+                long long out_col = (long long)clip * p.out_clip_stride + (long long)b_begin * cap + frame0;    // element index in out
+                const int esize = p.out_bf16 ? 2 : 4;
+                // four consecutive frames of a band go out as one 16-byte (fp32) / 8-byte (bf16) store when every row keeps them aligned
+                const bool vec_store = n_valid >= 4 && ((reinterpret_cast<uintptr_t>(p.out) | (uintptr_t)(p.out_clip_stride * esize) | (uintptr_t)(cap * esize)) & (4 * esize - 1)) == 0;
                 float vmax = -3.0e38f, vmin = 3.0e38f;
                 const float aff_scale = p.aff_scale, aff_shift = p.aff_shift;
                 const float4* pow4 = reinterpret_cast<const float4*>(s_pow) + lane;
@@ -671,14 +675,25 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     v.z = fmaf(v.z, aff_scale, aff_shift);
                     v.w = fmaf(v.w, aff_scale, aff_shift);
                     if (vec_store) {
-                        *reinterpret_cast<float4*>(out_col) = v;
+                        if (p.out_bf16) {
+                            const __nv_bfloat162 lo2 = __floats2bfloat162_rn(v.x, v.y), hi2 = __floats2bfloat162_rn(v.z, v.w);
+                            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out) + out_col) =
+                                make_uint2(*reinterpret_cast<const uint32_t*>(&lo2), *reinterpret_cast<const uint32_t*>(&hi2));
+                        } else {
+                            *reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_col) = v;
+                        }
                         vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
                         vmin = fminf(fminf(vmin, fminf(v.x, v.y)), fminf(v.z, v.w));
                     } else {
-                        if (n_valid > 0) { out_col[0] = v.x; vmax = fmaxf(vmax, v.x); vmin = fminf(vmin, v.x); }
-                        if (n_valid > 1) { out_col[1] = v.y; vmax = fmaxf(vmax, v.y); vmin = fminf(vmin, v.y); }
-                        if (n_valid > 2) { out_col[2] = v.z; vmax = fmaxf(vmax, v.z); vmin = fminf(vmin, v.z); }
-                        if (n_valid > 3) { out_col[3] = v.w; vmax = fmaxf(vmax, v.w); vmin = fminf(vmin, v.w); }
+                        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < n_valid) {
+                                if (p.out_bf16) static_cast<__nv_bfloat16*>(p.out)[out_col + j] = __float2bfloat16_rn(vv[j]);
+                                else static_cast<float*>(p.out)[out_col + j] = vv[j];
+                                vmax = fmaxf(vmax, vv[j]);
+                                vmin = fminf(vmin, vv[j]);
+                            }
                     }
                 }
                 if (p.clip_max) {
@@ -708,7 +723,13 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
 // applied and commutes with it).  One CTA per 4 tiles of 128 frames; a tile whose minimum is not below the floor -- the common
 // case -- is skipped after one load, so the pass costs a fraction of a read + write of the features.
 constexpr int kFloorTilesPerCta = 4;
-__global__ void __launch_bounds__(256) dftgemm_floor_kernel(float* __restrict__ out, long long out_clip_stride, long long frame_capacity, int n_mels,
+__device__ __forceinline__ float load_out(const float* q) { return *q; }
+__device__ __forceinline__ float load_out(const __nv_bfloat16* q) { return __bfloat162float(*q); }
+__device__ __forceinline__ void store_out(float* q, float v) { *q = v; }
+__device__ __forceinline__ void store_out(__nv_bfloat16* q, float v) { *q = __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) dftgemm_floor_kernel(T* __restrict__ out, long long out_clip_stride, long long frame_capacity, int n_mels,
                                                             int frames, int tiles_per_clip, const int* __restrict__ clip_max,
                                                             const int* __restrict__ tile_min, float range) {
     const int clip = blockIdx.y;
@@ -717,8 +738,8 @@ __global__ void __launch_bounds__(256) dftgemm_floor_kernel(float* __restrict__ 
     for (int tic = blockIdx.x * kFloorTilesPerCta; tic < t_end; ++tic) {
         if (!(key_float(__ldg(tile_min + clip * tiles_per_clip + tic)) < floor_v)) continue;      // CTA-uniform: nothing below the floor
         const int f0 = tic * kTileFrames, nf = min(kTileFrames, frames - f0);
-        float* base = out + (long long)clip * out_clip_stride + f0;
-        if (nf == kTileFrames && ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(frame_capacity * 4)) & 15) == 0) {
+        T* base = out + (long long)clip * out_clip_stride + f0;
+        if (sizeof(T) == 4 && nf == kTileFrames && ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(frame_capacity * 4)) & 15) == 0) {
 #pragma unroll 4
             for (int i = threadIdx.x; i < n_mels * (kTileFrames / 4); i += blockDim.x) {
                 const int b = i / (kTileFrames / 4), f4 = i - b * (kTileFrames / 4);
@@ -733,9 +754,8 @@ __global__ void __launch_bounds__(256) dftgemm_floor_kernel(float* __restrict__ 
             for (int i = threadIdx.x; i < n_mels * kTileFrames; i += blockDim.x) {
                 const int b = i / kTileFrames, f = i - b * kTileFrames;
                 if (f < nf) {
-                    float* q = base + (long long)b * frame_capacity + f;
-                    const float v = *q;
-                    if (v < floor_v) *q = floor_v;
+                    T* q = base + (long long)b * frame_capacity + f;
+                    if (load_out(q) < floor_v) store_out(q, floor_v);
                 }
             }
         }
@@ -945,6 +965,7 @@ static bool make_sample_map(CUtensorMap* tm, const float* base, long long rows, 
 int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* stream) {
     if (!fe || !a) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: null argument");
     if (!a->wav || !a->out) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: wav and out must be device pointers");
+    if (a->out_dtype != ACB_F32 && a->out_dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: out_dtype must be ACB_F32 or ACB_BF16");
     if (a->n_clips <= 0) return ACB_OK;
     const int64_t T = acb_dftgemm_frames(a->length, a->drop_last_frame);
     if (T < 0) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: clips of " + std::to_string(a->length) + " samples; reflect padding needs more than " + std::to_string(kNfft / 2));
@@ -977,6 +998,7 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     p.tiles_per_clip = (int)tiles_per_clip;
     p.frames_out = (int)T;
     p.out = a->out;
+    p.out_bf16 = a->out_dtype == ACB_BF16;
     p.out_clip_stride = a->out_clip_stride;
     p.frame_capacity = a->frame_capacity;
     p.clip_max = a->dyn_range > 0.f ? a->clip_max : nullptr;
@@ -1004,8 +1026,13 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     dftgemm_logmel_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, tm128, tm16);
     ACBG_CUDA(cudaGetLastError());
     if (p.clip_max) {
-        dftgemm_floor_kernel<<<dim3((unsigned)((tiles_per_clip + kFloorTilesPerCta - 1) / kFloorTilesPerCta), (unsigned)a->n_clips), 256, 0, s>>>(a->out, a->out_clip_stride, a->frame_capacity, fe->n_mels, (int)T,
-                                                                                           (int)tiles_per_clip, p.clip_max, p.tile_min, a->dyn_range * p.aff_scale);
+        const dim3 fgrid((unsigned)((tiles_per_clip + kFloorTilesPerCta - 1) / kFloorTilesPerCta), (unsigned)a->n_clips);
+        if (p.out_bf16)
+            dftgemm_floor_kernel<__nv_bfloat16><<<fgrid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(a->out), a->out_clip_stride, a->frame_capacity, fe->n_mels,
+                                                                     (int)T, (int)tiles_per_clip, p.clip_max, p.tile_min, a->dyn_range * p.aff_scale);
+        else
+            dftgemm_floor_kernel<float><<<fgrid, 256, 0, s>>>(static_cast<float*>(a->out), a->out_clip_stride, a->frame_capacity, fe->n_mels, (int)T,
+                                                             (int)tiles_per_clip, p.clip_max, p.tile_min, a->dyn_range * p.aff_scale);
         ACBG_CUDA(cudaGetLastError());
     }
     return ACB_OK;

@@ -89,8 +89,9 @@ class WhisperLogMel:
                                f"padding ({self.n_fft // 2}, {self.n_fft // 2}) at dimension 2 of input of length {length}")
         return t
 
-    def forward(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None, check: bool = False) -> torch.Tensor:
-        """``wav`` fp32 CUDA ``[B, L]`` (rows may be strided) -> ``[B, n_mels, frames]`` fp32."""
+    def forward(self, wav: torch.Tensor, out: Optional[torch.Tensor] = None, check: bool = False,
+                out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+        """``wav`` fp32 CUDA ``[B, L]`` (rows may be strided) -> ``[B, n_mels, frames]`` fp32 (or bf16: ``out_dtype`` / the dtype of ``out``)."""
         if not wav.is_cuda or wav.device != self.device:
             raise RuntimeError(f"expected a CUDA tensor on {self.device}, got {wav.device} (no CPU fallback)")
         if wav.dtype != torch.float32:
@@ -100,10 +101,10 @@ class WhisperLogMel:
         n_clips, length = int(wav.shape[0]), int(wav.shape[1])
         frames = self.frames_for_length(length)
         if out is None:
-            out = torch.empty((n_clips, self.n_mels, frames), dtype=torch.float32, device=self.device)
-        if out.dtype != torch.float32 or out.device != self.device or tuple(out.shape[:2]) != (n_clips, self.n_mels) \
+            out = torch.empty((n_clips, self.n_mels, frames), dtype=out_dtype, device=self.device)
+        if out.dtype not in (torch.float32, torch.bfloat16) or out.device != self.device or tuple(out.shape[:2]) != (n_clips, self.n_mels) \
                 or out.shape[2] < frames or out.stride(2) != 1 or out.stride(1) != out.shape[2]:
-            raise ValueError("out must be a float32 [B, n_mels, >= frames] tensor with contiguous rows on the same device")
+            raise ValueError("out must be a float32 / bfloat16 [B, n_mels, >= frames] tensor with contiguous rows on the same device")
         if n_clips == 0 or frames == 0:
             return out[:, :, :frames]
         a = DftGemmArgs()
@@ -113,6 +114,7 @@ class WhisperLogMel:
         a.n_clips = n_clips
         a.drop_last_frame = int(self.drop_last_frame)
         a.out = out.data_ptr()
+        a.out_dtype = _lib.ACB_BF16 if out.dtype == torch.bfloat16 else _lib.ACB_F32
         a.out_clip_stride = int(out.stride(0)) if n_clips > 1 else self.n_mels * int(out.shape[2])
         a.frame_capacity = int(out.shape[2])
         a.dyn_range = self.dyn_range

@@ -205,7 +205,7 @@ typedef struct acb_dftgemm_args {
     int64_t length;            /* samples per clip (Whisper pads / trims to 480000 on the host side) */
     int32_t n_clips;
     int32_t drop_last_frame;   /* !=0: store frames [0, L / 160) */
-    float* out;                /* device fp32 [n_clips][n_mels][frame_capacity] */
+    void* out;                 /* device fp32 or bf16 [n_clips][n_mels][frame_capacity] */
     int64_t out_clip_stride;   /* elements */
     int64_t frame_capacity;    /* >= frames */
     float dyn_range;           /* > 0: out = max(out, max over the clip - dyn_range) (Whisper: 8.0); <= 0: none */
@@ -214,6 +214,7 @@ typedef struct acb_dftgemm_args {
     float affine_std;
     int32_t* clip_max;         /* device workspace of acb_dftgemm_workspace_ints() int32 (per-clip maximum and per-tile minimum keys),
                                 * needed when dyn_range > 0 */
+    int32_t out_dtype;         /* ACB_F32 | ACB_BF16 (the affine is applied in fp32 before the single rounding) */
 } acb_dftgemm_args;
 
 /* One persistent tcgen05 launch on `stream`, plus -- when dyn_range > 0 -- a pass that rewrites only the tiles holding values below
