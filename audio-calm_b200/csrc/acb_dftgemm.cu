@@ -249,7 +249,7 @@ struct Params {
     long long out_clip_stride;
     long long frame_capacity;
     int* clip_max;             // [n_clips] ordered-int keys of the per-clip maximum, or nullptr (no dynamic-range floor)
-    int* tile_min;             // [n_clips * tiles_per_clip] ordered-int keys of the per-tile minimum (tiles above the floor are skipped later)
+    int* tile_min;             // [n_clips * tiles_per_clip] ordered-int keys of MINUS the per-tile minimum (tiles above the floor are skipped later)
     float aff_scale, aff_shift;   // out = v * aff_scale + aff_shift (1, 0 when no affine)
     int* error_flag;           // set to 1 when a barrier wait timed out
     int use_tma;               // the batch is 128-byte row addressable (16-byte aligned base, clip_stride % 32 == 0): tensor copies
@@ -702,7 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     if (lane == 0 && vmax > -3.0e38f) atomicMax(p.clip_max + clip, float_key(vmax));
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-                    if (lane == 0 && vmin < 3.0e38f) atomicMin(p.tile_min + tile, float_key(vmin));
+                    if (lane == 0 && vmin < 3.0e38f) atomicMax(p.tile_min + tile, float_key(-vmin));   // key of -min: same initial pattern as clip_max
                 }
                 if (warp == 0) stamp(0, tile_iter, 10);
                 worker_sync();       // nobody reads the power tile any more: the operand stages may be refilled
@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(256) dftgemm_floor_kernel(T* __restrict__ out,
     const float floor_v = key_float(__ldg(clip_max + clip)) - range;
     const int t_end = min(tiles_per_clip, (int)(blockIdx.x + 1) * kFloorTilesPerCta);
     for (int tic = blockIdx.x * kFloorTilesPerCta; tic < t_end; ++tic) {
-        if (!(key_float(__ldg(tile_min + clip * tiles_per_clip + tic)) < floor_v)) continue;      // CTA-uniform: nothing below the floor
+        if (!(-key_float(__ldg(tile_min + clip * tiles_per_clip + tic)) < floor_v)) continue;     // CTA-uniform: nothing below the floor
         const int f0 = tic * kTileFrames, nf = min(kTileFrames, frames - f0);
         T* base = out + (long long)clip * out_clip_stride + f0;
         if (sizeof(T) == 4 && nf == kTileFrames && ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(frame_capacity * 4)) & 15) == 0) {
@@ -1007,10 +1007,8 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     p.aff_shift = a->affine ? -a->affine_mean / a->affine_std : 0.f;
     p.error_flag = fe->d_err;
     p.trace = fe->d_trace;
-    if (p.clip_max) {
-        ACBG_CUDA(cudaMemsetAsync(p.clip_max, 0x80, sizeof(int) * (size_t)a->n_clips, s));   // keys below every float
-        ACBG_CUDA(cudaMemsetAsync(p.tile_min, 0x7f, sizeof(int) * (size_t)a->n_clips * (size_t)tiles_per_clip, s));   // keys above every float
-    }
+    if (p.clip_max)   // one fill for both arrays: keys below every float (tile_min holds keys of the negated minimum)
+        ACBG_CUDA(cudaMemsetAsync(p.clip_max, 0x80, sizeof(int) * (size_t)a->n_clips * (size_t)(1 + tiles_per_clip), s));
     const int64_t n_tiles = tiles_per_clip * a->n_clips;
     const int grid = (int)std::min<int64_t>(n_tiles, fe->num_sms);
     // tensor maps of the sample buffer: usable when every tile start is a whole 128-byte row of a 16-byte aligned buffer

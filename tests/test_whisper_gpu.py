@@ -140,3 +140,21 @@ def test_other_filterbanks(n_mels):
     ref = np.log(np.maximum(p @ fb.numpy().astype(np.float64), 1e-5)).T
     assert y.shape == ref.shape == (n_mels, 251)
     assert np.abs(y - ref).max() < 1e-4
+
+
+def test_bf16_output(fe):
+    """bf16 features (affine applied in fp32, one rounding): within 1e-2 of the fp32 oracle, floor included."""
+    xs = np.stack([o.synth_clip(48000, 50 + i) for i in range(3)])
+    y = fe.forward(dev(xs), check=True, out_dtype=torch.bfloat16)
+    assert y.dtype == torch.bfloat16 and tuple(y.shape) == (3, 80, 300)
+    y32 = fe.forward(dev(xs), check=True).cpu().numpy()
+    for i in range(3):
+        ref = wo.whisper_logmel(xs[i], fe.window.numpy(), fe.fb.numpy())
+        assert np.abs(y[i].float().cpu().numpy() - ref).max() < 1e-2, i
+        assert np.abs(y32[i] - ref).max() < EXPECT
+    # same values as rounding the fp32 result (the floor value itself is rounded once, too)
+    assert torch.equal(y.cpu(), torch.from_numpy(y32).to(torch.bfloat16))
+    # odd row pitch: scalar store path
+    buf = torch.zeros((3, 80, 301), dtype=torch.bfloat16, device="cuda")
+    y2 = fe.forward(dev(xs), out=buf, check=True)
+    assert torch.equal(y2.cpu(), y.cpu())
