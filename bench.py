@@ -183,6 +183,8 @@ def main() -> None:
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # keeps "NCCL version ..." off stdout: rank 0 prints ONE JSON line
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
 
     warm = max(args.warmup, 3)                       # timing rule: at least 3 warm-up steps
