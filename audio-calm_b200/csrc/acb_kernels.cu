@@ -451,6 +451,39 @@ __device__ __forceinline__ void store_tile(const LogmelParams& p, const ClipCurs
     }
 }
 
+// Fill `n` elements at `ptr` with `fv`: scalar head / tail around 16-byte stores, `nt` cooperating threads (index t)
+template <typename OutT>
+__device__ __forceinline__ void fill_span(OutT* ptr, long long n, OutT fv, int t, int nt) {
+    constexpr int per16 = 16 / (int)sizeof(OutT);
+    const long long head = min(n, (long long)(((16 - (reinterpret_cast<uintptr_t>(ptr) & 15)) & 15) / sizeof(OutT)));
+    for (long long i = t; i < head; i += nt) ptr[i] = fv;
+    const long long body = (n - head) / per16;
+    unsigned w;
+    if (sizeof(OutT) == 4) w = *reinterpret_cast<const unsigned*>(&fv);
+    else { const unsigned short h = *reinterpret_cast<const unsigned short*>(&fv); w = (unsigned)h | ((unsigned)h << 16); }
+    uint4* q = reinterpret_cast<uint4*>(ptr + head);
+    for (long long i = t; i < body; i += nt) q[i] = make_uint4(w, w, w, w);
+    for (long long i = head + body * per16 + t; i < n; i += nt) ptr[i] = fv;
+}
+
+// Padded batches with a tile plan (tiles cover only the frames that exist): the group that stores a clip's last tile also sets the
+// rest of the clip's row, frames [end of the tile, frame_capacity), to the fill value -- one vectorised sweep instead of one
+// near-empty tile per 8 frames.
+template <typename OutT>
+__device__ __forceinline__ void fill_row_tail(const LogmelParams& p, const ClipCursor& c, int n_mels, int tid) {
+    const int f_begin = (c.tile_in_clip + 1) * kTileFrames;
+    const long long n_fill = (long long)c.cap - f_begin;
+    if (n_fill <= 0) return;
+    OutT* out = reinterpret_cast<OutT*>(p.out) + c.out_base;
+    const OutT fv = to_out<OutT>(p.fill_value);
+    if (p.time_major) {
+        fill_span<OutT>(out + (size_t)f_begin * n_mels, n_fill * n_mels, fv, tid, kGroupThreads);
+    } else {
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int b = warp; b < n_mels; b += kGroupWarps) fill_span<OutT>(out + (size_t)b * c.cap + f_begin, n_fill, fv, lane, 32);
+    }
+}
+
 // log2 of a value known to be a normal float (it is above the clamp): the bare MUFU.LG2, without __log2f's denormal rescue
 __device__ __forceinline__ float lg2_normal(float x) {
     float y;
@@ -744,7 +777,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
         }
         if (!direct) {   // group-uniform
             group_sync(grp);  // output tile staged
-            if (write_out) store_tile<OutT>(p, cur, s_out, n_mels, S, gt);
+            if (write_out) {
+                store_tile<OutT>(p, cur, s_out, n_mels, S, gt);
+                if (p.fill_tail && p.tile_start != nullptr && cur.tile_in_clip == cur.tiles_in_clip - 1) fill_row_tail<OutT>(p, cur, n_mels, gt);
+            }
         }
         cur = nxt;
     }

@@ -251,18 +251,14 @@ class LogMelFrontend:
         a.wav = batch.wav.data_ptr()
         a.clip_offset = batch.offsets.data_ptr()
         a.clip_length = batch.lengths.data_ptr()
-        tile_start_t = None
-        if stats_only:
-            # only the frames that exist are visited: per-clip tile counts differ -> host plan (prefix sums) shipped to the device
-            tile_start = np.zeros(B + 1, dtype=np.int32)
-            n_tiles = int(self._lib.acb_plan_tiles(lens.ctypes.data, B, self.n_fft, self.hop, 0, tile_start.ctypes.data))
-            if n_tiles < 0:
-                _lib.check(n_tiles, "acb_plan_tiles")
-            tile_start_t = torch.from_numpy(tile_start).to(self.device, non_blocking=True)
-            a.tile_start = tile_start_t.data_ptr()
-        else:
-            # padded output: every clip covers its whole row, so the tile count per clip is uniform and no plan is needed
-            n_tiles = B * ((cap + self.frames_per_tile - 1) // self.frames_per_tile)
+        # only the frames that exist are visited: per-clip tile counts differ -> host plan (prefix sums) shipped to the device.
+        # For padded outputs the group that stores a clip's last tile also fills the rest of the row with fill_value.
+        tile_start = np.zeros(B + 1, dtype=np.int32)
+        n_tiles = int(self._lib.acb_plan_tiles(lens.ctypes.data, B, self.n_fft, self.hop, 0, tile_start.ctypes.data))
+        if n_tiles < 0:
+            _lib.check(n_tiles, "acb_plan_tiles")
+        tile_start_t = torch.from_numpy(tile_start).to(self.device, non_blocking=True)
+        a.tile_start = tile_start_t.data_ptr()
         a.n_clips = B
         a.n_tiles = n_tiles
         a.out_clip_stride = self.n_mels * cap

@@ -96,7 +96,8 @@ typedef struct acb_logmel_args {
     int64_t frame_capacity;      /* frames per clip row in `out` (row pitch of MEL_MAJOR; >= padded frames) */
     const int64_t* frame_capacity_per_clip; /* device [n_clips] overrides frame_capacity (packed outputs) or NULL */
     int32_t pad_multiple;        /* 1 = none, 4 = reflect-pad the time axis (process_dataset.py:146-150) */
-    int32_t fill_tail;           /* !=0: frames [padded, frame_capacity) are set to fill_value (ragged batches) */
+    int32_t fill_tail;           /* !=0: frames [padded, frame_capacity) are set to fill_value (ragged batches); with a tile plan
+                                  * (tile_start) the clip's last tile fills the rest of its row in one sweep */
     float fill_value;
     /* ---- optional fused affine normalisation (models/modeling_vae.py:317-319) ---- */
     int32_t affine;              /* 0 none, 1 scalar (affine_mean/affine_std), 2 per-bin arrays */
