@@ -158,3 +158,22 @@ def test_bf16_output(fe):
     buf = torch.zeros((3, 80, 301), dtype=torch.bfloat16, device="cuda")
     y2 = fe.forward(dev(xs), out=buf, check=True)
     assert torch.equal(y2.cpu(), y.cpu())
+
+
+def test_seeded_shape_fuzz(fe):
+    """Random batch sizes, lengths and row pitches (both staging paths: TMA tensor copies when the pitch is a multiple of 32
+    samples, worker gather otherwise) against the oracle."""
+    rng = np.random.default_rng(20261018)
+    for case in range(10):
+        B = int(rng.integers(1, 5))
+        L = int(rng.integers(201, 60000))
+        pitch = L + int(rng.integers(0, 40)) if case % 2 else ((L + 31) // 32) * 32
+        xs = np.stack([o.hash_noise(L, 1000 + 10 * case + i) * float(rng.uniform(0.05, 1.5)) for i in range(B)])
+        big = torch.randn((B, pitch), device="cuda")                    # whatever lies between the rows must not matter
+        big[:, :L] = dev(xs)
+        y = fe.forward(big[:, :L], check=True).cpu().numpy()
+        assert y.shape == (B, 80, L // 160), (case, B, L, pitch)
+        for i in range(B):
+            if y.shape[2]:
+                ref = wo.whisper_logmel(xs[i], fe.window.numpy(), fe.fb.numpy())
+                assert np.abs(y[i] - ref).max() < EXPECT, (case, B, L, pitch, i)
