@@ -83,6 +83,9 @@ def test_abi_host_logic(built_lib):
     assert lib.acb_dftgemm_frames(201, 1) == 1 and lib.acb_dftgemm_frames(200, 1) == -1
     for L in (201, 999, 16000, 20011, 480000):
         assert lib.acb_dftgemm_frames(L, 1) == wo.frames_for_length(L)
+    # workspace of the dynamic-range floor: one maximum per clip + one minimum per tile of 128 frames
+    assert lib.acb_dftgemm_workspace_ints(480000, 1, 256) == 256 * (1 + 24)
+    assert lib.acb_dftgemm_workspace_ints(16000, 1, 3) == 3 * (1 + 1) and lib.acb_dftgemm_workspace_ints(200, 1, 3) == -1
     # create() validates before touching the device: wrong transform size, asymmetric window
     h = ctypes.c_void_p()
     w, fb = acb.whisper_tables()
