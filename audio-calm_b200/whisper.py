@@ -136,6 +136,49 @@ class WhisperLogMel:
 
     __call__ = forward
 
+    def forward_host(self, wav_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, n_chunks: int = 8) -> torch.Tensor:
+        """Host buffers in and out (pinned memory for overlap): the batch is cut into ``n_chunks`` groups of clips; the H2D copy of
+        group i+1, the kernels of group i and the D2H copy of group i-1 run on three streams.  Returns ``out_host``
+        (``[B, n_mels, frames]`` fp32) after synchronising."""
+        if wav_host.is_cuda or wav_host.dtype != torch.float32 or wav_host.dim() != 2:
+            raise ValueError("wav_host must be a float32 host tensor [B, L]")
+        n_clips, length = int(wav_host.shape[0]), int(wav_host.shape[1])
+        frames = self.frames_for_length(length)
+        if out_host is None:
+            out_host = torch.empty((n_clips, self.n_mels, frames), dtype=torch.float32, pin_memory=True)
+        n_chunks = max(1, min(int(n_chunks), n_clips))
+        bounds = [n_clips * i // n_chunks for i in range(n_chunks + 1)]
+        st = getattr(self, "_host_state", None)
+        if st is None or st[0].shape != (n_clips, length):
+            st = (torch.empty((n_clips, length), dtype=torch.float32, device=self.device),
+                  torch.empty((n_clips, self.n_mels, frames), dtype=torch.float32, device=self.device),
+                  torch.cuda.Stream(self.device), torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+            self._host_state = st
+        dev_in, dev_out, s_in, s_run, s_out = st
+        cur = torch.cuda.current_stream(self.device)
+        for s_ in (s_in, s_run, s_out):
+            s_.wait_stream(cur)
+        for i in range(n_chunks):
+            a, b = bounds[i], bounds[i + 1]
+            if a == b:
+                continue
+            with torch.cuda.stream(s_in):
+                dev_in[a:b].copy_(wav_host[a:b], non_blocking=True)
+                e_in = torch.cuda.Event()
+                e_in.record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(e_in)
+                self.forward(dev_in[a:b], out=dev_out[a:b])
+                e_run = torch.cuda.Event()
+                e_run.record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(e_run)
+                out_host[a:b].copy_(dev_out[a:b], non_blocking=True)
+        for s_ in (s_in, s_run, s_out):
+            cur.wait_stream(s_)
+        cur.synchronize()
+        return out_host
+
     def extract(self, clips: Sequence[torch.Tensor], n_samples: int = WHISPER_CHUNK_SAMPLES, check: bool = False) -> torch.Tensor:
         """``WhisperFeatureExtractor.__call__`` semantics: every clip is zero-padded or trimmed to ``n_samples`` (30 s) before the
         STFT, so the result is ``[len(clips), n_mels, n_samples // 160]``."""

@@ -177,3 +177,10 @@ def test_seeded_shape_fuzz(fe):
             if y.shape[2]:
                 ref = wo.whisper_logmel(xs[i], fe.window.numpy(), fe.fb.numpy())
                 assert np.abs(y[i] - ref).max() < EXPECT, (case, B, L, pitch, i)
+
+
+def test_forward_host_matches_device_path(fe):
+    xs = torch.from_numpy(np.stack([o.synth_clip(32000, 60 + i) for i in range(5)]))
+    y_dev = fe.forward(xs.cuda(), check=True).cpu()
+    y_host = fe.forward_host(xs.pin_memory(), n_chunks=3)
+    assert torch.equal(y_host, y_dev)
