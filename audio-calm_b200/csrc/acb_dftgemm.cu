@@ -65,7 +65,11 @@ constexpr int kTileFrames = 128;
 #endif
 constexpr int kAhiCols = 448;                       // first TMEM column of the A_hi stages: [stage][gemm][8 columns = 16 fp16]
 constexpr int kWorkerWarps = 16;                    // all of them run the epilogue (4 per TMEM lane quarter)
-constexpr int kPrepWarps = 8;                       // the first 8 also build the A slices: thread = (frame row, k-half), 16-byte stores
+#ifndef ACBG_PREP_WARPS
+#define ACBG_PREP_WARPS 8
+#endif
+constexpr int kPrepWarps = ACBG_PREP_WARPS;         // 8: the first 8 warps build the A slices, thread = (frame row, k-half), 16-byte stores;
+                                                    // 16 (experiment): all of them, thread = (frame row, quarter of the K step), 8-byte stores
 constexpr int kWorkerThreads = kWorkerWarps * 32;
 constexpr int kThreads = kWorkerThreads + 64;      // + one MMA issuer warp + one B-slice loader warp (one elected lane each)
 constexpr int kKpad = 112;                       // K of every GEMM (n = 0..100 used)
@@ -177,6 +181,9 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uin
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t r0, uint32_t r1) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r0), "r"(r1) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
@@ -366,6 +373,47 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
     split_store(f.de, dst + 4 * kASliceBytes, dst + 5 * kASliceBytes);
     split_store(f.dd, dst + 6 * kASliceBytes, dst + 7 * kASliceBytes);
 #endif
+}
+
+// Experiment (ACBG_PREP_WARPS == 16): 4 consecutive n per thread; hi halves -> 2 TMEM columns, lo halves -> one 8-byte store
+__device__ __forceinline__ void split_store_tmem4(const float (&v)[4], uint32_t t_hi, uint8_t* dst_lo) {
+    uint32_t hi[2], lo[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    tmem_st2(t_hi, hi[0], hi[1]);
+    *reinterpret_cast<uint2*>(dst_lo) = make_uint2(lo[0], lo[1]);
+}
+__device__ __forceinline__ void build_a_slices4(const float* __restrict__ srow, int base, int n0, const float* __restrict__ s_wf,
+                                                const float* __restrict__ s_wr, uint8_t* dst, uint32_t t_hi) {
+    const float4 a = *reinterpret_cast<const float4*>(srow + staged_index(base + n0));              // x[n0 .. n0+3]
+    const float4 c = *reinterpret_cast<const float4*>(srow + staged_index(base + 200 + n0));        // x[200+n0 .. 200+n0+3]
+    const float4 b = *reinterpret_cast<const float4*>(srow + staged_index(base + 196 - n0));        // x[196-n0 .. 199-n0]
+    const float b4 = srow[staged_index(base + 200 - n0)];                                            // x[200-n0]
+    const float4 e = *reinterpret_cast<const float4*>(srow + staged_index(base + 396 - n0));        // x[396-n0 .. 399-n0]
+    const float e4 = srow[staged_index(base + (n0 == 0 ? 0 : 400 - n0))];                            // x[400-n0], index taken mod 400
+    const float4 wf = *reinterpret_cast<const float4*>(s_wf + n0), wr = *reinterpret_cast<const float4*>(s_wr + n0);
+    const float xa[4] = {a.x, a.y, a.z, a.w}, xc[4] = {c.x, c.y, c.z, c.w};
+    const float xb[4] = {b4, b.w, b.z, b.y}, xe[4] = {e4, e.w, e.z, e.y};
+    const float wa[4] = {wf.x, wf.y, wf.z, wf.w}, wb[4] = {wr.x, wr.y, wr.z, wr.w};
+    float se[4], so[4], de[4], dd[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float pa = wa[i] * xa[i], pe = wa[i] * xe[i];
+        const float pb = wb[i] * xb[i], pc = wb[i] * xc[i];
+        const float sn = pa + pc, sr = pb + pe, dn = pa - pc, dr = pb - pe;
+        se[i] = sn + sr; so[i] = sn - sr; de[i] = dn - dr; dd[i] = dn + dr;
+    }
+    split_store_tmem4(se, t_hi + 0, dst + 1 * kASliceBytes);
+    split_store_tmem4(so, t_hi + 8, dst + 3 * kASliceBytes);
+    split_store_tmem4(de, t_hi + 16, dst + 5 * kASliceBytes);
+    split_store_tmem4(dd, t_hi + 24, dst + 7 * kASliceBytes);
+    tmem_st_wait();
 }
 
 // Where a tile's samples come from: clip pointer and the clip sample held by staged position 0.  Returns whether the tile is fetched by
@@ -584,9 +632,14 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 for (int ks = 0; ks < kKsteps; ++ks) {
                     const uint32_t st = (gs + ks) & 1u, use = (gs + ks) >> 1;
                     if (gs + ks >= 2) ok = mbar_wait(bar_mma0 + 8 * st, (use - 1) & 1u) && ok;   // MMAs that read this stage are complete
-                    build_a_slices(s_samples, base, 16 * ks + 8 * hsel, s_wf, s_wr,
-                                   s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16,
-                                   tmem + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(kAhiCols + st * 32 + hsel * 4));
+                    if (kPrepWarps == 8)
+                        build_a_slices(s_samples, base, 16 * ks + 8 * hsel, s_wf, s_wr,
+                                       s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16,
+                                       tmem + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(kAhiCols + st * 32 + hsel * 4));
+                    else
+                        build_a_slices4(s_samples, base, 16 * ks + 4 * qsel, s_wf, s_wr,
+                                        s_a + st * kAStageBytes + (qsel >> 1) * (kTileFrames * 16) + row * 16 + (qsel & 1) * 8,
+                                        tmem + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(kAhiCols + st * 32 + qsel * 2));
                     if (ACBG_ABLATE != 1) fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
                     tc_fence_before();       // (and the tensor-memory stores of A_hi, completed by tcgen05.wait::st, ordered before the arrive)
                     __syncwarp();
