@@ -16,19 +16,21 @@
 // fp32 accuracy from fp16 tensor cores: A = A_hi + A_lo, B = B_hi + B_lo (fp16 pairs, 22 significant bits),
 // D = A_hi B_hi + A_lo B_hi + A_hi B_lo accumulated in fp32 in TMEM (measured 2e-6 on the final features).
 //
-// Kernel (persistent, one CTA per SM, tiles of 128 frames of one clip; 8 worker warps + 1 MMA issuer warp + 1 loader warp, every
+// Kernel (persistent, one CTA per SM, tiles of 128 frames of one clip; 16 worker warps + 1 MMA issuer warp + 1 loader warp, every
 // hand-off an mbarrier):
-//   1. loader warp: the tile's samples are staged in shared memory by bulk async copies (one per 160-sample hop block, rows padded
-//      to 164 floats so a warp's 16-byte loads of 32 different frames are conflict-free) while the previous tile's epilogue runs;
-//      edge tiles (reflection about sample 0 / L-1) are gathered by the workers;
-//   2. K loop, 7 steps of 16: the workers (thread = frame row x k-half) build the step's A slices (window, folds, fp16 hi/lo split
-//      with packed conversions) in the canonical K-major no-swizzle core-matrix layout; the loader streams the step's B slices
-//      (28 KB of the 200 KB DFT matrices, L2-resident) with one bulk copy; the issuer's elected lane issues 12 tcgen05.mma
-//      (M 128, N 112, K 16, kind::f16) and commits to mbarriers.  A and B are double-buffered: the MMAs of step k run under the
-//      CUDA-core work of step k+1;
-//   3. epilogue: tcgen05.ld of the four accumulators, |X|^2 into shared memory as [bin][frame] (the operand stages are idle),
-//      then the banded mel projection with lane = 4 consecutive frames (one 16-byte load per bin) and warp = a group of bands
-//      (warp-uniform weights), clamp, log, 512-byte band stores, per-clip max by atomicMax;
+//   1. loader warp: the tile's 20960 samples are staged in shared memory by 6 TMA tensor copies (the batch viewed as rows of 32
+//      floats, SWIZZLE_128B: frames are 5 rows apart, so a warp's 16-byte loads of 32 different frames are conflict-free) while
+//      the previous tile's epilogue runs; positions outside the clip (reflection about sample 0 / L-1) are patched by the workers;
+//      batches that are not 128-byte row addressable are gathered by the workers instead;
+//   2. K loop, 7 steps of 16: the first 8 worker warps (thread = frame row x k-half) build the step's A slices (window, folds, fp16
+//      hi/lo split with packed conversions): the lo halves go to shared memory in the canonical K-major no-swizzle core-matrix
+//      layout, the hi halves to the 64 TMEM columns the accumulators leave free (tcgen05.st; the MMAs that use them take A from
+//      tensor memory); the loader streams the step's B slices (28 KB of the 200 KB DFT matrices, L2-resident) with one bulk copy;
+//      the issuer's elected lane issues 12 tcgen05.mma (M 128, N 112, K 16, kind::f16) and commits to mbarriers.  A and B are
+//      double-buffered: the MMAs of step k run under the CUDA-core work of step k+1;
+//   3. epilogue (all 16 worker warps): tcgen05.ld of the four accumulators, |X|^2 into shared memory as [bin][frame] (the operand
+//      stages are idle), then the banded mel projection with lane = 4 consecutive frames (one 16-byte load per bin) and warp = a
+//      group of bands (warp-uniform weights), clamp, log, affine, 512-byte band stores, per-clip max / per-tile min by atomics;
 //   4. the affine (x + 4) / 4 is applied at the store (it commutes with the floor); the kernel also records the minimum of every tile,
 //      so the second kernel (dynamic-range floor, per-clip max - 8) only touches the tiles that hold values below the floor.
 #include "audiocalm_b200.h"
