@@ -184,3 +184,20 @@ def test_forward_host_matches_device_path(fe):
     y_dev = fe.forward(xs.cuda(), check=True).cpu()
     y_host = fe.forward_host(xs.pin_memory(), n_chunks=3)
     assert torch.equal(y_host, y_dev)
+
+
+@pytest.mark.parametrize("L,B,dtype", [(70000, 3, torch.float32), (20011, 2, torch.float32), (48000, 2, torch.bfloat16)])
+def test_guard_bands_untouched(fe, L, B, dtype):
+    """Nothing is written outside out[:, :, :frames]: sentinel columns inside the rows and sentinel elements before / after the
+    buffer must survive both kernels (the tcgen05 kernel and the floor pass)."""
+    frames, cap, guard = L // 160, L // 160 + 13, 4096
+    flat = torch.full((guard + B * 80 * cap + guard,), 777.0, dtype=dtype, device="cuda")
+    out = flat[guard:guard + B * 80 * cap].view(B, 80, cap)
+    xs = np.stack([o.synth_clip(L, 70 + i) for i in range(B)])
+    y = fe.forward(dev(xs), out=out, check=True)
+    assert tuple(y.shape) == (B, 80, frames)
+    assert torch.all(flat[:guard] == 777.0) and torch.all(flat[guard + B * 80 * cap:] == 777.0)
+    assert torch.all(out[:, :, frames:] == 777.0)
+    tol = EXPECT if dtype == torch.float32 else 1e-2
+    for i in range(B):
+        assert np.abs(y[i].float().cpu().numpy() - wo.whisper_logmel(xs[i], fe.window.numpy(), fe.fb.numpy())).max() < tol
