@@ -352,6 +352,23 @@ __device__ __forceinline__ void group_sync(int grp) {   // named barrier of one 
     asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(kGroupThreads) : "memory");
 }
 
+// Edge tiles (reflection about sample 0 / L - 1; torch.stft center=True, pad_mode="reflect") and unaligned clips: every thread of the
+// group fetches its 22 staged positions with all loads in flight together.  Kept out of line so that its registers do not weigh
+// on the hot loop's allocation; slots that belong only to frames >= T get zeros.
+__device__ __noinline__ void gather_edge_tile(const float* __restrict__ src, long long g0, long long L, float* s_samples, int gt) {
+    static_assert(kTileSamples % kGroupThreads == 0, "whole rounds");
+    float v[kTileSamples / kGroupThreads];
+#pragma unroll
+    for (int k = 0; k < kTileSamples / kGroupThreads; ++k) {
+        long long idx = g0 + gt + k * kGroupThreads;
+        if (idx < 0) idx = -idx;
+        if (idx >= L) idx = 2 * (L - 1) - idx;
+        v[k] = (idx >= 0 && idx < L) ? __ldg(src + idx) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kTileSamples / kGroupThreads; ++k) s_samples[gt + k * kGroupThreads] = v[k];
+}
+
 // Stage one tile's samples; the group's mbarrier completes a phase when they have landed.  Called by all threads of the group.
 // Interior tiles are ONE bulk async copy issued by one thread (the copy engine writes shared memory and counts the bytes on the
 // mbarrier); edge tiles (reflection about sample 0 / L-1, torch.stft center=True pad_mode="reflect") and unaligned clips are
@@ -369,16 +386,7 @@ __device__ __forceinline__ void load_tile_samples(const LogmelParams& p, const C
         }
         return;
     }
-    // slots that belong only to frames >= T get zeros
-    const long long L = t.length;
-    for (int i = gt; i < kTileSamples; i += kGroupThreads) {
-        long long idx = g0 + i;
-        if (idx < 0) idx = -idx;
-        if (idx >= L) idx = 2 * (L - 1) - idx;
-        float v = 0.f;
-        if (idx >= 0 && idx < L) v = __ldg(src + idx);
-        s_samples[i] = v;
-    }
+    gather_edge_tile(src, g0, t.length, s_samples, gt);
     group_sync(grp);
     if (gt == 0) mbar_arrive(full);
 }
