@@ -201,3 +201,16 @@ def test_guard_bands_untouched(fe, L, B, dtype):
     tol = EXPECT if dtype == torch.float32 else 1e-2
     for i in range(B):
         assert np.abs(y[i].float().cpu().numpy() - wo.whisper_logmel(xs[i], fe.window.numpy(), fe.fb.numpy())).max() < tol
+
+
+def test_tonal_high_dynamic_range(fe, gw):
+    """Two pure tones (spectral dynamic range > 80 dB inside every frame -- the hard case for split-precision operands) padded to
+    30 s: within the north star's 1e-4 of the unmodified WhisperFeatureExtractor, floor region exact."""
+    t = np.arange(16000) / 16000
+    x = (0.5 * np.sin(2 * np.pi * 440 * t) + 0.25 * np.sin(2 * np.pi * 3000 * t + 1)).astype(np.float32)
+    y = fe.extract([dev(x)], check=True)[0].cpu().numpy()
+    ref = gw["full_tone_1s_sub7"]
+    d = np.abs(y[:, ::7] - ref)
+    assert d.max() < TOL, d.max()
+    assert np.all(y[:, 150:] == y[0, -1])                    # the zero-padded tail sits on the dynamic-range floor
+    assert abs((y.max() - y.min()) - 2.0) < 1e-5             # max - floor = 8 / 4
