@@ -22,7 +22,7 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-from bench import ClockSampler, measured_peak, synth_batch  # noqa: E402
+from bench import ClockSampler, measured_peak, ncu_traffic, synth_batch  # noqa: E402
 
 SAMPLE_RATE = 16000
 
@@ -125,7 +125,7 @@ def main() -> None:
                    "n_fft": 400, "hop": 160, "n_mels": 80, "route": "DFT-as-GEMM on tcgen05 (4 real GEMMs 128x112x112 per 128 frames, 3 split terms)",
                    "l2": f"inputs {B * L * 4 / 1e6:.1f} MB + outputs {B * 80 * T * 4 / 1e6:.1f} MB per step exceed the 126 MB L2; no flush"},
         "frames_per_s": B * T / (ms * 1e-3), "clocks": clocks, "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic("whisper"),
                      "kernel": "dftgemm_logmel_kernel + dftgemm_floor_kernel", "kernel_ms": ms, "algorithmic_bytes_per_launch": alg, "peak_source": src},
         "tensor": {"achieved": flops / (ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": flops / (ms * 1e-3) / 1e12 / tpeak,
                    "flops_per_step": flops, "peak_source": tsrc},
