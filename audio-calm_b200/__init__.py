@@ -18,12 +18,12 @@ directory as that package.  Layout:
 from . import _lib, tables  # noqa: F401
 from .frontend import (LogMelFrontend, MEL_MEAN_DEFAULT, MEL_STD_DEFAULT, RaggedBatch, frames_for_length,  # noqa: F401
                        pack_clips, padded_frames)
-from .stats import MelStats, MelStatsAccumulator, finalize_moments  # noqa: F401
+from .stats import MelStats, MelStatsAccumulator, finalize_moments, normalize_per_utterance  # noqa: F401
 from . import collate, frontend, stats, sharding  # noqa: F401
 from .collate import crop_collate, pad_collate, pad_collate_packed  # noqa: F401
 from . import whisper  # noqa: F401
 from .whisper import WhisperLogMel, whisper_tables  # noqa: F401
 
 __all__ = ["LogMelFrontend", "MelStatsAccumulator", "MelStats", "RaggedBatch", "pack_clips", "frames_for_length",
-           "padded_frames", "finalize_moments", "MEL_MEAN_DEFAULT", "MEL_STD_DEFAULT", "WhisperLogMel", "whisper_tables"]
+           "padded_frames", "finalize_moments", "normalize_per_utterance", "MEL_MEAN_DEFAULT", "MEL_STD_DEFAULT", "WhisperLogMel", "whisper_tables"]
 __version__ = "0.1.0"

@@ -57,9 +57,10 @@ constexpr int kNfft = 400;
 constexpr int kHop = 160;
 constexpr int kBinsAll = 201;
 constexpr int kTileFrames = 128;
-// Development-only ablation switch (tools/ablate_dftgemm.sh prices each part of the K loop in situ; results are wrong for n != 0).
-// The shipped library is always built with ACBG_ABLATE == 0.
-#ifndef ACBG_ABLATE
+// Development-only hooks, compiled in only with -DACB_DEV: the ablation switch (tools/ablate_dftgemm.sh prices each part of the K loop
+// in situ; results are wrong for n != 0) and the in-kernel timeline (tools/whisper_trace.py).  The shipped library has neither.
+#if !defined(ACB_DEV) || !defined(ACBG_ABLATE)
+#undef ACBG_ABLATE
 #define ACBG_ABLATE 0
 #endif
 #ifndef ACBG_A_HI_TMEM
@@ -487,7 +488,11 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
 
     // development timeline (acb_dftgemm_set_trace): role 0 = worker warp 0, 1 = issuer, 2 = loader; CTA 0, first 8 tiles
     auto stamp = [&](int role, uint32_t tile_iter, int event) {
+#ifdef ACB_DEV
         if (p.trace && blockIdx.x == 0 && lane == 0 && tile_iter < 48 && event < 16) p.trace[(role * 48 + tile_iter) * 16 + event] = clock64();
+#else
+        (void)role; (void)tile_iter; (void)event;
+#endif
     };
 
     if (warp == kWorkerWarps + 1) {
@@ -1091,12 +1096,14 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     return ACB_OK;
 }
 
-/* development only (not in the public header): device buffer of 3 * 48 * 16 int64 clock stamps written by CTA 0, or NULL */
+#ifdef ACB_DEV
+/* development only (not in the public header, -DACB_DEV builds): device buffer of 3 * 48 * 16 int64 clock stamps written by CTA 0, or NULL */
 int acb_dftgemm_set_trace(acb_dftgemm* fe, long long* device_buffer) {
     if (!fe) return fail(ACB_ERR_INVALID, "acb_dftgemm_set_trace: null handle");
     fe->d_trace = device_buffer;
     return ACB_OK;
 }
+#endif
 
 int acb_dftgemm_check(const acb_dftgemm* fe, void* stream) {
     if (!fe) return fail(ACB_ERR_INVALID, "acb_dftgemm_check: null handle");

@@ -38,9 +38,10 @@
 #include <string>
 #include <vector>
 
-// Development-only ablation switch (tools/ablate.py builds variants with -DACB_ABLATE=n to price each part of the
-// kernel in situ; results are wrong for n != 0).  The shipped library is always built with ACB_ABLATE == 0.
-#ifndef ACB_ABLATE
+// Development-only ablation switch, compiled in only with -DACB_DEV (tools/ablate.py builds variants with
+// -DACB_DEV -DACB_ABLATE=n to price each part of the kernel in situ; results are wrong for n != 0).
+#if !defined(ACB_DEV) || !defined(ACB_ABLATE)
+#undef ACB_ABLATE
 #define ACB_ABLATE 0
 #endif
 
@@ -52,8 +53,10 @@ constexpr int kBins = 512;                                   // bins 0..511 are 
 constexpr int kTileFrames = 8;                               // one tile = 4 frame pairs = one pair per warp of a group
 constexpr int kGroupWarps = 4;
 constexpr int kGroupThreads = kGroupWarps * 32;
-constexpr int kGroups = 2;                                   // independent groups per CTA
-constexpr int kThreads = kGroups * kGroupThreads;
+// Groups per CTA are a template parameter G: 4 groups in ONE 512-thread CTA per SM (the tables are staged once per SM and
+// the 16 warps share one instruction footprint; measured 7 % faster than 2 CTAs of 2 groups), or 2 groups x 2 CTAs per SM when
+// a large filterbank plan does not leave room for four groups' buffers.
+constexpr int kMaxGroups = 4;
 constexpr int kTileSamples = (kTileFrames + 3) * kHop;       // 2816 samples staged per tile
 constexpr int kRowStride = 36;                               // floats per row of a transpose plane: 4-byte column stores and 16-byte row loads are both conflict-free
 constexpr int kPlaneFloats = 32 * kRowStride;                // the real and the imaginary parts are transposed in separate planes
@@ -96,12 +99,15 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    do {
+// Bounded wait: a faulted bulk copy must not hang the GPU box.  Returns false after ~2^26 polls (seconds); the kernel then
+// raises its error flag, which acb_frontend_check / the host-buffer paths turn into ACB_ERR_CUDA.
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    for (int spin = 0; spin < (1 << 26) && !ok; ++spin) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
-    } while (!ok);
+    }
+    return ok != 0;
 }
 __device__ __forceinline__ void bulk_copy_g2s(void* smem, const void* gmem, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -265,7 +271,8 @@ struct LogmelParams {
     float affine_inv_std;
     const float* bin_mean;
     const float* bin_std;
-    double* moments_partial;   // [gridDim.x * kGroups][2][n_mels] or nullptr
+    double* moments_partial;   // [gridDim.x * G][2][n_mels] or nullptr
+    int* error_flag;           // set to 1 when a sample-tile barrier timed out (results invalid)
 };
 
 struct SmemLayout {
@@ -274,7 +281,7 @@ struct SmemLayout {
 
 __host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }   // odd: conflict-free both ways
 
-__host__ __device__ inline SmemLayout make_smem_layout(int n_mels, int n_plan_w, bool with_moments = false) {
+__host__ __device__ inline SmemLayout make_smem_layout(int kGroups, int n_mels, int n_plan_w, bool with_moments = false) {
     SmemLayout L;
     int off = 0;  // in 4-byte words
     L.samples = off; off += kGroups * kTileSamples;
@@ -508,10 +515,12 @@ __device__ __forceinline__ void two_sum_add(float2& acc, float x) {
     acc.x = t;
 }
 
-template <bool kMoments, typename OutT>
-__global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelParams p) {
+template <int G, bool kMoments, typename OutT>
+__global__ void __launch_bounds__(G * kGroupThreads, G == 4 ? 1 : 2) logmel_fused_kernel(const LogmelParams p) {
+    constexpr int kGroups = G;
+    constexpr int kThreads = G * kGroupThreads;
     extern __shared__ __align__(16) float smem[];
-    const SmemLayout L = make_smem_layout(p.n_mels, p.n_plan_w, kMoments);
+    const SmemLayout L = make_smem_layout(G, p.n_mels, p.n_plan_w, kMoments);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int grp = tid / kGroupThreads;          // which of the CTA's independent groups
@@ -580,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel_fused_kernel(const LogmelP
 
     for (long long tile = t_begin; tile < t_end; ++tile) {
         if (staged) {             // the tile's samples have landed (bulk copy counted in, or the gathering group arrived)
-            mbar_wait(s_full, full_parity);
+            if (!mbar_wait(s_full, full_parity) && lane == 0) atomicExch(p.error_flag, 1);
             full_parity ^= 1;
         }
 
@@ -815,6 +824,14 @@ __global__ void __launch_bounds__(256) moments_reduce_kernel(const double* __res
 // --------------------------------------------------------------------------------------------
 // per-clip peak, process_audio_chunk
 // --------------------------------------------------------------------------------------------
+// max(m, |v|) that keeps a NaN once seen, like torch.max (preprocess/core.py:108: a NaN peak fails `peak > 0`, so the clip is left
+// unscaled).  As a bit pattern a quiet NaN (0x7fc00000) is above every finite non-negative float, so atomicMax keeps it too.
+__device__ __forceinline__ float nanmax_abs(float m, float v) {
+    const float a = fabsf(v);
+    return (a != a || m != m) ? __uint_as_float(0x7fc00000u) : fmaxf(m, a);
+}
+__device__ __forceinline__ float nanmax(float a, float b) { return (a != a || b != b) ? __uint_as_float(0x7fc00000u) : fmaxf(a, b); }
+
 __global__ void peak_abs_kernel(const float* __restrict__ wav, const long long* __restrict__ clip_offset,
                                 const long long* __restrict__ clip_length, long long clip_stride, long long uniform_length,
                                 int blocks_per_clip, float* __restrict__ peak_out) {
@@ -829,54 +846,88 @@ __global__ void peak_abs_kernel(const float* __restrict__ wav, const long long* 
     float m = 0.f;
     // scalar head until 16-byte aligned, then float4 body
     const long long head_end = min(hi, lo + ((4 - ((base + lo) & 3)) & 3));
-    for (long long k = lo + threadIdx.x; k < head_end; k += blockDim.x) m = fmaxf(m, fabsf(src[k]));
+    for (long long k = lo + threadIdx.x; k < head_end; k += blockDim.x) m = nanmax_abs(m, src[k]);
     const long long body0 = head_end;
     const long long nvec = (hi > body0 && (reinterpret_cast<uintptr_t>(src + body0) & 15) == 0) ? (hi - body0) / 4 : 0;
     const float4* v4 = reinterpret_cast<const float4*>(src + body0);
     for (long long k = threadIdx.x; k < nvec; k += blockDim.x) {
         const float4 v = __ldg(v4 + k);
-        m = fmaxf(fmaxf(m, fabsf(v.x)), fmaxf(fabsf(v.y), fmaxf(fabsf(v.z), fabsf(v.w))));
+        m = nanmax_abs(nanmax_abs(nanmax_abs(nanmax_abs(m, v.x), v.y), v.z), v.w);
     }
-    for (long long k = body0 + nvec * 4 + threadIdx.x; k < hi; k += blockDim.x) m = fmaxf(m, fabsf(src[k]));
+    for (long long k = body0 + nvec * 4 + threadIdx.x; k < hi; k += blockDim.x) m = nanmax_abs(m, src[k]);
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    for (int o = 16; o >= 1; o >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, o));
     __shared__ float s_m[32];
     if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x < 32) {
         m = (threadIdx.x < (blockDim.x >> 5)) ? s_m[threadIdx.x] : 0.f;
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        for (int o = 16; o >= 1; o >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, o));
         // non-negative floats order like their bit patterns
         if (threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned int*>(peak_out + clip), __float_as_uint(m));
     }
 }
 
-// channel mean (sequential fp32 sum then divide, as torch.mean over dim 0 does) + peak
-__global__ void mixdown_peak_kernel(const float* __restrict__ wav_cl, int channels, long long length, float* __restrict__ out,
-                                    float* __restrict__ peak) {
+// channel mean (sequential fp32 sum then divide, as torch.mean over dim 0 does) + peak.  16-byte accesses when every channel row
+// is 16-byte aligned (length % 4 == 0 and aligned bases), scalar otherwise; `peak` may be null (mixdown only).
+__global__ void __launch_bounds__(256) mixdown_peak_kernel(const float* __restrict__ wav_cl, int channels, long long length,
+                                                           float* __restrict__ out, float* __restrict__ peak) {
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec = (length & 3) == 0 && ((reinterpret_cast<uintptr_t>(wav_cl) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    const float inv_c = (float)channels;
     float m = 0.f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < length; i += (long long)gridDim.x * blockDim.x) {
-        float v = wav_cl[i];
-        if (channels > 1) {
-            for (int c = 1; c < channels; ++c) v += wav_cl[(long long)c * length + i];
-            v = __fdiv_rn(v, (float)channels);
+    if (vec) {
+        const long long n4 = length >> 2;
+        for (long long i = t0; i < n4; i += stride) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(wav_cl) + i);
+            if (channels > 1) {
+                for (int c = 1; c < channels; ++c) {
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(wav_cl + (long long)c * length) + i);
+                    v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+                }
+                v.x = __fdiv_rn(v.x, inv_c); v.y = __fdiv_rn(v.y, inv_c); v.z = __fdiv_rn(v.z, inv_c); v.w = __fdiv_rn(v.w, inv_c);
+            }
+            reinterpret_cast<float4*>(out)[i] = v;
+            m = nanmax_abs(nanmax_abs(nanmax_abs(nanmax_abs(m, v.x), v.y), v.z), v.w);
         }
-        out[i] = v;
-        m = fmaxf(m, fabsf(v));
+    } else {
+        for (long long i = t0; i < length; i += stride) {
+            float v = wav_cl[i];
+            if (channels > 1) {
+                for (int c = 1; c < channels; ++c) v += wav_cl[(long long)c * length + i];
+                v = __fdiv_rn(v, inv_c);
+            }
+            out[i] = v;
+            m = nanmax_abs(m, v);
+        }
     }
+    if (peak == nullptr) return;
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(peak), __float_as_uint(m));
+    for (int o = 16; o >= 1; o >>= 1) m = nanmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ float s_m[8];
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = nanmax(m, s_m[w]);
+        atomicMax(reinterpret_cast<unsigned int*>(peak), __float_as_uint(m));   // non-negative floats order like their bit patterns
+    }
 }
 
 // wav / (peak + 1e-8) * 0.95, division first (preprocess/core.py:110)
-__global__ void peak_scale_kernel(float* __restrict__ x, long long length, const float* __restrict__ peak) {
+__global__ void __launch_bounds__(256) peak_scale_kernel(float* __restrict__ x, long long length, const float* __restrict__ peak) {
     const float pk = *peak;
     if (!(pk > 0.f)) return;
     const float d = pk + 1e-8f;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < length; i += (long long)gridDim.x * blockDim.x)
-        x[i] = __fmul_rn(__fdiv_rn(x[i], d), 0.95f);
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long n4 = (reinterpret_cast<uintptr_t>(x) & 15) == 0 ? (length >> 2) : 0;
+    for (long long i = t0; i < n4; i += stride) {
+        float4 v = reinterpret_cast<float4*>(x)[i];
+        v.x = __fmul_rn(__fdiv_rn(v.x, d), 0.95f); v.y = __fmul_rn(__fdiv_rn(v.y, d), 0.95f);
+        v.z = __fmul_rn(__fdiv_rn(v.z, d), 0.95f); v.w = __fmul_rn(__fdiv_rn(v.w, d), 0.95f);
+        reinterpret_cast<float4*>(x)[i] = v;
+    }
+    for (long long i = n4 * 4 + t0; i < length; i += stride) x[i] = __fmul_rn(__fdiv_rn(x[i], d), 0.95f);
 }
 
 // --------------------------------------------------------------------------------------------
@@ -889,8 +940,27 @@ __device__ __forceinline__ float load_feat<float>(const float* p, long long i) {
 template <>
 __device__ __forceinline__ float load_feat<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
 
-// one warp per (clip, band) row; rows are dealt round-robin to the grid's warps; per-warp fp64 accumulators in
-// shared memory, combined in a fixed order -> deterministic partial per CTA.
+// Eight (fp32) or sixteen (bf16) consecutive features of a row as floats: two 16-byte loads.
+template <typename T>
+__device__ __forceinline__ void load_feat_vec(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load_feat_vec<float>(const float* p, float (&f)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load_feat_vec<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+    const unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { f[2 * k] = __uint_as_float(w[k] << 16); f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+}
+
+// One warp per (clip, band) row; rows are dealt round-robin to the grid's warps.  A lane takes 8 consecutive values per step
+// (two 16-byte loads for fp32, one for bf16) and keeps 4 steps in flight -- up to 4 KB per lane-step of the warp, enough bytes
+// in flight to cover HBM latency at 8 warps x 8 CTAs per SM.  Every value enters fp64 accumulators (B200 has full-rate fp64
+// units: 2 fp64 operations per 4 bytes read are far below their rate), so the moments are exact to fp64 rounding.  Per-warp fp64
+// accumulators in shared memory, combined in a fixed order -> deterministic partial per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) moments_rows_kernel(const T* __restrict__ feat, int n_clips, int n_mels, long long cap,
                                                            long long clip_stride, const long long* __restrict__ frames,
@@ -905,26 +975,32 @@ __global__ void __launch_bounds__(256) moments_rows_kernel(const T* __restrict__
         const int clip = (int)(row / n_mels), b = (int)(row - (long long)clip * n_mels);
         const long long n_fr = frames ? frames[clip] : cap;
         const T* src = feat + (long long)clip * clip_stride + (long long)b * cap;
-        // four coalesced 128-byte loads in flight per lane, four independent fp64 accumulator pairs
-        double sa[4] = {0.0, 0.0, 0.0, 0.0}, sb[4] = {0.0, 0.0, 0.0, 0.0};
-        long long i = lane;
-        for (; i + 96 < n_fr; i += 128) {
-            float f[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) f[k] = load_feat<T>(src, i + 32 * k);
+        double sa[2] = {0.0, 0.0}, sb[2] = {0.0, 0.0};
+        // scalar head up to the first 32-byte (fp32) / 16-byte (bf16) boundary, vector body, scalar tail
+        const int mis = (int)((reinterpret_cast<uintptr_t>(src) & 31) / sizeof(T));
+        const long long head = min(n_fr, (long long)((mis ? (32 / (int)sizeof(T)) - mis : 0)));
+        for (long long i = lane; i < head; i += 32) { const double v = (double)load_feat<T>(src, i); sa[0] += v; sb[0] += v * v; }
+        const long long n8 = (n_fr - head) >> 3;
+        const T* body = src + head;
+        for (long long i = lane; i < n8; i += 128) {          // four predicated 8-value groups per lane and trip, all loads up front
+            float f[4][8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                const double v = (double)f[k];
-                sa[k] += v;
-                sb[k] += v * v;
+                if (i + 32 * k < n8) {
+                    load_feat_vec<T>(body + 8 * (i + 32 * k), f[k]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) f[k][j] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const double v = (double)f[k][j]; sa[j & 1] += v; sb[j & 1] = fma(v, v, sb[j & 1]); }
             }
         }
-        for (; i < n_fr; i += 32) {
-            const double v = (double)load_feat<T>(src, i);
-            sa[0] += v;
-            sb[0] += v * v;
-        }
-        double s = (sa[0] + sa[1]) + (sa[2] + sa[3]), s2 = (sb[0] + sb[1]) + (sb[2] + sb[3]);
+        for (long long t = head + (n8 << 3) + lane; t < n_fr; t += 32) { const double v = (double)load_feat<T>(src, t); sa[1] += v; sb[1] += v * v; }
+        double s = sa[0] + sa[1], s2 = sb[0] + sb[1];
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -1010,55 +1086,98 @@ template <>
 __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 // out[b][d][t] = feat[b][d][start[b] + t] while start[b] + t < frames[b], else pad: the crop / zero-pad of MelDataset.__getitem__
-// followed by the stack of data_collator.  One CTA per (clip, band) row; reads and writes are contiguous along t.
+// followed by the stack of data_collator.  One warp per (clip, band) row, rows dealt round-robin over a grid sized to the chip; a
+// lane moves 4 consecutive frames per step (16-byte store when the output row allows it; the crop start is arbitrary, so the
+// loads are scalar but coalesced).
 template <typename T>
-__global__ void __launch_bounds__(256) crop_pad_kernel(const T* __restrict__ feat, int n_mels, long long cap, long long clip_stride,
+__global__ void __launch_bounds__(256) crop_pad_kernel(const T* __restrict__ feat, int n_clips, int n_mels, long long cap, long long clip_stride,
                                                        const long long* __restrict__ frames, const long long* __restrict__ start,
                                                        T* __restrict__ out, long long out_frames, float pad_value) {
-    const int clip = blockIdx.x / n_mels, b = blockIdx.x - clip * n_mels;
-    const long long n = frames ? frames[clip] : cap;
-    const long long s0 = start ? start[clip] : 0;
-    const T* src = feat + (long long)clip * clip_stride + (long long)b * cap;
-    T* dst = out + ((long long)clip * n_mels + b) * out_frames;
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long n_rows = (long long)n_clips * n_mels;
     const T padv = from_float<T>(pad_value);
-    for (long long t = threadIdx.x; t < out_frames; t += blockDim.x) {
-        const long long f = s0 + t;
-        dst[t] = (f >= 0 && f < n) ? src[f] : padv;
+    const bool vec = sizeof(T) == 4 && (out_frames & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (long long row = (long long)blockIdx.x * warps + warp; row < n_rows; row += (long long)gridDim.x * warps) {
+        const int clip = (int)(row / n_mels), b = (int)(row - (long long)clip * n_mels);
+        const long long n = frames ? frames[clip] : cap;
+        const long long s0 = start ? start[clip] : 0;
+        const T* src = feat + (long long)clip * clip_stride + (long long)b * cap;
+        T* dst = out + row * out_frames;
+        if (vec) {
+            if constexpr (sizeof(T) == 4) {
+                for (long long t = 4 * lane; t < out_frames; t += 128) {
+                    T v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const long long f = s0 + t + j; v[j] = (f >= 0 && f < n) ? src[f] : padv; }
+                    *reinterpret_cast<float4*>(dst + t) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        } else {
+            for (long long t = lane; t < out_frames; t += 32) {
+                const long long f = s0 + t;
+                dst[t] = (f >= 0 && f < n) ? src[f] : padv;
+            }
+        }
     }
 }
 
 // Ragged time-major features [sum T_i][dim] -> channels-first padded batch out[b][d][t] (CalmCollator: pad_sequence of (T, D)
 // items, then transpose(1, 2)), with the optional time mask of _apply_spec_augment (frames [mask_start, mask_start + mask_len)
-// set to 0).  32 x 32 tiles are transposed through shared memory so that both sides stay coalesced.
+// set to 0).  64 x 64 tiles go through shared memory: 16-byte global reads along the feature dimension, 16-byte global writes
+// along time (when rows are 16-byte aligned; scalar otherwise), 16 values per thread in flight.
 template <typename T>
 __global__ void __launch_bounds__(256) pad_transpose_kernel(const T* __restrict__ feat, const long long* __restrict__ row_offset,
                                                             const long long* __restrict__ lens, int dim, T* __restrict__ out,
                                                             long long out_frames, float pad_value,
                                                             const long long* __restrict__ mask_start, const long long* __restrict__ mask_len) {
-    __shared__ float tile[32][33];
+    constexpr int kT = 64;
+    __shared__ float tile[kT][kT + 1];          // [d][t], odd pitch
     const int clip = blockIdx.z;
-    const long long t0 = (long long)blockIdx.x * 32;
-    const int d0 = blockIdx.y * 32;
+    const long long t0 = (long long)blockIdx.x * kT;
+    const int d0 = blockIdx.y * kT;
     const long long n = lens[clip];
     const T* src = feat + row_offset[clip] * dim;
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     const long long m0 = mask_start ? mask_start[clip] : 0, m1 = mask_start ? m0 + mask_len[clip] : 0;
+    const int q = threadIdx.x & 15, r0 = threadIdx.x >> 4;    // 16 quads x 16 rows per pass
+    const bool vec_in = sizeof(T) == 4 && (dim & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {                        // read: rows = time, columns = feature dim (contiguous)
+    for (int pass = 0; pass < kT / 16; ++pass) {              // read: rows = time, 4 consecutive feature values per thread
+        const int r = pass * 16 + r0;
         const long long t = t0 + r;
-        float v = pad_value;
-        if (t < n && d0 + tx < dim) {
-            v = (float)src[t * dim + d0 + tx];
-            if (t >= m0 && t < m1) v = 0.f;
+        const int d = d0 + 4 * q;
+        float v[4] = {pad_value, pad_value, pad_value, pad_value};
+        if (t < n) {
+            const bool masked = t >= m0 && t < m1;
+            if (vec_in && d + 3 < dim) {
+                if constexpr (sizeof(T) == 4) {
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(src + t * dim + d));
+                    v[0] = u.x; v[1] = u.y; v[2] = u.z; v[3] = u.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (d + j < dim) v[j] = (float)src[t * dim + d + j];
+            }
+            if (masked) { v[0] = v[1] = v[2] = v[3] = 0.f; }
         }
-        tile[r][tx] = v;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tile[4 * q + j][r] = v[j];
     }
     __syncthreads();
+    const bool vec_out = sizeof(T) == 4 && (out_frames & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
 #pragma unroll
-    for (int r = ty; r < 32; r += 8) {                        // write: rows = feature dim, columns = time (contiguous)
+    for (int pass = 0; pass < kT / 16; ++pass) {              // write: rows = feature dim, 4 consecutive frames per thread
+        const int r = pass * 16 + r0;
         const int d = d0 + r;
-        const long long t = t0 + tx;
-        if (d < dim && t < out_frames) out[((long long)clip * dim + d) * out_frames + t] = from_float<T>(tile[tx][r]);
+        const long long t = t0 + 4 * q;
+        if (d >= dim || t >= out_frames) continue;
+        T* dst = out + ((long long)clip * dim + d) * out_frames + t;
+        if (vec_out && t + 3 < out_frames) {
+            if constexpr (sizeof(T) == 4)
+                *reinterpret_cast<float4*>(dst) = make_float4(tile[r][4 * q], tile[r][4 * q + 1], tile[r][4 * q + 2], tile[r][4 * q + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (t + j < out_frames) dst[j] = from_float<T>(tile[r][4 * q + j]);
+        }
     }
 }
 
@@ -1072,6 +1191,7 @@ struct acb_frontend {
     int n_fft = 0, hop = 0, n_mels = 0, n_weights = 0, log_kind = 0;
     float clamp_min = 0.f;
     int num_sms = 0;
+    int groups = 0;        // groups per CTA (template parameter G of the kernel): 4, or 2 when four do not fit in shared memory
     int grid = 0;          // persistent grid (CTAs)
     int smem_bytes = 0;
     int smem_bytes_moments = 0;
@@ -1085,6 +1205,7 @@ struct acb_frontend {
     const short* d_plan_band = nullptr;
     const short* d_plan_astart = nullptr;
     int n_plan_w = 0;
+    int* d_err = nullptr;  // in-kernel barrier timeout flag
     // host-path streams/events (created lazily)
     cudaStream_t s_in = nullptr, s_out = nullptr;
     std::vector<cudaEvent_t> ev;
@@ -1261,7 +1382,7 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     const size_t o_win = take(sizeof(float) * kNfft), o_tw = take(sizeof(float4) * 160),
                  o_pw = take(sizeof(float) * std::max<size_t>(plan_w.size(), 1)), o_po = take(sizeof(int) * plan_woff.size()),
                  o_pt = take(sizeof(short) * plan_trip.size()), o_pb = take(sizeof(short) * plan_band.size()),
-                 o_pa = take(sizeof(short) * plan_astart.size());
+                 o_pa = take(sizeof(short) * plan_astart.size()), o_err = take(16);
     std::vector<unsigned char> host(o, 0);
     memcpy(host.data() + o_win, window_host, sizeof(float) * kNfft);
     memcpy(host.data() + o_tw, tw.data(), sizeof(float4) * 160);
@@ -1274,25 +1395,36 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     if (e == cudaSuccess) e = cudaMemcpy(fe->d_blob, host.data(), o, cudaMemcpyHostToDevice);
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device);
-    const SmemLayout L = make_smem_layout(n_mels, fe->n_plan_w, false);
-    const SmemLayout Lm = make_smem_layout(n_mels, fe->n_plan_w, true);
-    fe->smem_bytes = L.total_bytes;
-    fe->smem_bytes_moments = Lm.total_bytes;
     // The attribute is per function, not per handle: several front-ends (different n_mels) may live in one process, so it is
     // always raised to the device's opt-in maximum; the launch passes the handle's own size.
     const int optin = (int)prop.sharedMemPerBlockOptin;
+    fe->groups = make_smem_layout(kMaxGroups, n_mels, fe->n_plan_w, true).total_bytes <= optin ? kMaxGroups : 2;
+    const SmemLayout L = make_smem_layout(fe->groups, n_mels, fe->n_plan_w, false);
+    const SmemLayout Lm = make_smem_layout(fe->groups, n_mels, fe->n_plan_w, true);
+    fe->smem_bytes = L.total_bytes;
+    fe->smem_bytes_moments = Lm.total_bytes;
     if (e == cudaSuccess && Lm.total_bytes > optin) {
         if (fe->d_blob) cudaFree(fe->d_blob);
         delete fe;
         cudaSetDevice(prev);
         return fail(ACB_ERR_UNSUPPORTED, "acb_frontend_create: filterbank plan needs more shared memory than the device offers");
     }
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<false, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(logmel_fused_kernel<true, __nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
     int occ = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, logmel_fused_kernel<false, float>, kThreads, L.total_bytes);
+    auto prepare = [&](auto kernel, int threads) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+        if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, L.total_bytes);
+    };
+    if (fe->groups == 4) {
+        prepare(logmel_fused_kernel<4, false, float>, 4 * kGroupThreads);
+        prepare(logmel_fused_kernel<4, false, __nv_bfloat16>, 4 * kGroupThreads);
+        prepare(logmel_fused_kernel<4, true, float>, 4 * kGroupThreads);
+        prepare(logmel_fused_kernel<4, true, __nv_bfloat16>, 4 * kGroupThreads);
+    } else {
+        prepare(logmel_fused_kernel<2, false, float>, 2 * kGroupThreads);
+        prepare(logmel_fused_kernel<2, false, __nv_bfloat16>, 2 * kGroupThreads);
+        prepare(logmel_fused_kernel<2, true, float>, 2 * kGroupThreads);
+        prepare(logmel_fused_kernel<2, true, __nv_bfloat16>, 2 * kGroupThreads);
+    }
     if (e != cudaSuccess) {
         if (fe->d_blob) cudaFree(fe->d_blob);
         delete fe;
@@ -1309,6 +1441,7 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     fe->d_plan_trip = reinterpret_cast<const short*>(base + o_pt);
     fe->d_plan_band = reinterpret_cast<const short*>(base + o_pb);
     fe->d_plan_astart = reinterpret_cast<const short*>(base + o_pa);
+    fe->d_err = reinterpret_cast<int*>(base + o_err);
     cudaSetDevice(prev);
     *out = fe;
     return ACB_OK;
@@ -1330,7 +1463,7 @@ int acb_frontend_destroy(acb_frontend* fe) {
 
 int64_t acb_moments_workspace_bytes(const acb_frontend* fe) {
     if (!fe) return fail(ACB_ERR_INVALID, "acb_moments_workspace_bytes: null handle");
-    return (int64_t)fe->grid * kGroups * 2 * fe->n_mels * (int64_t)sizeof(double);
+    return (int64_t)fe->grid * fe->groups * 2 * fe->n_mels * (int64_t)sizeof(double);
 }
 
 int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* stream) {
@@ -1341,6 +1474,10 @@ int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* s
     if (a->out_dtype != ACB_F32 && a->out_dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_logmel_forward: bad out_dtype");
     if (a->out_layout != ACB_MEL_MAJOR && a->out_layout != ACB_TIME_MAJOR) return fail(ACB_ERR_INVALID, "acb_logmel_forward: bad out_layout");
     if (a->pad_multiple < 1) return fail(ACB_ERR_INVALID, "acb_logmel_forward: pad_multiple must be >= 1");
+    // the reflected pad columns are written by the tile that holds their source frames, which needs the padded count to end on a
+    // tile boundary or inside the last tile: multiples that divide the tile (1, 2, 4, 8; the reference uses 4)
+    if (kTileFrames % a->pad_multiple != 0)
+        return fail(ACB_ERR_UNSUPPORTED, "acb_logmel_forward: pad_multiple must divide the " + std::to_string(kTileFrames) + "-frame tile (1, 2, 4 or 8)");
     if (a->affine < 0 || a->affine > 2) return fail(ACB_ERR_INVALID, "acb_logmel_forward: bad affine mode");
     if (a->affine == 2 && (!a->bin_mean || !a->bin_std)) return fail(ACB_ERR_INVALID, "acb_logmel_forward: per-bin affine needs bin_mean/bin_std");
     if (a->affine == 1 && !(a->affine_std > 0.f)) return fail(ACB_ERR_INVALID, "acb_logmel_forward: affine_std must be > 0");
@@ -1380,6 +1517,8 @@ int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* s
             return fail(ACB_ERR_INVALID, "acb_logmel_forward: n_tiles does not match n_clips * tiles per clip");
         if (acb_padded_frames(T, a->pad_multiple) > a->frame_capacity)
             return fail(ACB_ERR_INVALID, "acb_logmel_forward: frame_capacity smaller than the padded frame count");
+        if (acb_padded_frames(T, a->pad_multiple) - T >= T)   // F.pad(mode="reflect") needs pad < T (process_dataset.py:147-150)
+            return fail(ACB_ERR_INVALID, "acb_logmel_forward: reflect pad to the multiple needs more frames than the clip has");
     }
     p.clip_peak = a->clip_peak;
     p.out = a->out; p.out_bf16 = a->out_dtype == ACB_BF16; p.time_major = a->out_layout == ACB_TIME_MAJOR;
@@ -1391,25 +1530,58 @@ int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* a, void* s
     p.affine_inv_std = a->affine == 1 ? (float)(1.0 / (double)a->affine_std) : 1.f;
     p.bin_mean = a->bin_mean; p.bin_std = a->bin_std;
     p.moments_partial = a->moments ? static_cast<double*>(a->moments_workspace) : nullptr;
+    p.error_flag = fe->d_err;
 
     int prev = 0;
     ACB_CUDA(cudaGetDevice(&prev));
     if (prev != fe->device) ACB_CUDA(cudaSetDevice(fe->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = fe->grid;  // persistent: every CTA takes a contiguous share of the tiles (possibly empty)
-    if (a->moments) {
-        if (p.out_bf16) logmel_fused_kernel<true, __nv_bfloat16><<<grid, kThreads, fe->smem_bytes_moments, st>>>(p);
-        else logmel_fused_kernel<true, float><<<grid, kThreads, fe->smem_bytes_moments, st>>>(p);
-        const int n_vals = 2 * fe->n_mels;
-        moments_reduce_kernel<<<(n_vals + 7) / 8, 256, 0, st>>>(p.moments_partial, grid * kGroups, n_vals, a->moments);
+    const int threads = fe->groups * kGroupThreads;
+    const size_t smem = a->moments ? fe->smem_bytes_moments : fe->smem_bytes;
+    auto launch = [&](auto kernel) { kernel<<<grid, threads, smem, st>>>(p); };
+    if (fe->groups == 4) {
+        if (a->moments) { if (p.out_bf16) launch(logmel_fused_kernel<4, true, __nv_bfloat16>); else launch(logmel_fused_kernel<4, true, float>); }
+        else { if (p.out_bf16) launch(logmel_fused_kernel<4, false, __nv_bfloat16>); else launch(logmel_fused_kernel<4, false, float>); }
     } else {
-        if (p.out_bf16) logmel_fused_kernel<false, __nv_bfloat16><<<grid, kThreads, fe->smem_bytes, st>>>(p);
-        else logmel_fused_kernel<false, float><<<grid, kThreads, fe->smem_bytes, st>>>(p);
+        if (a->moments) { if (p.out_bf16) launch(logmel_fused_kernel<2, true, __nv_bfloat16>); else launch(logmel_fused_kernel<2, true, float>); }
+        else { if (p.out_bf16) launch(logmel_fused_kernel<2, false, __nv_bfloat16>); else launch(logmel_fused_kernel<2, false, float>); }
+    }
+    if (a->moments) {
+        const int n_vals = 2 * fe->n_mels;
+        moments_reduce_kernel<<<(n_vals + 7) / 8, 256, 0, st>>>(p.moments_partial, grid * fe->groups, n_vals, a->moments);
     }
     cudaError_t e = cudaGetLastError();
     if (prev != fe->device) cudaSetDevice(prev);
     if (e != cudaSuccess) return cuda_fail(e, "acb_logmel_forward launch");
     return ACB_OK;
+}
+
+int acb_frontend_check(const acb_frontend* fe, void* stream) {
+    if (!fe) return fail(ACB_ERR_INVALID, "acb_frontend_check: null handle");
+    int flag = 0, prev = 0;
+    ACB_CUDA(cudaGetDevice(&prev));
+    if (prev != fe->device) ACB_CUDA(cudaSetDevice(fe->device));
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (e == cudaSuccess) e = cudaMemcpy(&flag, fe->d_err, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && flag) cudaMemset(fe->d_err, 0, sizeof(int));
+    if (prev != fe->device) cudaSetDevice(prev);
+    if (e != cudaSuccess) return cuda_fail(e, "acb_frontend_check");
+    if (flag) return fail(ACB_ERR_CUDA, "acb_frontend_check: a sample-tile copy did not complete inside the kernel (results are invalid)");
+    return ACB_OK;
+}
+
+// SM count of the current device (launch sizing of the small kernels); 148 on a B200
+static int current_sm_count() {
+    thread_local int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached_dev = dev; cached = n;
+    }
+    return cached;
 }
 
 int acb_peak_abs(const float* wav, const int64_t* clip_offset, const int64_t* clip_length, int64_t clip_stride,
@@ -1419,7 +1591,7 @@ int acb_peak_abs(const float* wav, const int64_t* clip_offset, const int64_t* cl
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ACB_CUDA(cudaMemsetAsync(peak_out, 0, sizeof(float) * n_clips, st));
     // enough CTAs to fill the chip even for a single clip
-    int blocks_per_clip = std::max(1, std::min(64, (148 * 8 + n_clips - 1) / n_clips));
+    int blocks_per_clip = std::max(1, std::min(64, (current_sm_count() * 8 + n_clips - 1) / n_clips));
     peak_abs_kernel<<<n_clips * blocks_per_clip, 256, 0, st>>>(wav, reinterpret_cast<const long long*>(clip_offset),
                                                                reinterpret_cast<const long long*>(clip_length), clip_stride,
                                                                uniform_length, blocks_per_clip, peak_out);
@@ -1432,15 +1604,29 @@ int acb_process_audio_chunk(const float* wav_cl, int32_t channels, int64_t lengt
     if (length == 0) return ACB_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ACB_CUDA(cudaMemsetAsync(scratch_peak, 0, sizeof(float), st));
-    const int blocks = (int)std::min<int64_t>(148 * 8, (length + 255) / 256);
+    const int blocks = (int)std::min<int64_t>(current_sm_count() * 8, (length + 255) / 256);
     mixdown_peak_kernel<<<blocks, 256, 0, st>>>(wav_cl, channels, length, out, scratch_peak);
     peak_scale_kernel<<<blocks, 256, 0, st>>>(out, length, scratch_peak);
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
 }
 
+// upper bound of the standalone moments grid (the workspace is sized before a device is known): 8 CTAs per SM of a 256-SM part
+constexpr int kMomentsMaxCtas = 2048;
+
+int acb_mixdown_peak(const float* wav_cl, int32_t channels, int64_t length, float* out, float* peak_out, void* stream) {
+    if (!wav_cl || !out || channels < 1 || length < 0) return fail(ACB_ERR_INVALID, "acb_mixdown_peak: bad argument");
+    if (length == 0) return ACB_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (peak_out) ACB_CUDA(cudaMemsetAsync(peak_out, 0, sizeof(float), st));
+    const int blocks = (int)std::min<int64_t>(current_sm_count() * 8, (length / 4 + 255) / 256 + 1);
+    mixdown_peak_kernel<<<blocks, 256, 0, st>>>(wav_cl, channels, length, out, peak_out);
+    ACB_CUDA(cudaGetLastError());
+    return ACB_OK;
+}
+
 int64_t acb_moments_accumulate_workspace_bytes(int32_t n_mels) {
-    return (int64_t)sizeof(double) * 148 * 8 * 2 * (int64_t)(n_mels > 0 ? n_mels : 0);
+    return (int64_t)sizeof(double) * kMomentsMaxCtas * 2 * (int64_t)(n_mels > 0 ? n_mels : 0);
 }
 
 int acb_moments_accumulate(const void* feat, int32_t dtype, int32_t n_clips, int32_t n_mels, int64_t frame_capacity,
@@ -1451,7 +1637,10 @@ int acb_moments_accumulate(const void* feat, int32_t dtype, int32_t n_clips, int
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int warps = 8;
     const long long n_rows = (long long)n_clips * n_mels;
-    const int grid = (int)std::min<long long>(148 * 8, (n_rows + warps - 1) / warps);
+    // one wave of CTAs in which every warp takes the same number of rows (a ragged last trip would leave most warps idle)
+    const long long max_ctas = std::min(kMomentsMaxCtas, current_sm_count() * 8);
+    const long long rows_per_warp = (n_rows + max_ctas * warps - 1) / (max_ctas * warps);
+    const int grid = (int)((n_rows + rows_per_warp * warps - 1) / (rows_per_warp * warps));
     double* partial = static_cast<double*>(workspace);   // caller-owned scratch (acb_moments_accumulate_workspace_bytes), or a stream-ordered one
     if (!workspace) ACB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&partial), sizeof(double) * (size_t)grid * 2 * n_mels, st));
     const size_t smem = sizeof(double) * warps * 2 * n_mels;
@@ -1505,16 +1694,16 @@ int acb_crop_pad(const void* feat, int32_t dtype, int32_t n_clips, int32_t n_mel
     if (!feat || !out || n_mels < 1 || frame_capacity < 1) return fail(ACB_ERR_INVALID, "acb_crop_pad: bad argument");
     if (dtype != ACB_F32 && dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_crop_pad: bad dtype");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned grid = (unsigned)n_clips * (unsigned)n_mels;
-    const int threads = out_frames >= 256 ? 256 : 128;
+    const long long n_rows = (long long)n_clips * n_mels;
+    const unsigned grid = (unsigned)std::min<long long>((long long)current_sm_count() * 8, (n_rows + 7) / 8);
     if (dtype == ACB_F32)
-        crop_pad_kernel<float><<<grid, threads, 0, st>>>(static_cast<const float*>(feat), n_mels, frame_capacity, clip_stride,
-                                                        reinterpret_cast<const long long*>(frames), reinterpret_cast<const long long*>(start),
-                                                        static_cast<float*>(out), out_frames, pad_value);
+        crop_pad_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(feat), n_clips, n_mels, frame_capacity, clip_stride,
+                                                    reinterpret_cast<const long long*>(frames), reinterpret_cast<const long long*>(start),
+                                                    static_cast<float*>(out), out_frames, pad_value);
     else
-        crop_pad_kernel<__nv_bfloat16><<<grid, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(feat), n_mels, frame_capacity, clip_stride,
-                                                                reinterpret_cast<const long long*>(frames), reinterpret_cast<const long long*>(start),
-                                                                static_cast<__nv_bfloat16*>(out), out_frames, pad_value);
+        crop_pad_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(feat), n_clips, n_mels, frame_capacity, clip_stride,
+                                                            reinterpret_cast<const long long*>(frames), reinterpret_cast<const long long*>(start),
+                                                            static_cast<__nv_bfloat16*>(out), out_frames, pad_value);
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
 }
@@ -1527,7 +1716,7 @@ int acb_pad_transpose(const void* feat_tm, int32_t dtype, const int64_t* row_off
     if (dtype != ACB_F32 && dtype != ACB_BF16) return fail(ACB_ERR_INVALID, "acb_pad_transpose: bad dtype");
     if (n_clips > 65535) return fail(ACB_ERR_INVALID, "acb_pad_transpose: at most 65535 clips per call");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const dim3 grid((unsigned)((out_frames + 31) / 32), (unsigned)((dim + 31) / 32), (unsigned)n_clips);
+    const dim3 grid((unsigned)((out_frames + 63) / 64), (unsigned)((dim + 63) / 64), (unsigned)n_clips);
     if (dtype == ACB_F32)
         pad_transpose_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(feat_tm), reinterpret_cast<const long long*>(row_offset),
                                                           reinterpret_cast<const long long*>(lens), dim, static_cast<float*>(out), out_frames,
@@ -1547,7 +1736,7 @@ int acb_pad_transpose(const void* feat_tm, int32_t dtype, const int64_t* row_off
 int acb_pcm16_to_float(const int16_t* pcm, float* out, int64_t n, void* stream) {
     if (n <= 0) return ACB_OK;
     if (!pcm || !out) return fail(ACB_ERR_INVALID, "acb_pcm16_to_float: null argument");
-    const int blocks = (int)std::min<int64_t>(148 * 8, (n / 8 + 255) / 256 + 1);
+    const int blocks = (int)std::min<int64_t>(current_sm_count() * 8, (n / 8 + 255) / 256 + 1);
     pcm16_to_float_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(pcm, out, n, 1.0f / 32768.0f);
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
@@ -1584,20 +1773,23 @@ static int forward_host_impl(const acb_frontend* fe_c, const void* wav_host, int
     ACB_CUDA(cudaEventRecord(fe->ev[2 * n_chunks], st));
     ACB_CUDA(cudaStreamWaitEvent(fe->s_in, fe->ev[2 * n_chunks], 0));
     const int cover_tiles = (int)(((tmpl->fill_tail ? cap : T) + kTileFrames - 1) / kTileFrames);
+    // Errors inside the loop are recorded and break out: the streams are always drained and the device restored before returning.
     int rc = ACB_OK;
-    for (int c = 0; c < n_chunks && rc == ACB_OK; ++c) {
+    cudaError_t ce = cudaSuccess;
+#define ACB_TRY(call) { ce = (call); if (ce != cudaSuccess) break; }
+    for (int c = 0; c < n_chunks; ++c) {
         const int c0 = (int)((int64_t)n_clips * c / n_chunks), c1 = (int)((int64_t)n_clips * (c + 1) / n_chunks);
         if (c1 == c0) continue;
         const size_t n_samples = (size_t)(c1 - c0) * length;
         if (dev_pcm) {
-            ACB_CUDA(cudaMemcpyAsync(dev_pcm + (int64_t)c0 * length, static_cast<const int16_t*>(wav_host) + (int64_t)c0 * length,
-                                     sizeof(int16_t) * n_samples, cudaMemcpyHostToDevice, fe->s_in));
+            ACB_TRY(cudaMemcpyAsync(dev_pcm + (int64_t)c0 * length, static_cast<const int16_t*>(wav_host) + (int64_t)c0 * length,
+                                    sizeof(int16_t) * n_samples, cudaMemcpyHostToDevice, fe->s_in));
         } else {
-            ACB_CUDA(cudaMemcpyAsync(dev_in + (int64_t)c0 * length, static_cast<const float*>(wav_host) + (int64_t)c0 * length,
-                                     sizeof(float) * n_samples, cudaMemcpyHostToDevice, fe->s_in));
+            ACB_TRY(cudaMemcpyAsync(dev_in + (int64_t)c0 * length, static_cast<const float*>(wav_host) + (int64_t)c0 * length,
+                                    sizeof(float) * n_samples, cudaMemcpyHostToDevice, fe->s_in));
         }
-        ACB_CUDA(cudaEventRecord(fe->ev[2 * c], fe->s_in));
-        ACB_CUDA(cudaStreamWaitEvent(st, fe->ev[2 * c], 0));
+        ACB_TRY(cudaEventRecord(fe->ev[2 * c], fe->s_in));
+        ACB_TRY(cudaStreamWaitEvent(st, fe->ev[2 * c], 0));
         if (dev_pcm) {
             rc = acb_pcm16_to_float(dev_pcm + (int64_t)c0 * length, dev_in + (int64_t)c0 * length, (int64_t)n_samples, st);
             if (rc != ACB_OK) break;
@@ -1612,20 +1804,27 @@ static int forward_host_impl(const acb_frontend* fe_c, const void* wav_host, int
         if (a.clip_peak) a.clip_peak = tmpl->clip_peak + c0;
         rc = acb_logmel_forward(fe, &a, st);
         if (rc != ACB_OK) break;
-        ACB_CUDA(cudaEventRecord(fe->ev[2 * c + 1], st));
-        ACB_CUDA(cudaStreamWaitEvent(fe->s_out, fe->ev[2 * c + 1], 0));
-        ACB_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(out_host) + (size_t)c0 * out_clip * esz,
-                                 static_cast<unsigned char*>(dev_out) + (size_t)c0 * out_clip * esz, (size_t)(c1 - c0) * out_clip * esz,
-                                 cudaMemcpyDeviceToHost, fe->s_out));
+        ACB_TRY(cudaEventRecord(fe->ev[2 * c + 1], st));
+        ACB_TRY(cudaStreamWaitEvent(fe->s_out, fe->ev[2 * c + 1], 0));
+        ACB_TRY(cudaMemcpyAsync(static_cast<unsigned char*>(out_host) + (size_t)c0 * out_clip * esz,
+                                static_cast<unsigned char*>(dev_out) + (size_t)c0 * out_clip * esz, (size_t)(c1 - c0) * out_clip * esz,
+                                cudaMemcpyDeviceToHost, fe->s_out));
     }
+#undef ACB_TRY
     cudaError_t e1 = cudaStreamSynchronize(fe->s_out);
     cudaError_t e2 = cudaStreamSynchronize(st);
     cudaError_t e3 = cudaStreamSynchronize(fe->s_in);
+    int flag = 0;
+    cudaError_t e4 = cudaMemcpy(&flag, fe->d_err, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e4 == cudaSuccess && flag) cudaMemset(fe->d_err, 0, sizeof(int));
     if (prev != fe->device) cudaSetDevice(prev);
     if (rc != ACB_OK) return rc;
+    if (ce != cudaSuccess) return cuda_fail(ce, "acb_logmel_forward_host");
     if (e1 != cudaSuccess) return cuda_fail(e1, "acb_logmel_forward_host sync");
     if (e2 != cudaSuccess) return cuda_fail(e2, "acb_logmel_forward_host sync");
     if (e3 != cudaSuccess) return cuda_fail(e3, "acb_logmel_forward_host sync");
+    if (e4 != cudaSuccess) return cuda_fail(e4, "acb_logmel_forward_host flag");
+    if (flag) return fail(ACB_ERR_CUDA, "acb_logmel_forward_host: a sample-tile copy did not complete inside the kernel (results are invalid)");
     return ACB_OK;
 }
 

@@ -163,6 +163,11 @@ class LogMelFrontend:
             a.moments_workspace = self._moments_workspace().data_ptr()
         return keep
 
+    def check(self) -> None:
+        """Synchronise the current stream and raise if a launch since the last check reported an in-kernel copy timeout
+        (``acb_frontend_check``).  The host-buffer path checks by itself."""
+        _lib.check(self._lib.acb_frontend_check(self._handle, _stream_ptr(self.device)), "acb_frontend_check")
+
     # ------------------------------------------------------------------ uniform batches [B, L]
     def forward(self, wav: torch.Tensor, *, out_dtype: torch.dtype = torch.float32, layout: str = "mel_major",
                 pad_multiple: int = 1, frame_capacity: Optional[int] = None, fill_tail: bool = False,

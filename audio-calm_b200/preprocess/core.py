@@ -114,7 +114,7 @@ def load_vae(ckpt_path, device):
     return vae
 
 
-def process_audio_chunk(wav, target_sr=16000):
+def process_audio_chunk(wav, target_sr=16000, device=None):
     """``wav[C, L]`` -> ``[1, L]``: channel mean when ``C > 1``, then ``wav / (max|wav| + 1e-8) * 0.95`` when the peak
     is positive (preprocess/core.py:93-112; ``target_sr`` is unused there too).
 
@@ -123,11 +123,19 @@ def process_audio_chunk(wav, target_sr=16000):
     multiply): a host tensor is copied to the current CUDA device first and the result STAYS on the device, so
     the caller's ``.to(device)`` becomes a no-op.  There is no CPU arithmetic path; without a GPU this raises.
     For batches the fused route is ``LogMelFrontend.forward(..., peak=frontend.peak_abs(wav))``.
+
+    A host tensor goes to the CURRENT CUDA device.  The reference's worker (process_dataset.py:75-97) never calls
+    ``torch.cuda.set_device`` and moves the result with ``.to(cuda:gpu_id)`` afterwards, so a worker that keeps that code should
+    call ``torch.cuda.set_device(gpu_id)`` first (or pass ``device=``); otherwise every worker would mix down on GPU 0 and pay
+    a peer copy.  An empty clip raises like the reference's ``wav.abs().max()``; a NaN sample leaves the clip unscaled, as the
+    reference's ``peak > 0`` test does.
     """
+    if wav.dim() == 2 and wav.shape[-1] == 0:
+        raise RuntimeError("max(): Expected reduction dim to be specified for input.numel() == 0. Specify the reduction dim with the 'dim' argument.")
     if not wav.is_cuda:
         if not torch.cuda.is_available():
             raise RuntimeError("process_audio_chunk (B200 build) needs a CUDA device: there is no CPU fallback")
-        wav = wav.to("cuda", non_blocking=True)
+        wav = wav.to(torch.device(device) if device is not None else "cuda", non_blocking=True)
     if wav.dim() != 2:
         raise ValueError("process_audio_chunk expects [C, L]")
     if wav.dtype != torch.float32:

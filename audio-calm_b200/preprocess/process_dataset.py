@@ -10,7 +10,8 @@ followed by one D2H copy; writer threads ``torch.save`` the per-clip payloads.  
 (``:230-238``), the mirrored output tree and ``<file_id>.pt`` names (``:113-122``), skip-if-exists unless ``--force``
 (``:125-130``), the ``{"mel": FloatTensor[80, T4]}`` / ``{"latent", "vae_path"}`` payloads (``:152-168``), transcript files
 (``:170-189, 209-214``), contiguous ``ceil(N / procs)`` sharding (``:256-259``) and the ``None`` end-of-worker message
-(``:98-100, 217``).  Unlike the reference (``:197-202``), per-file errors are counted AND reported, not swallowed.
+(``:98-100, 217``).  Unlike the reference (``:197-202``), per-file errors -- decode, kernel AND save failures -- are counted and reported,
+not swallowed; a clip's transcript line is written only after its payload has been saved, as in the reference (``:152-189``).
 
     python preprocess/process_dataset.py --dataset_name librispeech --in_dir IN --out_dir OUT --mel_only [--num_gpus N] [--force]
 """
@@ -22,22 +23,24 @@ import os
 import queue as queue_mod
 import sys
 import time
-from concurrent.futures import ThreadPoolExecutor
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from concurrent.futures import Future, ThreadPoolExecutor
+from typing import Callable, Dict, List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
 
 try:
     from ..frontend import LogMelFrontend, pack_clips
+    from .._lib import check as _lib_check
     from ..sharding import contiguous_shard
-    from .core import load_vae, process_audio_chunk
+    from .core import load_vae, process_audio_chunk  # noqa: F401
 except ImportError:  # run as a script / as top-level `preprocess.process_dataset`
     _root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     if _root not in sys.path:
         sys.path.insert(0, _root)
     from audio_calm_b200.frontend import LogMelFrontend, pack_clips
+    from audio_calm_b200._lib import check as _lib_check
     from audio_calm_b200.sharding import contiguous_shard
-    from audio_calm_b200.preprocess.core import load_vae, process_audio_chunk
+    from audio_calm_b200.preprocess.core import load_vae, process_audio_chunk  # noqa: F401
 
 AUDIO_EXTENSIONS = {".wav", ".flac", ".mp3"}   # process_dataset.py:66
 TARGET_SR = 16000
@@ -131,6 +134,15 @@ def load_audio(path: str) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------- the per-GPU engine
+class Clip(NamedTuple):
+    wav_path: str
+    save_dir: str
+    file_id: str
+    save_path: str
+    text: Optional[str]
+    wav: torch.Tensor
+
+
 class ShardRunner:
     """Processes one shard of files on one GPU in ragged batches."""
 
@@ -149,43 +161,65 @@ class ShardRunner:
         self.done = 0
 
     # -- one ragged batch: peak -> fused log-mel (+ peak norm, + pad-to-4) -> D2H -> save
-    def _flush(self, items: List[Tuple[str, str, str, torch.Tensor]], writer: ThreadPoolExecutor) -> None:
+    def _flush(self, items: List[Clip], writer: ThreadPoolExecutor) -> None:
         if not items:
             return
+        lib = self.fe._lib
         with torch.inference_mode(), torch.cuda.device(self.device):
-            # mono clips: peak normalisation is fused into the log-mel kernel (per-clip gain from acb_peak_abs);
-            # multi-channel clips go through acb_process_audio_chunk first (mixdown + scale) and get gain 1 (peak := 0)
-            clips, prenormalised = [], []
-            for i, (_, _, _, wav) in enumerate(items):
-                w = wav.to(self.device, non_blocking=True)
+            # Peak normalisation is fused into the log-mel kernel (per-clip gain from acb_peak_abs).  Multi-channel clips are
+            # mixed down first (acb_mixdown_peak: channel mean only) and then take the same fused route.
+            clips = []
+            for it in items:
+                w = it.wav.to(self.device, non_blocking=True)
                 if w.dtype == torch.int16:
                     w = self.fe.pcm16_to_float(w)          # 16-bit PCM transport, widened on the device
                 if w.shape[0] == 1:
                     clips.append(w[0])
                 else:
-                    clips.append(process_audio_chunk(w)[0])
-                    prenormalised.append(i)
+                    w = w.contiguous()
+                    mono = torch.empty(w.shape[1], dtype=torch.float32, device=self.device)
+                    _lib_check(lib.acb_mixdown_peak(w.data_ptr(), int(w.shape[0]), int(w.shape[1]), mono.data_ptr(), None,
+                                                    torch.cuda.current_stream(self.device).cuda_stream), "acb_mixdown_peak")
+                    clips.append(mono)
             batch = pack_clips(clips, self.device)
             peak = self.fe.peak_abs_ragged(batch)
-            if prenormalised:
-                peak[torch.tensor(prenormalised, device=self.device)] = 0.0
             feats, frames = self.fe.forward_ragged(batch, pad_multiple=PAD_TO, peak=peak)      # [B, 80, Tmax], frames[B] = T4
+            frames_h = frames.cpu().tolist()
             if self.vae is None:
                 host = feats.cpu()
-                frames_h = frames.cpu().tolist()
-                for i, (save_dir, _, save_path, _) in enumerate(items):
+                for i, it in enumerate(items):
                     mel = host[i, :, :frames_h[i]].clone()                                     # logical [80, T4] float32
-                    writer.submit(self._save, save_dir, save_path, {"mel": mel})
+                    self._inflight.append((writer.submit(self._save, it.save_dir, it.save_path, {"mel": mel}), it))
             else:
-                frames_h = frames.cpu().tolist()
-                for i, (save_dir, _, save_path, _) in enumerate(items):
+                for i, it in enumerate(items):
                     mu, _ = self.vae.encode(feats[i:i + 1, :, :frames_h[i]])                   # process_dataset.py:159-163
-                    writer.submit(self._save, save_dir, save_path, {"latent": mu.squeeze(0).cpu(), "vae_path": self.args.vae_ckpt})
+                    payload = {"latent": mu.squeeze(0).cpu(), "vae_path": self.args.vae_ckpt}
+                    self._inflight.append((writer.submit(self._save, it.save_dir, it.save_path, payload), it))
 
     @staticmethod
     def _save(save_dir: str, save_path: str, payload: dict) -> None:
         os.makedirs(save_dir, exist_ok=True)
         torch.save(payload, save_path)
+
+    def _collect(self, wait: bool) -> None:
+        """Harvest finished saves: a failed save (disk full, permissions ...) becomes a reported error; a clip's transcript line
+        is buffered only once its payload is on disk (process_dataset.py:152-189 writes the entry after torch.save)."""
+        keep: List[Tuple[Future, Clip]] = []
+        for fut, it in self._inflight:
+            if not wait and not fut.done():
+                keep.append((fut, it))
+                continue
+            try:
+                fut.result()
+            except Exception as e:  # noqa: BLE001
+                self.errors.append((it.wav_path, f"save failed: {type(e).__name__}: {e}"))
+            else:
+                if it.text:
+                    fname = ("commonvoice.trans.txt" if self.args.dataset_name == "commonvoice"
+                             else f"{os.path.basename(it.save_dir)}.trans.txt")
+                    self.trans_buffer.setdefault(os.path.join(it.save_dir, fname), []).append(f"{it.file_id} {it.text}")
+            self._tick()
+        self._inflight = keep
 
     def _tick(self, n: int = 1) -> None:
         self.done += n
@@ -210,8 +244,9 @@ class ShardRunner:
             except Exception as e:  # noqa: BLE001
                 return job, None, f"{type(e).__name__}: {e}"
 
-        pending: List[Tuple[str, str, str, torch.Tensor]] = []
+        pending: List[Clip] = []
         pending_samples = 0
+        self._inflight: List[Tuple[Future, Clip]] = []
         with ThreadPoolExecutor(self.decode_threads) as decoders, ThreadPoolExecutor(2) as writer:
             for job, wav, err in decoders.map(decode, todo):
                 wav_path, save_dir, file_id, save_path = job
@@ -224,13 +259,11 @@ class ShardRunner:
                 if pending and pending_samples + wav.shape[-1] > self.batch_samples:
                     self._flush_safe(pending, writer)
                     pending, pending_samples = [], 0
-                pending.append((save_dir, file_id, save_path, wav))
+                    self._collect(wait=False)
+                pending.append(Clip(wav_path, save_dir, file_id, save_path, transcript_for(wav_path, args, self.cv_mapping), wav))
                 pending_samples += int(wav.shape[-1])
-                text = transcript_for(wav_path, args, self.cv_mapping)
-                if text:
-                    fname = "commonvoice.trans.txt" if args.dataset_name == "commonvoice" else f"{os.path.basename(save_dir)}.trans.txt"
-                    self.trans_buffer.setdefault(os.path.join(save_dir, fname), []).append(f"{file_id} {text}")
             self._flush_safe(pending, writer)
+            self._collect(wait=True)
         if self.done:
             self.report(self.done)
             self.done = 0
@@ -239,13 +272,16 @@ class ShardRunner:
             with open(path, "a", encoding="utf-8") as f:
                 f.writelines(line + "\n" for line in lines)
 
-    def _flush_safe(self, items, writer) -> None:
+    def _flush_safe(self, items: List[Clip], writer) -> None:
+        n_before = len(self._inflight)
         try:
             self._flush(items, writer)
         except Exception as e:  # noqa: BLE001 - report, keep the shard going
-            for save_dir, file_id, _, _ in items:
-                self.errors.append((os.path.join(save_dir, file_id), f"{type(e).__name__}: {e}"))
-        self._tick(len(items))
+            submitted = {id(it) for _, it in self._inflight[n_before:]}
+            for it in items:
+                if id(it) not in submitted:                                                    # clips whose save was never queued
+                    self.errors.append((it.wav_path, f"{type(e).__name__}: {e}"))
+                    self._tick()
 
 
 def worker_process(rank: int, gpu_id: int, file_list: Sequence[str], args, cv_mapping, queue) -> None:

@@ -44,6 +44,34 @@ class MelStats:
     def save(self, path: str) -> None:
         torch.save(self.state(), path)
 
+    @classmethod
+    def load(cls, path: str) -> "MelStats":
+        """Read a stats file back: either one written by :meth:`save`, or the reference's bare
+        ``{"mean": [D], "std": [D]}`` layout (preprocess/compute_latent_stats.py:44-47), for which the scalar
+        pair is the mean of the per-bin means and the pooled standard deviation."""
+        payload = torch.load(path, map_location="cpu", weights_only=False)
+        if not isinstance(payload, dict) or "mean" not in payload or "std" not in payload:
+            raise ValueError(f"{path}: not a stats file (expected a dict with 'mean' and 'std')")
+        bm = np.asarray(torch.as_tensor(payload["mean"]).detach().to(torch.float64).reshape(-1).numpy())
+        bs = np.asarray(torch.as_tensor(payload["std"]).detach().to(torch.float64).reshape(-1).numpy())
+        if bm.shape != bs.shape or bm.size == 0:
+            raise ValueError(f"{path}: 'mean' and 'std' must be vectors of the same length")
+        if "mel_mean" in payload and "mel_std" in payload:
+            mean, std = float(payload["mel_mean"]), float(payload["mel_std"])
+        else:
+            mean = float(bm.mean())
+            std = math.sqrt(max(float((bs * bs + bm * bm).mean()) - mean * mean, VAR_FLOOR))
+        frames = int(payload.get("frames", 0))
+        return cls(bm, bs, mean, std, frames, int(payload.get("count", frames * bm.size)))
+
+    def affine(self, per_bin: bool = True):
+        """The ``affine=`` argument of :meth:`LogMelFrontend.forward`: per-bin ``(mean[n_mels], std[n_mels])`` fp32 tensors
+        (north-star wording: "per-bin normalisation with the stored mel stats") or the reference's scalar pair
+        (models/modeling_vae.py:317-319)."""
+        if not per_bin:
+            return (float(self.mel_mean), float(self.mel_std))
+        return (torch.from_numpy(self.bin_mean.astype(np.float32)), torch.from_numpy(self.bin_std.astype(np.float32)))
+
 
 def finalize_moments(moments: np.ndarray, frames: int, var_floor: float = VAR_FLOOR) -> MelStats:
     """Host-side finalise (compute_mel_stats.py:30-33 per bin and globally).  Pure numpy: also used on CPU by the
@@ -112,6 +140,38 @@ class MelStatsAccumulator:
 
     def finalize(self, var_floor: float = VAR_FLOOR) -> MelStats:
         return finalize_moments(self.moments.detach().cpu().numpy(), self.frames, var_floor)
+
+
+def normalize_per_utterance(mel: torch.Tensor, frames: Optional[torch.Tensor] = None, min_std: float = 1e-5,
+                            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``(mel - mean_t) / clamp(std_t, min=1e-5)`` per utterance and per mel bin, unbiased std over time -- the three
+    lines of the reference's eval path (eval/eval_vae.py:80-82) as one kernel (``acb_normalize_per_utterance``).
+
+    ``mel``: device fp32 ``[..., n_mels, T]``; ``frames[B]`` (int64) limits a padded batch to each clip's valid frames."""
+    from . import _lib
+    lib = _lib.load()
+    if not mel.is_cuda:
+        raise RuntimeError("normalize_per_utterance expects a CUDA tensor (no CPU fallback)")
+    if mel.dtype != torch.float32 or mel.dim() < 2:
+        raise ValueError("normalize_per_utterance expects float32 [..., n_mels, T]")
+    x = mel.contiguous()
+    n_mels, cap = int(x.shape[-2]), int(x.shape[-1])
+    B = x.numel() // max(n_mels * cap, 1)
+    if out is None:
+        out = torch.empty_like(x)
+    elif out.shape != x.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+        raise ValueError("out must be a contiguous float32 tensor of the input's shape on the same device")
+    fr_ptr = None
+    if frames is not None:
+        frames = frames.to(x.device, torch.int64).contiguous()
+        if frames.numel() != B:
+            raise ValueError("frames must hold one count per utterance")
+        fr_ptr = frames.data_ptr()
+    if B and cap:
+        with torch.cuda.device(x.device):
+            _lib.check(lib.acb_normalize_per_utterance(x.data_ptr(), out.data_ptr(), B, n_mels, cap, fr_ptr, float(min_std),
+                                                       torch.cuda.current_stream(x.device).cuda_stream), "acb_normalize_per_utterance")
+    return out
 
 
 def finalize_moments_c(moments: np.ndarray, frames: int, var_floor: float = VAR_FLOOR) -> MelStats:

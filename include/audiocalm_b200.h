@@ -114,6 +114,10 @@ typedef struct acb_logmel_args {
  * (+ pad-to-4, + affine normalisation, + per-bin moments): replaces MelExtractor.forward
  * (preprocess/core.py:50-61) and the torchaudio/torch.stft calls below it. */
 int acb_logmel_forward(const acb_frontend* fe, const acb_logmel_args* args, void* stream);
+/* Synchronises `stream` and reports (ACB_ERR_CUDA) whether a sample-tile copy failed to complete inside a launch since the last
+ * check: the kernel's barrier waits are bounded so that a faulted copy cannot hang the device; the host-buffer entry points
+ * below run this check themselves.  The reference's counterpart is the exception a failed torch.stft launch raises. */
+int acb_frontend_check(const acb_frontend* fe, void* stream);
 
 /* Per-clip max|x| (preprocess/core.py:108). peak_out: device [n_clips] fp32. */
 int acb_peak_abs(const float* wav, const int64_t* clip_offset, const int64_t* clip_length, int64_t clip_stride,
@@ -124,6 +128,10 @@ int acb_peak_abs(const float* wav, const int64_t* clip_offset, const int64_t* cl
  * scratch_peak: device [1] fp32 workspace. */
 int acb_process_audio_chunk(const float* wav_cl, int32_t channels, int64_t length, float* out,
                             float* scratch_peak, void* stream);
+/* First half of process_audio_chunk only (preprocess/core.py:102-108): channel mean -> out device [length] and, when peak_out
+ * (device [1]) is given, max|mean|.  The scaling is then fused into the log-mel kernel through acb_logmel_args.clip_peak, which
+ * saves the second pass over the waveform for multi-channel clips too. */
+int acb_mixdown_peak(const float* wav_cl, int32_t channels, int64_t length, float* out, float* peak_out, void* stream);
 
 /* Per-bin moments of already-extracted features (compute_mel_stats.py:19-28 over saved files):
  * feat device, MEL_MAJOR [n_clips][n_mels][frame_capacity] fp32 or bf16, frames[i] valid frames of clip i

@@ -85,6 +85,52 @@ def test_iter_files_generators(tmp_path):
     assert sorted(os.path.basename(p) for p in compute_mel_stats.iter_mel_files(str(tmp_path))) == ["a.pt", "b.pt"]
 
 
+def test_failed_saves_are_reported_and_keep_their_transcript_out(tmp_path):
+    """A torch.save / makedirs failure must surface in runner.errors, and the clip's transcript line must not be written
+    (process_dataset.py:152-189 appends the entry only after the save)."""
+    from concurrent.futures import ThreadPoolExecutor
+    runner = pd.ShardRunner.__new__(pd.ShardRunner)            # host bookkeeping only: no device objects needed
+    runner.args, runner.errors, runner.trans_buffer, runner.done = _args(out_dir=str(tmp_path)), [], {}, 0
+    runner.report = lambda n: None
+    blocked = tmp_path / "blocked"
+    blocked.write_text("a file where a directory is needed")   # makedirs(save_dir) fails under it
+    good_dir = str(tmp_path / "spk" / "chap")
+    ok = pd.Clip("in/spk/chap/u1.flac", good_dir, "u1", os.path.join(good_dir, "u1.pt"), "HELLO", torch.zeros(1, 1))
+    bad = pd.Clip("in/x/u2.flac", str(blocked / "x"), "u2", str(blocked / "x" / "u2.pt"), "LOST", torch.zeros(1, 1))
+    with ThreadPoolExecutor(1) as ex:
+        runner._inflight = [(ex.submit(pd.ShardRunner._save, c.save_dir, c.save_path, {"mel": torch.zeros(80, 4)}), c) for c in (ok, bad)]
+        runner._collect(wait=True)
+    assert os.path.exists(ok.save_path) and not runner._inflight
+    assert len(runner.errors) == 1 and runner.errors[0][0] == bad.wav_path and "save failed" in runner.errors[0][1]
+    assert runner.trans_buffer == {os.path.join(good_dir, "chap.trans.txt"): ["u1 HELLO"]}
+    assert runner.done == 2                                      # both files count as processed for the progress bar
+
+
+def test_mel_stats_file_round_trip(tmp_path):
+    """MelStats.save -> MelStats.load keeps the per-bin vectors and the scalar pair; the reference's bare {"mean","std"}
+    layout (compute_latent_stats.py:44-47) loads too."""
+    rng = np.random.default_rng(3)
+    s, frames = rng.normal(-500.0, 20.0, 80), 100
+    s2 = s * s / frames + rng.uniform(50.0, 90.0, 80)
+    st = acb.finalize_moments(np.concatenate([s, s2]), frames)
+    path = str(tmp_path / "mel_stats.pt")
+    st.save(path)
+    back = acb.MelStats.load(path)
+    assert np.allclose(back.bin_mean, st.bin_mean, rtol=0, atol=1e-6 * np.abs(st.bin_mean).max())     # stored as fp32
+    assert np.allclose(back.bin_std, st.bin_std, rtol=1e-6)
+    assert back.mel_mean == st.mel_mean and back.mel_std == st.mel_std and back.frames == frames and back.count == 80 * frames
+    mean_t, std_t = back.affine()
+    assert mean_t.dtype == torch.float32 and tuple(mean_t.shape) == (80,) and tuple(std_t.shape) == (80,)
+    assert back.affine(per_bin=False) == (st.mel_mean, st.mel_std)
+    torch.save({"mean": torch.from_numpy(st.bin_mean.astype(np.float32)), "std": torch.from_numpy(st.bin_std.astype(np.float32))},
+               str(tmp_path / "bare.pt"))
+    bare = acb.MelStats.load(str(tmp_path / "bare.pt"))
+    assert abs(bare.mel_mean - st.mel_mean) < 1e-5 and abs(bare.mel_std - st.mel_std) < 1e-4
+    with pytest.raises(ValueError):
+        torch.save({"latent": torch.zeros(3)}, str(tmp_path / "no.pt"))
+        acb.MelStats.load(str(tmp_path / "no.pt"))
+
+
 # ------------------------------------------------------------------------------------------------ GPU: end to end
 @pytest.mark.gpu
 def test_driver_mel_only_matches_reference_pipeline(tmp_path):
@@ -115,6 +161,31 @@ def test_driver_mel_only_matches_reference_pipeline(tmp_path):
     stamp = {rel: os.path.getmtime(str(out / rel.replace(".wav", ".pt"))) for rel in clips}
     pd.ShardRunner(args, 0).run(pd.scan_files(str(root)))
     assert stamp == {rel: os.path.getmtime(str(out / rel.replace(".wav", ".pt"))) for rel in clips}
+
+
+@pytest.mark.gpu
+def test_stored_stats_round_trip_normalises_like_the_oracle(tmp_path, capsys):
+    """stats CLI --save -> MelStats.load -> LogMelFrontend.forward(affine=stats): "per-bin normalisation with the stored mel
+    stats" end to end, against the oracle's (mel - mean[b]) / std[b] with the reference's statistics algorithm per bin."""
+    fe = acb.LogMelFrontend("cuda")
+    window, fb = fe.window.numpy(), fe.fb.numpy()
+    waves = [o.hash_noise(16000, 1), o.synth_clip(40000, 2), o.hash_noise(100001, 3)]
+    mels = [o.dataset_mel(w[None], window, fb).astype(np.float32) for w in waves]
+    for i, m in enumerate(mels):
+        torch.save({"mel": torch.from_numpy(m)}, str(tmp_path / f"m{i}.pt"))
+    path = str(tmp_path / "mel_stats.pt")
+    compute_mel_stats.main(["--root", str(tmp_path), "--save", path])
+    capsys.readouterr()
+    st = acb.MelStats.load(path)
+    s, s2, frames = o.stats_per_bin(mels)
+    bm, bs = o.stats_per_bin_finalise(s, s2, frames)
+    assert st.frames == frames and np.max(np.abs(st.bin_mean - bm)) < 1e-5 and np.max(np.abs(st.bin_std - bs)) < 1e-5
+    x = o.synth_clip(30000, 9)
+    y = fe.forward(torch.from_numpy(x)[None].cuda(), affine=st.affine())[0].cpu().numpy()
+    ref = (o.logmel(x, window, fb) - bm[:, None]) / bs[:, None]
+    assert float(np.max(np.abs(y - ref))) < 1e-4
+    y1 = fe.forward(torch.from_numpy(x)[None].cuda(), affine=st.affine(per_bin=False))[0].cpu().numpy()     # the reference's scalar pair
+    assert float(np.max(np.abs(y1 - o.normalise_global(o.logmel(x, window, fb), st.mel_mean, st.mel_std)))) < 1e-4
 
 
 @pytest.mark.gpu

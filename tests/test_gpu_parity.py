@@ -352,6 +352,57 @@ def test_per_utterance_normalisation(golden):
     assert float(np.max(np.abs(out[0].cpu().numpy() - golden["norm_utt_noise_16000_s1"]))) < 1e-5
 
 
+def test_normalize_per_utterance_symbol(golden):
+    """The package-level wrapper of eval/eval_vae.py:80-82 (mean / unbiased std over time per bin, std clamped at 1e-5)."""
+    m = dev(golden["pipeline_noise_16000_s1"])                                       # [80, 64]
+    y = acb.normalize_per_utterance(m)
+    assert tuple(y.shape) == (80, 64)
+    assert float(np.max(np.abs(y.cpu().numpy() - golden["norm_utt_noise_16000_s1"]))) < 1e-5
+    # padded batch: only each clip's valid frames enter the statistics
+    a, b = golden["pipeline_noise_16000_s1"], golden["pipeline_noise_40000_s2"]
+    batch = np.zeros((2, 80, b.shape[1]), np.float32)
+    batch[0, :, :a.shape[1]], batch[1] = a, b
+    frames = torch.tensor([a.shape[1], b.shape[1]])
+    yb = acb.normalize_per_utterance(dev(batch), frames=frames).cpu().numpy()
+    assert float(np.max(np.abs(yb[0, :, :a.shape[1]] - o.normalise_per_utterance(a)))) < 1e-5
+    assert float(np.max(np.abs(yb[1] - o.normalise_per_utterance(b)))) < 1e-5
+    with pytest.raises(RuntimeError):
+        acb.normalize_per_utterance(torch.zeros(80, 8))                              # no CPU fallback
+
+
+def test_process_audio_chunk_edge_cases():
+    """Empty input raises like the reference's wav.abs().max(); a NaN sample leaves the clip unscaled (peak > 0 is False)."""
+    with pytest.raises(RuntimeError):
+        process_audio_chunk(torch.zeros(1, 0))
+    x = o.hash_noise(4096, 8).copy()
+    x[100] = np.nan
+    y = process_audio_chunk(torch.from_numpy(x)[None]).cpu().numpy()[0]
+    assert np.isnan(y[100]) and np.array_equal(np.delete(y, 100), np.delete(x, 100))
+
+
+def test_mixdown_peak_matches_process_audio_chunk(fe, golden):
+    """acb_mixdown_peak + the kernel's fused clip_peak gain == process_audio_chunk + MelExtractor for a stereo clip."""
+    lib = acb._lib.load()
+    st = np.stack([o.synth_clip(20000, 24), o.hash_noise(20000, 25)])                # [2, L]
+    w = dev(st)
+    mono = torch.empty(20000, device="cuda")
+    peak = torch.empty(1, device="cuda")
+    acb._lib.check(lib.acb_mixdown_peak(w.data_ptr(), 2, 20000, mono.data_ptr(), peak.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    ref_mono = (torch.from_numpy(st).mean(dim=0)).numpy()
+    assert np.array_equal(mono.cpu().numpy(), ref_mono)                              # bit-exact channel mean
+    assert float(peak.item()) == float(np.abs(ref_mono).max())
+    y = fe.forward(mono[None], peak=peak, pad_multiple=4)[0].cpu().numpy()
+    ref = o.dataset_mel(st, fe.window.numpy(), fe.fb.numpy())
+    assert float(np.max(np.abs(y - ref))) < EXPECT
+
+
+def test_pad_multiple_must_divide_the_tile(fe):
+    x = dev(o.synth_clip(16000, 1)[None])
+    with pytest.raises(acb._lib.AcbError):
+        fe.forward(x, pad_multiple=16)
+    assert fe.forward(x, pad_multiple=8).shape[-1] % 8 == 0
+
+
 # ----------------------------------------------------------------------------------- host-buffer path
 def test_host_buffer_path_matches_device_path(fe):
     x = torch.from_numpy(np.stack([o.synth_clip(48000, 400 + i) for i in range(6)])).pin_memory()

@@ -21,7 +21,7 @@ def build():
     os.makedirs(OUT, exist_ok=True)
     for n in NAMES:
         dst = os.path.join(OUT, f"lib{n}.so")
-        cmd = [acb._lib._nvcc()] + acb._lib.NVCC_FLAGS + [f"-DACB_ABLATE={n}", "-I", acb._lib.INCLUDE, "-o", dst,
+        cmd = [acb._lib._nvcc()] + acb._lib.NVCC_FLAGS + ["-DACB_DEV", f"-DACB_ABLATE={n}", "-I", acb._lib.INCLUDE, "-o", dst,
                                                          os.path.join(acb._lib.CSRC, "acb_kernels.cu")]
         subprocess.run(cmd, check=True)
         print("built", dst)

@@ -21,13 +21,20 @@ from bench import measured_peak
 
 
 def timed(fn, steps=20, warmup=3):
+    """Device time per call: the call is captured ONCE in a CUDA graph (the C ABI launches on torch's current stream, which is
+    the capture stream inside torch.cuda.graph) and replayed, so the 20-40 us of Python / ctypes work per call stay out."""
     for _ in range(warmup):
         fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        fn()
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
     return e0.elapsed_time(e1) / steps
@@ -54,15 +61,31 @@ def main():
     import ctypes
     lib = acb._lib.load()
     o = torch.empty_like(feats)
-    s = torch.cuda.current_stream().cuda_stream
-    emit("normalize_rows_kernel", timed(lambda: lib.acb_normalize_per_utterance(feats.data_ptr(), o.data_ptr(), 256, 80, 1876, None, 1e-5, s)),
+    cs = lambda: torch.cuda.current_stream().cuda_stream      # inside a graph capture this is the capture stream
+    emit("normalize_rows_kernel", timed(lambda: lib.acb_normalize_per_utterance(feats.data_ptr(), o.data_ptr(), 256, 80, 1876, None, 1e-5, cs())),
          feats.numel() * 4 * 3, "256 x [80, 1876] fp32: mean pass + variance pass + write")
-    frames = torch.full((256,), 1876, dtype=torch.int64)
-    emit("crop_pad_kernel", timed(lambda: acb.crop_collate(feats, frames, 256, is_eval=True)), 256 * 80 * 256 * 4 * 2,
-         "256 x [80, 1876] fp32 -> [256, 80, 256] centre crops (read + write of the crop)")
-    lens = torch.full((512,), 384, dtype=torch.int64)
+    # the two collation kernels are timed through the raw C ABI with every argument already on the device (the Python wrappers
+    # compute starts / offsets on the host, which is not kernel time)
+    frames = torch.full((256,), 1876, dtype=torch.int64, device="cuda")
+    start = (frames - 256) // 2
+    crop = torch.empty((256, 80, 256), device="cuda")
+    emit("crop_pad_kernel", timed(lambda: lib.acb_crop_pad(feats.data_ptr(), 0, 256, 80, 1876, 80 * 1876, frames.data_ptr(), start.data_ptr(),
+                                                           crop.data_ptr(), 256, 0.0, cs())), 256 * 80 * 256 * 4 * 2,
+         "256 x [80, 1876] fp32 -> [256, 80, 256] centre crops (read + write of the crop; 42 MB: L2-resident, launch-bound)")
+    big = torch.randn(2048, 80, 1876, device="cuda")
+    frames_b = torch.full((2048,), 1876, dtype=torch.int64, device="cuda")
+    start_b = (frames_b - 1024) // 2
+    crop_b = torch.empty((2048, 80, 1024), device="cuda")
+    emit("crop_pad_kernel (large)", timed(lambda: lib.acb_crop_pad(big.data_ptr(), 0, 2048, 80, 1876, 80 * 1876, frames_b.data_ptr(), start_b.data_ptr(),
+                                                                   crop_b.data_ptr(), 1024, 0.0, cs())), 2048 * 80 * 1024 * 4 * 2,
+         "2048 x [80, 1876] fp32 -> [2048, 80, 1024] centre crops (1.3 GB moved)")
+    del big, crop_b
+    lens = torch.full((512,), 384, dtype=torch.int64, device="cuda")
+    offs = torch.arange(512, dtype=torch.int64, device="cuda") * 384
     lat = torch.randn(512 * 384, 128, device="cuda")
-    emit("pad_transpose_kernel", timed(lambda: acb.pad_collate_packed(lat, lens)), lat.numel() * 4 * 2,
+    pt = torch.empty((512, 128, 384), device="cuda")
+    emit("pad_transpose_kernel", timed(lambda: lib.acb_pad_transpose(lat.data_ptr(), 0, offs.data_ptr(), lens.data_ptr(), 512, 128, pt.data_ptr(), 384,
+                                                                     0.0, None, None, cs())), lat.numel() * 4 * 2,
          "512 x (384, 128) fp32 latents -> [512, 128, 384] (read + write)")
 
 

@@ -1,0 +1,95 @@
+"""Build-time variants of the fused log-mel kernel, timed side by side (development tool, not part of the product path).
+
+    python tools/variants.py build [name ...]     # here (CPU box): one nvcc per variant -> tools/_variants/lib_<name>.so
+    python tools/variants.py run [name ...]       # on the GPU box: parity vs the oracle + config-2 timing per variant
+
+Every variant is the full library with different -D switches; parity is checked before a time is believed.
+"""
+import json
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tools", "_variants")
+
+VARIANTS = {
+    "g2": ["-DACB_GROUPS=2", "-DACB_SINGLE_PLANE=0"],
+    "g2sp": ["-DACB_GROUPS=2", "-DACB_SINGLE_PLANE=1"],
+    "g4sp": ["-DACB_GROUPS=4", "-DACB_SINGLE_PLANE=1"],
+    "g5sp": ["-DACB_GROUPS=5", "-DACB_SINGLE_PLANE=1"],
+    "g6sp": ["-DACB_GROUPS=6", "-DACB_SINGLE_PLANE=1"],
+    "g4": ["-DACB_GROUPS=4", "-DACB_SINGLE_PLANE=0"],
+    "g3": ["-DACB_GROUPS=3", "-DACB_SINGLE_PLANE=0"],
+    "g2c1": ["-DACB_GROUPS=2", "-DACB_SINGLE_PLANE=0", "-DACB_CTAS_PER_SM=1"],
+    "g1c3": ["-DACB_GROUPS=1", "-DACB_SINGLE_PLANE=0", "-DACB_CTAS_PER_SM=3"],
+}
+
+
+def build_one(name):
+    import audio_calm_b200 as acb
+    dst = os.path.join(OUT, f"lib_{name}.so")
+    cmd = [acb._lib._nvcc()] + acb._lib.NVCC_FLAGS + VARIANTS[name] + ["-I", acb._lib.INCLUDE, "-o", dst] + \
+          [os.path.join(acb._lib.CSRC, s) for s in acb._lib.SOURCES]
+    subprocess.run(cmd, check=True)
+    return dst
+
+
+def build(names):
+    import audio_calm_b200  # noqa: F401  (imported once before the worker threads)
+    os.makedirs(OUT, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        for dst in ex.map(build_one, names):
+            print("built", dst, flush=True)
+
+
+def run_one(name, steps=50):
+    import numpy as np
+    import torch
+    import audio_calm_b200 as acb
+    from bench import synth_batch
+    from oracle import logmel_oracle as o
+    acb._lib.LIB_PATH = os.path.join(OUT, f"lib_{name}.so")
+    fe = acb.LogMelFrontend("cuda")
+    # parity: ragged pair of clips, peak-normalised, pad-to-4, fused moments
+    clips = [o.synth_clip(48000 + 777, 5), o.hash_noise(16000, 1)]
+    worst = 0.0
+    for c in clips:
+        xd = torch.from_numpy(c)[None].cuda()
+        acc = acb.MelStatsAccumulator(80, "cuda")
+        y = fe.forward(xd, peak=fe.peak_abs(xd), pad_multiple=4, moments=acc)
+        ref = o.dataset_mel(c[None], fe.window.numpy(), fe.fb.numpy())
+        worst = max(worst, float(np.max(np.abs(y[0].cpu().numpy() - ref))))
+        s, s2, frames = o.stats_per_bin([ref])
+        bm, _ = o.stats_per_bin_finalise(s, s2, frames)
+        worst = max(worst, float(np.max(np.abs(acc.finalize().bin_mean - bm))))
+    x = synth_batch(256, 480000, "cuda")
+    out = torch.empty((256, 80, 1876), device="cuda")
+    aff = (acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT)
+    for _ in range(5):
+        fe.forward(x, affine=aff, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fe.forward(x, affine=aff, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    ref_clip = o.normalise_global(o.logmel(x[3].cpu().numpy(), fe.window.numpy(), fe.fb.numpy()))
+    d2 = float(np.max(np.abs(out[3].cpu().numpy() - ref_clip)))
+    print(json.dumps({"variant": name, "flags": VARIANTS[name], "ms": ms, "gframes_s": 256 * 1876 / ms / 1e6,
+                      "frac": 256 * (4 * 480000 + 320 * 1876) / (ms * 1e-3) / 1e9 / 6537.6, "max_abs_err": worst, "cfg2_err": d2}), flush=True)
+
+
+if __name__ == "__main__":
+    names = sys.argv[2:] or list(VARIANTS)
+    if sys.argv[1] == "build":
+        build(names)
+    elif sys.argv[1] == "one":
+        run_one(sys.argv[2])
+    else:
+        for n in names:   # one process per variant: the library is loaded once per process
+            subprocess.run([sys.executable, os.path.abspath(__file__), "one", n], check=False)

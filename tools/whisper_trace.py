@@ -1,4 +1,4 @@
-"""Development: per-phase clock stamps of CTA 0 of the tensor-core kernel (worker warp 0, MMA issuer, loader) for the first tiles."""
+"""Development (library built with ACB_NVCC_EXTRA=-DACB_DEV): per-phase clock stamps of CTA 0 of the tensor-core kernel (worker warp 0, MMA issuer, loader) for the first tiles."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
