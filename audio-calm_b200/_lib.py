@@ -35,7 +35,7 @@ ACB_LOG_NATURAL, ACB_LOG_10 = 0, 1
 EXPORTED_SYMBOLS = [
     "acb_abi_version", "acb_last_error", "acb_frames_per_tile", "acb_frames_for_length", "acb_padded_frames",
     "acb_plan_tiles", "acb_frontend_create", "acb_frontend_destroy", "acb_moments_workspace_bytes",
-    "acb_logmel_forward", "acb_frontend_check", "acb_peak_abs", "acb_process_audio_chunk", "acb_mixdown_peak", "acb_moments_accumulate",
+    "acb_logmel_forward", "acb_frontend_check", "acb_frontend_set_kernel", "acb_peak_abs", "acb_process_audio_chunk", "acb_mixdown_peak", "acb_moments_accumulate",
     "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host", "acb_crop_pad", "acb_pad_transpose",
     "acb_moments_accumulate_workspace_bytes", "acb_pcm16_to_float", "acb_logmel_forward_host_pcm16",
     "acb_dftgemm_frames", "acb_dftgemm_workspace_ints", "acb_dftgemm_create", "acb_dftgemm_destroy", "acb_dftgemm_forward", "acb_dftgemm_check",
@@ -165,6 +165,8 @@ def load() -> ctypes.CDLL:
         lib.acb_moments_workspace_bytes.argtypes = [vp]
         lib.acb_logmel_forward.restype = ctypes.c_int
         lib.acb_logmel_forward.argtypes = [vp, ctypes.POINTER(LogmelArgs), vp]
+        lib.acb_frontend_set_kernel.restype = ctypes.c_int
+        lib.acb_frontend_set_kernel.argtypes = [vp, ctypes.c_int]
         lib.acb_frontend_check.restype = ctypes.c_int
         lib.acb_frontend_check.argtypes = [vp, vp]
         lib.acb_peak_abs.restype = ctypes.c_int

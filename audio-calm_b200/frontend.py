@@ -163,6 +163,13 @@ class LogMelFrontend:
             a.moments_workspace = self._moments_workspace().data_ptr()
         return keep
 
+    def set_kernel(self, kind: str = "auto") -> None:
+        """Choose the implementation behind ``acb_logmel_forward``: ``"auto"`` (the faster one as measured: the CUDA-core kernel),
+        ``"cuda_core"`` or ``"tensor_core"`` (warp-specialised variant with the mel projection on the tensor pipe).  Same results
+        within the parity tolerance; the switch exists for A/B measurement and so that the tests can pin either."""
+        _lib.check(self._lib.acb_frontend_set_kernel(self._handle, {"auto": 0, "cuda_core": 1, "tensor_core": 2}[kind]),
+                   "acb_frontend_set_kernel")
+
     def check(self) -> None:
         """Synchronise the current stream and raise if a launch since the last check reported an in-kernel copy timeout
         (``acb_frontend_check``).  The host-buffer path checks by itself."""

@@ -388,6 +388,10 @@ def main() -> None:
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    # rank 0 prints ONE JSON line: anything native code writes to fd 1 meanwhile ("NCCL version ..." from libnccl) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     affinity = pin_to_gpu_cpus(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
 
     import audio_calm_b200 as acb
@@ -601,7 +605,8 @@ def main() -> None:
             "sustained": sustained, "sustained_ms_per_step": None if sustained is None else sustained["ms_per_step"],
             "stats_pass": stats, "config1": config1, "config4": config4, "whisper_preset": whisper,
         }
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -7,7 +7,9 @@ keep = ['gpu__time_duration.sum','dram__bytes_read.sum','dram__bytes_write.sum',
 for i, k in enumerate(h):
     if k in keep: print(f"{k},{u[i]},{v[i]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(src))); hdr = rows[1]; data = rows[2:]
+rows = list(csv.reader(io.StringIO(src))); hdr = rows[1]
+ends = [i for i, r in enumerate(rows) if i > 1 and r and r[0] == 'Kernel Name']      # several captured launches: keep the first
+data = rows[2:ends[0]] if ends else rows[2:]
 ci = {k: i for i, k in enumerate(hdr)}
 tot = sum(int(r[ci['Instructions Executed']]) for r in data)
 print(f"# warp-inst total {tot}  per frame {tot/frames:.1f}")

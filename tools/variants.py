@@ -16,6 +16,11 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "tools", "_variants")
 
 VARIANTS = {
+    "base": [],
+    "tcab1": ["-DACB_DEV", "-DACB_TC_ABLATE=1"],
+    "tcab2": ["-DACB_DEV", "-DACB_TC_ABLATE=2"],
+    "tcab3": ["-DACB_DEV", "-DACB_TC_ABLATE=3"],
+    "tcab7": ["-DACB_DEV", "-DACB_TC_ABLATE=7"],
     "g2": ["-DACB_GROUPS=2", "-DACB_SINGLE_PLANE=0"],
     "g2sp": ["-DACB_GROUPS=2", "-DACB_SINGLE_PLANE=1"],
     "g4sp": ["-DACB_GROUPS=4", "-DACB_SINGLE_PLANE=1"],
@@ -53,6 +58,7 @@ def run_one(name, steps=50):
     from oracle import logmel_oracle as o
     acb._lib.LIB_PATH = os.path.join(OUT, f"lib_{name}.so")
     fe = acb.LogMelFrontend("cuda")
+    fe.set_kernel(os.environ.get("ACB_KIND", "auto"))
     # parity: ragged pair of clips, peak-normalised, pad-to-4, fused moments
     clips = [o.synth_clip(48000 + 777, 5), o.hash_noise(16000, 1)]
     worst = 0.0
@@ -80,7 +86,8 @@ def run_one(name, steps=50):
     ms = e0.elapsed_time(e1) / steps
     ref_clip = o.normalise_global(o.logmel(x[3].cpu().numpy(), fe.window.numpy(), fe.fb.numpy()))
     d2 = float(np.max(np.abs(out[3].cpu().numpy() - ref_clip)))
-    print(json.dumps({"variant": name, "flags": VARIANTS[name], "ms": ms, "gframes_s": 256 * 1876 / ms / 1e6,
+    fe.check()
+    print(json.dumps({"variant": name, "kind": os.environ.get("ACB_KIND", "auto"), "flags": VARIANTS[name], "ms": ms, "gframes_s": 256 * 1876 / ms / 1e6,
                       "frac": 256 * (4 * 480000 + 320 * 1876) / (ms * 1e-3) / 1e9 / 6537.6, "max_abs_err": worst, "cfg2_err": d2}), flush=True)
 
 
