@@ -13,6 +13,8 @@ directory as that package.  Layout:
     stats.py                 per-bin moments, single all-reduce, finalise like compute_mel_stats.py
     sharding.py              utterance sharding across ranks (length-balanced)
     collate.py               training-feed collation on the device (crop / zero-pad to 256 frames; ragged pad + transpose)
+    spectral.py              VAE-side STFT magnitudes over the mel time axis (AcousticVAE._stft_mag / stft_loss forward)
+    csrc/acb_spectral.cu     its kernel (shares the in-register FFT-32 of csrc/acb_fft32.cuh)
     preprocess/              drop-in mirrors of the reference's preprocess/{core,compute_mel_stats,process_dataset}.py
 """
 from . import _lib, tables  # noqa: F401
@@ -21,7 +23,7 @@ from .frontend import (LogMelFrontend, MEL_MEAN_DEFAULT, MEL_STD_DEFAULT, Ragged
 from .stats import MelStats, MelStatsAccumulator, finalize_moments, normalize_per_utterance  # noqa: F401
 from . import collate, frontend, stats, sharding  # noqa: F401
 from .collate import crop_collate, pad_collate, pad_collate_packed  # noqa: F401
-from . import whisper  # noqa: F401
+from . import spectral, whisper  # noqa: F401
 from .whisper import WhisperLogMel, whisper_tables  # noqa: F401
 
 __all__ = ["LogMelFrontend", "MelStatsAccumulator", "MelStats", "RaggedBatch", "pack_clips", "frames_for_length",

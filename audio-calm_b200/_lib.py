@@ -18,7 +18,8 @@ CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 LIB_NAME = "libaudiocalm_b200.so"
 LIB_PATH = os.path.join(CSRC, LIB_NAME)
-SOURCES = ["acb_kernels.cu", "acb_dftgemm.cu"]
+SOURCES = ["acb_kernels.cu", "acb_dftgemm.cu", "acb_spectral.cu"]
+HEADERS = ["acb_fft32.cuh"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -38,6 +39,7 @@ EXPORTED_SYMBOLS = [
     "acb_logmel_forward", "acb_frontend_check", "acb_frontend_set_kernel", "acb_peak_abs", "acb_process_audio_chunk", "acb_mixdown_peak", "acb_moments_accumulate",
     "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host", "acb_crop_pad", "acb_pad_transpose",
     "acb_moments_accumulate_workspace_bytes", "acb_pcm16_to_float", "acb_logmel_forward_host_pcm16",
+    "acb_stft_mag_frames", "acb_stft_mag",
     "acb_dftgemm_frames", "acb_dftgemm_workspace_ints", "acb_dftgemm_create", "acb_dftgemm_destroy", "acb_dftgemm_forward", "acb_dftgemm_check",
 ]
 
@@ -109,7 +111,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(INCLUDE, "audiocalm_b200.h")]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.join(INCLUDE, "audiocalm_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -193,6 +195,10 @@ def load() -> ctypes.CDLL:
         lib.acb_pcm16_to_float.argtypes = [vp, vp, i64, vp]
         lib.acb_logmel_forward_host_pcm16.restype = ctypes.c_int
         lib.acb_logmel_forward_host_pcm16.argtypes = [vp, vp, i32, i64, vp, ctypes.POINTER(LogmelArgs), vp, vp, vp, i32, vp]
+        lib.acb_stft_mag_frames.restype = i64
+        lib.acb_stft_mag_frames.argtypes = [i64, ctypes.c_int, ctypes.c_int]
+        lib.acb_stft_mag.restype = ctypes.c_int
+        lib.acb_stft_mag.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.c_int, vp, vp, vp]
         lib.acb_dftgemm_frames.restype = i64
         lib.acb_dftgemm_frames.argtypes = [i64, ctypes.c_int]
         lib.acb_dftgemm_workspace_ints.restype = i64

@@ -25,6 +25,7 @@
 // The next tile's samples are prefetched while step 3/4 run; the first FFT-32 of the next tile runs before the barrier that
 // frees the scratch, so a warp never waits for its group with nothing to do.
 #include "audiocalm_b200.h"
+#include "acb_fft32.cuh"
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -43,6 +44,13 @@
 #if !defined(ACB_DEV) || !defined(ACB_ABLATE)
 #undef ACB_ABLATE
 #define ACB_ABLATE 0
+#endif
+
+#ifndef ACB_WIN_FUSE
+#define ACB_WIN_FUSE 1
+#endif
+#ifndef ACB_WIN_T
+#define ACB_WIN_T 1
 #endif
 
 namespace acb {
@@ -71,7 +79,7 @@ static_assert(kOutStageOffset + kTileFrames * (kMaxMels | 1) <= kScratchFloats, 
 
 thread_local std::string g_last_error;
 
-static int fail(int code, const std::string& msg) {
+int fail(int code, const std::string& msg) {   // also used by acb_spectral.cu: one thread-local message for the whole library
     g_last_error = msg;
     return code;
 }
@@ -113,116 +121,6 @@ __device__ __forceinline__ void bulk_copy_g2s(void* smem, const void* gmem, unsi
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(smem)), "l"(gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
 }
-
-__host__ __device__ constexpr int brev5(int x) {
-    return ((x & 1) << 4) | ((x & 2) << 2) | (x & 4) | ((x & 8) >> 2) | ((x & 16) >> 4);
-}
-
-// cos/sin of 2*pi*j/32, j = 0..15
-__device__ constexpr float kCos32[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
-                                         0.70710678118654757f, 0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f,
-                                         0.f, -0.19509032201612819f, -0.38268343236508973f, -0.55557023301960196f,
-                                         -0.70710678118654746f, -0.83146961230254535f, -0.92387953251128674f, -0.98078528040323043f};
-__device__ constexpr float kSin32[16] = {0.f, 0.19509032201612825f, 0.38268343236508978f, 0.55557023301960218f,
-                                         0.70710678118654746f, 0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f,
-                                         1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254546f,
-                                         0.70710678118654757f, 0.55557023301960218f, 0.38268343236508989f, 0.19509032201612861f};
-
-// One radix-2 DIT butterfly with twiddle W = exp(-2*pi*i*TW/32): (u, v) -> (u + W v, u - W v).
-// Generic twiddles use the 6-FMA form (sum by 4 FMAs, difference as 2u - sum).
-template <int TW>
-__device__ __forceinline__ void bfly(float& ur, float& ui, float& vr, float& vi) {
-    if (TW == 0) {
-        const float sr = ur + vr, si = ui + vi;
-        vr = ur - vr; vi = ui - vi;
-        ur = sr; ui = si;
-    } else if (TW == 8) {  // W = -i : W v = (vi, -vr)
-        const float sr = ur + vi, si = ui - vr;
-        const float dr = ur - vi, di = ui + vr;
-        ur = sr; ui = si; vr = dr; vi = di;
-    } else {
-        constexpr float wr = kCos32[TW];
-        constexpr float wi = -kSin32[TW];
-        const float sr = fmaf(wr, vr, fmaf(-wi, vi, ur));
-        const float si = fmaf(wr, vi, fmaf(wi, vr, ui));
-        vr = fmaf(2.f, ur, -sr);
-        vi = fmaf(2.f, ui, -si);
-        ur = sr; ui = si;
-    }
-}
-
-// ---- packed fp32 (FFMA2 / FADD2 / FMUL2, new on sm_100): two butterflies per instruction ----
-// The 32 complex values of an FFT-32 are held as 16 pairs (x[i], x[i + 16]) in 64-bit registers, real and imaginary parts
-// in separate arrays.  Stages 1-4 of the radix-2 DIT network combine indices i and i + half with both below 16 or both above,
-// and the twin butterfly 16 places up uses the same twiddle: one packed butterfly does both.  Stage 5 pairs i with i + 16,
-// i.e. the two halves of one register pair, and runs as scalar code on the halves.
-__device__ __forceinline__ float2 bcast2(float a) { return make_float2(a, a); }
-__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }   // folds into the consumer's operand modifier
-
-template <int TW>
-__device__ __forceinline__ void bfly2(float2& ur, float2& ui, float2& vr, float2& vi) {
-    if (TW == 0) {            // W = 1
-        const float2 sr = __fadd2_rn(ur, vr), si = __fadd2_rn(ui, vi);
-        vr = __fadd2_rn(ur, neg2(vr));
-        vi = __fadd2_rn(ui, neg2(vi));
-        ur = sr; ui = si;
-    } else if (TW == 8) {     // W = -i : W v = (vi, -vr)
-        const float2 sr = __fadd2_rn(ur, vi), si = __fadd2_rn(ui, neg2(vr));
-        const float2 dr = __fadd2_rn(ur, neg2(vi)), di = __fadd2_rn(ui, vr);
-        ur = sr; ui = si; vr = dr; vi = di;
-    } else {                  // generic: s = u + W v by 4 packed FMAs, d = 2u - s by 2 more (6 for two butterflies)
-        constexpr float wr = kCos32[TW];
-        constexpr float wi = -kSin32[TW];
-        const float2 sr = __ffma2_rn(vi, bcast2(-wi), __ffma2_rn(vr, bcast2(wr), ur));
-        const float2 si = __ffma2_rn(vr, bcast2(wi), __ffma2_rn(vi, bcast2(wr), ui));
-        vr = __ffma2_rn(ur, bcast2(2.f), neg2(sr));
-        vi = __ffma2_rn(ui, bcast2(2.f), neg2(si));
-        ur = sr; ui = si;
-    }
-}
-
-template <int S, int K, int J>
-struct Bfly2Loop {
-    // packed stage S <= 4 (m = 2^S), group base K < 16, index J within the half-group
-    static __device__ __forceinline__ void run(float2 (&pr)[16], float2 (&pi)[16]) {
-        constexpr int m = 1 << S, half = m >> 1;
-        bfly2<J * (32 / m)>(pr[K + J], pi[K + J], pr[K + J + half], pi[K + J + half]);
-        if constexpr (J + 1 < half) {
-            Bfly2Loop<S, K, J + 1>::run(pr, pi);
-        } else if constexpr (K + m < 16) {
-            Bfly2Loop<S, K + m, 0>::run(pr, pi);
-        }
-    }
-};
-
-template <int J>
-struct LastStageLoop {
-    // stage 5: butterfly (J, J + 16) = the two halves of pair J, twiddle W32^J, scalar code
-    static __device__ __forceinline__ void run(float2 (&pr)[16], float2 (&pi)[16]) {
-        bfly<J>(pr[J].x, pi[J].x, pr[J].y, pi[J].y);
-        if constexpr (J + 1 < 16) LastStageLoop<J + 1>::run(pr, pi);
-    }
-};
-
-// In-register complex FFT-32, decimation in time: input in bit-reversed order, output natural order
-// (element k < 16 is pr[k].x, element k >= 16 is pr[k - 16].y).
-__device__ __forceinline__ void fft32_packed(float2 (&pr)[16], float2 (&pi)[16]) {
-    Bfly2Loop<1, 0, 0>::run(pr, pi);
-    Bfly2Loop<2, 0, 0>::run(pr, pi);
-    Bfly2Loop<3, 0, 0>::run(pr, pi);
-    Bfly2Loop<4, 0, 0>::run(pr, pi);
-    LastStageLoop<0>::run(pr, pi);
-}
-
-// Same, when stage 1 (span-1 butterflies, twiddle 1) has already been applied by the caller.
-__device__ __forceinline__ void fft32_packed_from_stage2(float2 (&pr)[16], float2 (&pi)[16]) {
-    Bfly2Loop<2, 0, 0>::run(pr, pi);
-    Bfly2Loop<3, 0, 0>::run(pr, pi);
-    Bfly2Loop<4, 0, 0>::run(pr, pi);
-    LastStageLoop<0>::run(pr, pi);
-}
-
-__host__ __device__ constexpr int brev3(int x) { return ((x & 1) << 2) | (x & 2) | ((x & 4) >> 2); }
 
 // --------------------------------------------------------------------------------------------
 // fused log-mel kernel
@@ -290,7 +188,7 @@ __host__ __device__ inline SmemLayout make_smem_layout(int kGroups, int n_mels, 
     L.samples = off; off += kGroups * kTileSamples;
     L.scratch = off; off += kGroups * kGroupWarps * kScratchFloats;
     L.twiddle = off; off += 5 * 32 * 4;
-    L.window = off; off += kNfft / 2;                             // first half only: w[n + N/2] = 1 - w[n]
+    L.window = off; off += 32 * 20;                               // first half only (w[n + N/2] = 1 - w[n]), per lane with a 20-float pitch
     L.plan_w = off; off += (n_plan_w + 3) & ~3;
     L.affine = off; off += 2 * ((n_mels + 1) & ~1);
     off = (off + 3) & ~3;
@@ -546,7 +444,10 @@ __global__ void __launch_bounds__(G * kGroupThreads, G == 4 ? 1 : 2) logmel_fuse
 
     // ---- one-time table staging (whole CTA) ----
     for (int i = tid; i < 5 * 32; i += kThreads) s_tw4[i] = p.twiddle[i];
-    for (int i = tid; i < kNfft / 2; i += kThreads) s_win[i] = p.window[i];
+    for (int i = tid; i < kNfft / 2; i += kThreads) {
+        if (ACB_WIN_T) s_win[(i & 31) * 20 + (i >> 5)] = p.window[i];      // [lane][row], 20-float pitch: conflict-free 16-byte loads
+        else s_win[i] = p.window[i];
+    }
     for (int i = tid; i < p.n_plan_w; i += kThreads) s_pw[i] = p.plan_w[i];
     for (int i = tid; i < kGroupWarps * kMaxRounds * kSlots; i += kThreads) {
         const int slot = i / kSlots, qq = i - slot * kSlots;
@@ -613,10 +514,25 @@ __global__ void __launch_bounds__(G * kGroupThreads, G == 4 ? 1 : 2) logmel_fuse
                 float2 v[20];
 #pragma unroll
                 for (int r = 0; r < 20; ++r) v[r] = make_float2(sp[32 * (2 * r)], sp[32 * (2 * r + 1)]);
+                float4 w4[4];
+                if (ACB_WIN_T) {   // the lane's 16 window values, stored per lane: four 16-byte loads instead of sixteen 4-byte ones
+                    const float4* wq = reinterpret_cast<const float4*>(s_win + lane * 20);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) w4[u] = wq[u];
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int t = brev5(2 * j) >> 1;      // sample rows n1 = 2t, 2t + 1 (n1 < 16)
-                    const float2 wa = make_float2(s_win[32 * (2 * t) + lane], s_win[32 * (2 * t + 1) + lane]);
+                    const float2 wa = ACB_WIN_T ? ((t & 1) ? make_float2(w4[t >> 1].z, w4[t >> 1].w) : make_float2(w4[t >> 1].x, w4[t >> 1].y))
+                                                : make_float2(s_win[32 * (2 * t) + lane], s_win[32 * (2 * t + 1) + lane]);
+#if ACB_WIN_FUSE
+                    // periodic Hann: w[n + N/2] = 1 - w[n], so b (1 - w) = b - b w is one FMA, and a w +- that another
+                    const float2 br = __ffma2_rn(neg2(v[t + 8]), wa, v[t + 8]), bi = __ffma2_rn(neg2(v[t + 12]), wa, v[t + 12]);
+                    pr[2 * j] = __ffma2_rn(v[t], wa, br);
+                    pr[2 * j + 1] = __ffma2_rn(v[t], wa, neg2(br));
+                    pi[2 * j] = __ffma2_rn(v[t + 4], wa, bi);
+                    pi[2 * j + 1] = __ffma2_rn(v[t + 4], wa, neg2(bi));
+#else
                     const float2 wb = __fadd2_rn(bcast2(1.f), neg2(wa));   // periodic Hann: w[n + N/2] = 1 - w[n]
                     const float2 ar = __fmul2_rn(v[t], wa), br = __fmul2_rn(v[t + 8], wb);
                     const float2 ai = __fmul2_rn(v[t + 4], wa), bi = __fmul2_rn(v[t + 12], wb);
@@ -624,6 +540,7 @@ __global__ void __launch_bounds__(G * kGroupThreads, G == 4 ? 1 : 2) logmel_fuse
                     pr[2 * j + 1] = __fadd2_rn(ar, neg2(br));
                     pi[2 * j] = __fadd2_rn(ai, bi);
                     pi[2 * j + 1] = __fadd2_rn(ai, neg2(bi));
+#endif
                 }
             }
             fft32_packed_from_stage2(pr, pi);  // over n1 -> k1 (natural order)

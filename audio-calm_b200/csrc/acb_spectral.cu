@@ -1,0 +1,234 @@
+// VAE-side spectral kernel of the Audio-CALM front-end family: short-time Fourier magnitudes over the TIME axis of log-mel
+// features, as AcousticVAE._stft_mag computes them for the multi-resolution STFT loss (reference models/modeling_vae.py:271-305:
+// torch.stft(n_fft in {256, 128, 64}, hop n_fft / 4, periodic Hann, center=False, onesided) followed by torch.abs).
+//
+// One launch per resolution replaces reshape + torch.stft (framing copy, window multiply, cuFFT R2C) + abs.  A CTA stages a few
+// rows [T] in shared memory once, packs every two frames (of any of its rows) into one complex FFT of n_fft = 32 R points -- R
+// lanes per transform, each running the packed-FFMA2 in-register FFT-32 of the log-mel kernel (acb_fft32.cuh) over its stride-R
+// samples, a twiddle, and an R-point FFT across the R lanes through a small shared-memory exchange -- separates the two real
+// spectra, takes the magnitudes and writes the rows' [n_freq][frames] blocks with coalesced stores.  HBM traffic is one read of the
+// features and one write of the magnitudes.
+#include "audiocalm_b200.h"
+#include "acb_fft32.cuh"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+
+namespace acb {
+int fail(int code, const std::string& msg);   // acb_kernels.cu: sets the thread-local message behind acb_last_error()
+}
+
+namespace acb_spectral {
+
+using namespace acb;
+
+constexpr int kThreads = 128;
+
+__host__ __device__ constexpr int brev_bits(int x, int bits) {
+    int r = 0;
+    for (int i = 0; i < bits; ++i) r |= ((x >> i) & 1) << (bits - 1 - i);
+    return r;
+}
+__host__ __device__ constexpr int ilog2(int x) { return x <= 1 ? 0 : 1 + ilog2(x >> 1); }
+
+// In-register complex FFT of R points (R a power of two <= 32), natural order in and out: the cross-lane factor of the transform.
+template <int R>
+__device__ __forceinline__ void small_fft(float2 (&v)[R]) {
+    constexpr int kLog = ilog2(R);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+        const int j = brev_bits(i, kLog);
+        if (i < j) { const float2 t = v[i]; v[i] = v[j]; v[j] = t; }
+    }
+#pragma unroll
+    for (int half = 1; half < R; half <<= 1) {
+#pragma unroll
+        for (int base = 0; base < R; base += 2 * half) {
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+                const int tw = j * (16 / half);                       // W_(2 half)^j = W_32^tw, tw < 16
+                const float wr = kCos32[tw], wi = -kSin32[tw];
+                const float2 u = v[base + j], w = v[base + j + half];
+                const float tr = fmaf(wr, w.x, -wi * w.y), ti = fmaf(wr, w.y, wi * w.x);
+                v[base + j] = make_float2(u.x + tr, u.y + ti);
+                v[base + j + half] = make_float2(u.x - tr, u.y - ti);
+            }
+        }
+    }
+}
+
+struct SpectralSmem {
+    int x, win, tw, buf, out, total_bytes;
+};
+
+__host__ __device__ inline SpectralSmem spectral_smem(int R, int rows_per_cta, int T, int n_frames) {
+    const int N = 32 * R, n_freq = N / 2 + 1;
+    SpectralSmem L;
+    int off = 0;   // 4-byte words
+    L.x = off; off += (rows_per_cta * T + 3) & ~3;
+    L.win = off; off += N;
+    L.tw = off; off += 2 * N;
+    L.buf = off; off += (kThreads / R) * (2 * 33 * R);           // per lane group: N complex values, index k1 + 33 * k2
+    L.out = off; off += rows_per_cta * n_freq * n_frames;
+    L.total_bytes = off * 4;
+    return L;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restrict__ x, long long rows, int T, int hop, int n_frames,
+                                                            const float* __restrict__ window, float* __restrict__ out, int rows_per_cta) {
+    constexpr int N = 32 * R, kFreq = N / 2 + 1, kGroups = kThreads / R, kPerLane = 32 / R;
+    extern __shared__ __align__(16) float smem[];
+    const SpectralSmem L = spectral_smem(R, rows_per_cta, T, n_frames);
+    float* s_x = smem + L.x;
+    float* s_win = smem + L.win;
+    float2* s_tw = reinterpret_cast<float2*>(smem + L.tw);
+    float* s_out = smem + L.out;
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * rows_per_cta;
+    const int n_rows = (int)min((long long)rows_per_cta, rows - row0);
+
+    // stage the rows, the window and the twiddles W_N^m = exp(-2 pi i m / N)
+    {
+        const float* src = x + row0 * T;
+        const int n = n_rows * T;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            for (int i = tid; i < n / 4; i += kThreads) reinterpret_cast<float4*>(s_x)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+            for (int i = (n & ~3) + tid; i < n; i += kThreads) s_x[i] = src[i];
+        } else {
+            for (int i = tid; i < n; i += kThreads) s_x[i] = src[i];
+        }
+        for (int i = tid; i < N; i += kThreads) {
+            s_win[i] = window[i];
+            float sn, cs;
+            sincospif(2.f * (float)i / (float)N, &sn, &cs);
+            s_tw[i] = make_float2(cs, -sn);
+        }
+    }
+    __syncthreads();
+
+    const int g = tid / R, r = tid % R;                 // lane group (one transform) and position inside it
+    float2* buf = reinterpret_cast<float2*>(smem + L.buf) + g * (33 * R);
+    const int total_frames = n_rows * n_frames;
+    const int n_items = (total_frames + 1) / 2;         // two frames per complex transform
+    const int n_iter = (n_items + kGroups - 1) / kGroups;
+    for (int it = 0; it < n_iter; ++it) {
+        const int item = it * kGroups + g;
+        const bool valid = item < n_items;
+        const int qa = 2 * item, qb = qa + 1;
+        const bool valid_b = valid && qb < total_frames;
+        const int row_a = valid ? qa / n_frames : 0, fa = valid ? qa - row_a * n_frames : 0;
+        const int row_b = valid_b ? qb / n_frames : 0, fb = valid_b ? qb - row_b * n_frames : 0;
+        if (valid) {
+            const float* pa = s_x + row_a * T + fa * hop;
+            const float* pb = s_x + row_b * T + fb * hop;
+            float2 pr[16], pi[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {              // fft32_packed takes bit-reversed input: position q holds elements j0, j0 + 1
+                const int j0 = brev5(q);
+                const int n0 = R * j0 + r, n1 = R * (j0 + 1) + r;
+                const float w0 = s_win[n0], w1 = s_win[n1];
+                pr[q] = make_float2(pa[n0] * w0, pa[n1] * w1);
+                pi[q] = valid_b ? make_float2(pb[n0] * w0, pb[n1] * w1) : make_float2(0.f, 0.f);
+            }
+            fft32_packed(pr, pi);                       // over the lane's stride-R samples -> k1 (natural order)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {              // twiddle W_N^(r k1) and hand over: index k1 + 33 * r
+                const float2 t0 = s_tw[r * k], t1 = s_tw[r * (k + 16)];
+                buf[k + 33 * r] = make_float2(fmaf(pr[k].x, t0.x, -pi[k].x * t0.y), fmaf(pr[k].x, t0.y, pi[k].x * t0.x));
+                buf[k + 16 + 33 * r] = make_float2(fmaf(pr[k].y, t1.x, -pi[k].y * t1.y), fmaf(pr[k].y, t1.y, pi[k].y * t1.x));
+            }
+        }
+        __syncwarp();
+        if (valid) {                                    // R-point FFT across the group's lanes, in place: Z[k1 + 32 k2] at index k1 + 33 k2
+#pragma unroll
+            for (int t = 0; t < kPerLane; ++t) {
+                const int k1 = r * kPerLane + t;
+                float2 v[R];
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) v[rr] = buf[k1 + 33 * rr];
+                small_fft<R>(v);
+#pragma unroll
+                for (int rr = 0; rr < R; ++rr) buf[k1 + 33 * rr] = v[rr];
+            }
+        }
+        __syncwarp();
+        if (valid) {                                    // separate the two real spectra, magnitudes
+            float* oa = s_out + (size_t)row_a * kFreq * n_frames + fa;
+            float* ob = s_out + (size_t)row_b * kFreq * n_frames + fb;
+            for (int k = r; k < kFreq; k += R) {
+                const int kc = (N - k) & (N - 1);
+                const float2 z = buf[(k & 31) + 33 * (k >> 5)], zc = buf[(kc & 31) + 33 * (kc >> 5)];
+                const float apc = z.x + zc.x, bmd = z.y - zc.y, amc = z.x - zc.x, bpd = z.y + zc.y;
+                oa[(size_t)k * n_frames] = 0.5f * sqrtf(fmaf(apc, apc, bmd * bmd));
+                if (valid_b) ob[(size_t)k * n_frames] = 0.5f * sqrtf(fmaf(amc, amc, bpd * bpd));
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // the CTA's rows are one contiguous span of the output
+        float* dst = out + row0 * kFreq * n_frames;
+        const int n = n_rows * kFreq * n_frames;
+        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0 && (L.out & 3) == 0) {
+            for (int i = tid; i < n / 4; i += kThreads) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(s_out)[i];
+            for (int i = (n & ~3) + tid; i < n; i += kThreads) dst[i] = s_out[i];
+        } else {
+            for (int i = tid; i < n; i += kThreads) dst[i] = s_out[i];
+        }
+    }
+}
+
+template <int R>
+static int launch(const float* x, int64_t rows, int T, int hop, int n_frames, const float* window, float* out, cudaStream_t st) {
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return fail(ACB_ERR_CUDA, "acb_stft_mag: cannot query the device");
+    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, 16384 / T));
+    while (rpc > 1 && spectral_smem(R, rpc, T, n_frames).total_bytes > std::min(optin, 160 * 1024)) rpc >>= 1;
+    const SpectralSmem L = spectral_smem(R, rpc, T, n_frames);
+    if (L.total_bytes > optin)
+        return fail(ACB_ERR_UNSUPPORTED, "acb_stft_mag: a row of " + std::to_string(T) + " frames does not fit in shared memory");
+    cudaError_t e = cudaFuncSetAttribute(stft_mag_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) return fail(ACB_ERR_CUDA, std::string("acb_stft_mag: ") + cudaGetErrorString(e));
+    const unsigned grid = (unsigned)((rows + rpc - 1) / rpc);
+    stft_mag_kernel<R><<<grid, kThreads, L.total_bytes, st>>>(x, rows, T, hop, n_frames, window, out, rpc);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ACB_ERR_CUDA, std::string("acb_stft_mag launch: ") + cudaGetErrorString(e));
+    return ACB_OK;
+}
+
+}  // namespace acb_spectral
+
+extern "C" {
+
+int64_t acb_stft_mag_frames(int64_t length, int n_fft, int hop) {
+    if (n_fft <= 0 || hop <= 0 || length < n_fft) return -1;
+    return 1 + (length - n_fft) / hop;
+}
+
+int acb_stft_mag(const float* x, int64_t rows, int64_t length, int n_fft, int hop, const float* window, float* out, void* stream) {
+    using namespace acb_spectral;
+    if (rows <= 0) return ACB_OK;
+    if (!x || !window || !out) return fail(ACB_ERR_INVALID, "acb_stft_mag: null argument");
+    if (hop < 1) return fail(ACB_ERR_INVALID, "acb_stft_mag: hop must be >= 1");
+    if (length < n_fft)
+        return fail(ACB_ERR_INVALID, "acb_stft_mag: rows of " + std::to_string(length) + " values are shorter than n_fft = " + std::to_string(n_fft) +
+                                         " (center=False: torch.stft raises)");
+    if (length > (1 << 24) || rows > ((int64_t)1 << 40)) return fail(ACB_ERR_UNSUPPORTED, "acb_stft_mag: input too large");
+    const int n_frames = (int)acb_stft_mag_frames(length, n_fft, hop);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (n_fft) {
+        case 64: return launch<2>(x, rows, (int)length, hop, n_frames, window, out, st);
+        case 128: return launch<4>(x, rows, (int)length, hop, n_frames, window, out, st);
+        case 256: return launch<8>(x, rows, (int)length, hop, n_frames, window, out, st);
+        case 512: return launch<16>(x, rows, (int)length, hop, n_frames, window, out, st);
+        case 1024: return launch<32>(x, rows, (int)length, hop, n_frames, window, out, st);
+        default:
+            return fail(ACB_ERR_UNSUPPORTED, "acb_stft_mag: n_fft must be 64, 128, 256, 512 or 1024 (got " + std::to_string(n_fft) + ")");
+    }
+}
+
+}  // extern "C"

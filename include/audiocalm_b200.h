@@ -238,6 +238,18 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* args, voi
 /* Synchronises `stream` and reports whether any in-kernel pipeline barrier timed out since the last check. */
 int acb_dftgemm_check(const acb_dftgemm* fe, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * VAE-side spectral op: short-time Fourier magnitudes over the time axis of features.
+ * Replaces AcousticVAE._stft_mag (models/modeling_vae.py:271-289: torch.stft(n_fft, hop, window = periodic Hann(n_fft),
+ * center=False, onesided, normalized=False) + torch.abs), which stft_loss (:291-305) calls with (n_fft, hop) = (256, 64),
+ * (128, 32), (64, 16) on [B, 80, T] features.
+ *   x      device [rows][length] fp32 (rows = B * C, contiguous)
+ *   window device [n_fft] fp32 (torch.hann_window(n_fft), passed by the host so that it is bit-identical)
+ *   out    device [rows][n_fft / 2 + 1][frames] fp32, frames = acb_stft_mag_frames(length, n_fft, hop) = 1 + (length - n_fft) / hop
+ * n_fft in {64, 128, 256, 512, 1024}; length < n_fft returns ACB_ERR_INVALID (torch.stft raises for center=False). */
+int64_t acb_stft_mag_frames(int64_t length, int n_fft, int hop);
+int acb_stft_mag(const float* x, int64_t rows, int64_t length, int n_fft, int hop, const float* window, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

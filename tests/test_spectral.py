@@ -1,0 +1,95 @@
+"""VAE-side spectral op: AcousticVAE._stft_mag / stft_loss of the reference (models/modeling_vae.py:271-305).
+
+CPU: the numpy oracle against goldens minted from the unmodified reference function (oracle/gen_golden_spectral.py).
+GPU: acb_stft_mag (through audio_calm_b200.spectral) against the same goldens and the oracle.  Tolerance: 1e-4 absolute on
+magnitudes up to ~1 and 1e-4 relative above (fp32 transforms of 64-1024 points; the goldens themselves are fp32)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import audio_calm_b200 as acb
+from audio_calm_b200 import spectral
+from oracle import spectral_oracle as so
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "stft_mag_cases.npz")
+SPECS = ((256, 64), (128, 32), (64, 16))
+
+
+def close(a, b, tol=1e-4):
+    return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b)))) < tol
+
+
+@pytest.fixture(scope="module")
+def g():
+    return np.load(GOLDEN)
+
+
+def test_oracle_matches_the_reference_goldens(g):
+    for n_fft, hop in SPECS:
+        ref = g[f"mag_x_{n_fft}"]
+        got = so.stft_mag(g["x"], n_fft, hop)
+        assert got.shape == ref.shape and close(got, ref, 2e-5), n_fft
+    assert close(so.stft_mag(g["short"], 64, 16), g["mag_short_64"], 2e-5)
+    assert abs(so.stft_loss(g["x"], g["y"]) - float(g["loss_xy"])) < 1e-5
+    assert abs(so.stft_loss(g["short"], g["short"] * 0.5) - float(g["loss_short"])) < 1e-4 * max(1.0, float(g["loss_short"]))
+    with pytest.raises(RuntimeError):
+        so.stft_mag(g["short"], 128, 32)                        # 96 frames < n_fft: torch.stft raises for center=False
+    assert np.array_equal(so.hann_periodic(64, np.float32), torch.hann_window(64).numpy()) or \
+        float(np.max(np.abs(so.hann_periodic(64) - torch.hann_window(64, dtype=torch.float64).numpy()))) < 1e-15
+
+
+def test_frame_counts():
+    assert spectral.stft_frames(256, 256, 64) == 1 and spectral.stft_frames(256, 128, 32) == 5 and spectral.stft_frames(256, 64, 16) == 13
+    assert spectral.stft_frames(96, 64, 16) == 3
+    with pytest.raises(RuntimeError):
+        spectral.stft_frames(96, 128, 32)
+
+
+@pytest.mark.gpu
+def test_kernel_matches_the_reference_goldens(g):
+    x = torch.from_numpy(g["x"]).cuda()
+    for n_fft, hop in SPECS:
+        got = spectral.stft_mag(x, n_fft=n_fft, hop_length=hop)
+        ref = g[f"mag_x_{n_fft}"]
+        assert got.dtype == torch.float32 and tuple(got.shape) == ref.shape          # frame / bin counts exact
+        assert close(got.cpu().numpy(), ref), n_fft
+    short = torch.from_numpy(g["short"]).cuda()
+    assert close(spectral.stft_mag(short, 64, 16).cpu().numpy(), g["mag_short_64"])
+    with pytest.raises(RuntimeError):
+        spectral.stft_mag(short, 128, 32)
+    mags = spectral.multires_stft_mags(short)
+    assert len(mags) == 1 and tuple(mags[0].shape) == (1, 4, 33, 3)                  # only n_fft = 64 fits 96 frames
+    y = torch.from_numpy(g["y"]).cuda()
+    assert abs(float(spectral.stft_loss(x, y)) - float(g["loss_xy"])) < 1e-5
+    assert abs(float(spectral.stft_loss(short, short * 0.5)) - float(g["loss_short"])) < 1e-4 * max(1.0, float(g["loss_short"]))
+    with pytest.raises(RuntimeError):
+        spectral.stft_mag(torch.zeros(1, 2, 256), 64, 16)                            # no CPU fallback
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_fft,hop,T,B,C", [(64, 16, 256, 3, 80), (128, 32, 256, 3, 80), (256, 64, 256, 3, 80), (256, 64, 1000, 2, 5),
+                                             (512, 128, 777, 1, 3), (1024, 256, 2048, 2, 2), (64, 7, 100, 1, 1), (128, 32, 128, 33, 1)])
+def test_kernel_matches_the_oracle(n_fft, hop, T, B, C):
+    rng = np.random.default_rng(n_fft + T)
+    x = (rng.normal(-6.0, 3.0, (B, C, T))).astype(np.float32)                        # log-mel-like values
+    got = spectral.stft_mag(torch.from_numpy(x).cuda(), n_fft=n_fft, hop_length=hop).cpu().numpy()
+    ref = so.stft_mag(x, n_fft, hop, window=torch.hann_window(n_fft).numpy())
+    # the reference only uses n_fft <= 256; at 512 / 1024 points the fp32 rounding of a transform whose DC term is ~3000 (mean -6
+    # times the window sum) reaches 1.5e-4 of unit-sized bins, for torch.stft in fp32 just as much as for this kernel
+    tol = 1e-4 if n_fft <= 256 else 4e-4
+    assert got.shape == ref.shape and close(got, ref, tol), float(np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))))
+
+
+@pytest.mark.gpu
+def test_training_batch_size():
+    """[256, 80, 256] (the VAE training batch, config/vae_config.yaml): all three resolutions against torch.stft on the device."""
+    x = torch.randn(256, 80, 256, device="cuda") * 3.0 - 6.0
+    for n_fft, hop in SPECS:
+        got = spectral.stft_mag(x, n_fft, hop)
+        X = torch.stft(x.reshape(-1, 256), n_fft=n_fft, hop_length=hop, win_length=n_fft, window=torch.hann_window(n_fft, device="cuda"),
+                       return_complex=True, normalized=False, center=False)
+        ref = X.abs().view(256, 80, n_fft // 2 + 1, -1)
+        assert got.shape == ref.shape
+        assert float(((got - ref).abs() / ref.abs().clamp(min=1.0)).max()) < 1e-4

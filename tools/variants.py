@@ -17,6 +17,9 @@ OUT = os.path.join(ROOT, "tools", "_variants")
 
 VARIANTS = {
     "base": [],
+    "win00": ["-DACB_WIN_FUSE=0", "-DACB_WIN_T=0"],
+    "win10": ["-DACB_WIN_FUSE=1", "-DACB_WIN_T=0"],
+    "win01": ["-DACB_WIN_FUSE=0", "-DACB_WIN_T=1"],
     "tcab1": ["-DACB_DEV", "-DACB_TC_ABLATE=1"],
     "tcab2": ["-DACB_DEV", "-DACB_TC_ABLATE=2"],
     "tcab3": ["-DACB_DEV", "-DACB_TC_ABLATE=3"],
