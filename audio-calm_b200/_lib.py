@@ -40,7 +40,7 @@ EXPORTED_SYMBOLS = [
     "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host", "acb_crop_pad", "acb_pad_transpose",
     "acb_moments_accumulate_workspace_bytes", "acb_pcm16_to_float", "acb_logmel_forward_host_pcm16",
     "acb_stft_mag_frames", "acb_stft_mag",
-    "acb_dftgemm_frames", "acb_dftgemm_workspace_ints", "acb_dftgemm_create", "acb_dftgemm_destroy", "acb_dftgemm_forward", "acb_dftgemm_check",
+    "acb_dftgemm_frames", "acb_dftgemm_workspace_ints", "acb_dftgemm_create", "acb_dftgemm_destroy", "acb_dftgemm_forward", "acb_dftgemm_check", "acb_dftgemm_moments_workspace_bytes",
 ]
 
 
@@ -97,6 +97,14 @@ class DftGemmArgs(ctypes.Structure):
         ("affine_std", ctypes.c_float),
         ("clip_max", ctypes.c_void_p),
         ("out_dtype", ctypes.c_int32),
+        ("clip_length", ctypes.c_void_p),
+        ("clip_peak", ctypes.c_void_p),
+        ("peak_norm", ctypes.c_int32),
+        ("fill_value", ctypes.c_float),
+        ("bin_mean", ctypes.c_void_p),
+        ("bin_std", ctypes.c_void_p),
+        ("moments", ctypes.c_void_p),
+        ("moments_workspace", ctypes.c_void_p),
     ]
 
 
@@ -210,10 +218,12 @@ def load() -> ctypes.CDLL:
         lib.acb_dftgemm_destroy.argtypes = [vp]
         lib.acb_dftgemm_forward.restype = ctypes.c_int
         lib.acb_dftgemm_forward.argtypes = [vp, ctypes.POINTER(DftGemmArgs), vp]
+        lib.acb_dftgemm_moments_workspace_bytes.restype = i64
+        lib.acb_dftgemm_moments_workspace_bytes.argtypes = [vp]
         lib.acb_dftgemm_check.restype = ctypes.c_int
         lib.acb_dftgemm_check.argtypes = [vp, vp]
-        if lib.acb_abi_version() != 1:
-            raise RuntimeError(f"{LIB_PATH}: ABI version {lib.acb_abi_version()} != 1; rebuild")
+        if lib.acb_abi_version() != 2:
+            raise RuntimeError(f"{LIB_PATH}: ABI version {lib.acb_abi_version()} != 2; rebuild")
         _lib = lib
         return lib
 

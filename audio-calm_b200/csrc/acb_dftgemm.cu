@@ -107,8 +107,10 @@ constexpr int kOffMelW = kOffBand + kMaxMels * 16;
 constexpr int kOffBar = kOffMelW + kMaxWeights * 4;
 constexpr int kOffPow = kOffA;                                // |X|^2 [224 bins][128 rows] fp32 reuses the A/B stages during the epilogue
 static_assert(kPowBins * kTileFrames * 4 <= 2 * kAStageBytes + 2 * kBStageBytes, "power tile must fit the operand stages");
-constexpr int kSmemBytes = kOffBar + 96;
-static_assert(kOffWin % 16 == 0 && kOffBand % 16 == 0 && kOffBar % 8 == 0, "alignment");
+constexpr int kOffAff = kOffBar + 96;                         // float2 per band: (scale, shift) of the affine
+constexpr int kOffMom = kOffAff + kMaxMels * 8;               // float2 [2][kMaxMels]: compensated per-band sums of the fused moments
+constexpr int kSmemBytes = kOffMom + 2 * kMaxMels * 8;
+static_assert(kOffWin % 16 == 0 && kOffBand % 16 == 0 && kOffBar % 8 == 0 && kOffAff % 8 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 static int fail(int code, const std::string& msg) {
@@ -214,6 +216,15 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// (hi, lo) += x with the rounding error of hi + x carried in lo (Knuth two-sum)
+__device__ __forceinline__ void two_sum_add(float2& acc, float x) {
+    const float t = __fadd_rn(acc.x, x);
+    const float bb = __fsub_rn(t, acc.x);
+    const float e = __fadd_rn(__fsub_rn(acc.x, __fsub_rn(t, bb)), __fsub_rn(x, bb));
+    acc.y = __fadd_rn(acc.y, e);
+    acc.x = t;
+}
+
 __device__ __forceinline__ float lg2_normal(float x) {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -261,6 +272,14 @@ struct Params {
     int* clip_max;             // [n_clips] ordered-int keys of the per-clip maximum, or nullptr (no dynamic-range floor)
     int* tile_min;             // [n_clips * tiles_per_clip] ordered-int keys of MINUS the per-tile minimum (tiles above the floor are skipped later)
     float aff_scale, aff_shift;   // out = v * aff_scale + aff_shift (1, 0 when no affine)
+    const float* bin_mean;     // per-band affine (v - bin_mean[b]) / bin_std[b] instead of the uniform pair, or nullptr
+    const float* bin_std;
+    const long long* clip_length;   // [n_clips] samples of every clip (<= length; rows are padded to `length`), or nullptr: uniform
+    const float* clip_peak;    // [n_clips] max|x|: power-of-two pre-scale of the samples (any amplitude fits the fp16 operands) and,
+    int peak_norm;             //   with peak_norm, the fused process_audio_chunk gain 0.95 / (peak + 1e-8); or nullptr
+    int drop_last_frame;
+    float fill_value;          // stored for frames beyond a clip's own count (ragged batches)
+    double* moments_partial;   // [gridDim.x][2][n_mels] per-CTA sums of v and v^2 over the frames that exist, or nullptr
     int* error_flag;           // set to 1 when a barrier wait timed out
     int use_tma;               // the batch is 128-byte row addressable (16-byte aligned base, clip_stride % 32 == 0): tensor copies
     long long* trace;          // development: clock64 stamps of CTA 0 ([role][tile < 48][event < 16]), or nullptr
@@ -319,7 +338,7 @@ __device__ __forceinline__ int staged_index(int lin) { return lin ^ (((lin >> 5)
 // One K step of A-operand construction for one thread: 8 consecutive n (n0 .. n0 + 7) of its frame row, for the 4 GEMMs.
 // `srow` = the staged samples, `base` = 160 * row + 120 (linear staged position of the frame's sample 0).
 __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, int base, int n0, const float* __restrict__ s_wf,
-                                               const float* __restrict__ s_wr, uint8_t* dst, uint32_t t_hi) {
+                                               const float* __restrict__ s_wr, uint8_t* dst, uint32_t t_hi, float pre) {
     float xa[8], xc[8], xb[8], xe[8];
     {
         const float* pa = srow + staged_index(base + n0);              // x[n0 .. n0+7]
@@ -347,8 +366,12 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
     {
         const float4 wf0 = *reinterpret_cast<const float4*>(s_wf + n0), wf1 = *reinterpret_cast<const float4*>(s_wf + n0 + 4);
         const float4 wr0 = *reinterpret_cast<const float4*>(s_wr + n0), wr1 = *reinterpret_cast<const float4*>(s_wr + n0 + 4);
-        const float wa[8] = {wf0.x, wf0.y, wf0.z, wf0.w, wf1.x, wf1.y, wf1.z, wf1.w};
-        const float wb[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
+        float wa[8] = {wf0.x, wf0.y, wf0.z, wf0.w, wf1.x, wf1.y, wf1.z, wf1.w};
+        float wb[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
+        if (pre != 1.f) {      // warp-uniform: the clip's power-of-two pre-scale (exact), folded into the window
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { wa[i] *= pre; wb[i] *= pre; }
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float pa = wa[i] * xa[i], pe = wa[i] * xe[i];      // w[400-n] = w[n]
@@ -393,7 +416,7 @@ __device__ __forceinline__ void split_store_tmem4(const float (&v)[4], uint32_t 
     *reinterpret_cast<uint2*>(dst_lo) = make_uint2(lo[0], lo[1]);
 }
 __device__ __forceinline__ void build_a_slices4(const float* __restrict__ srow, int base, int n0, const float* __restrict__ s_wf,
-                                                const float* __restrict__ s_wr, uint8_t* dst, uint32_t t_hi) {
+                                                const float* __restrict__ s_wr, uint8_t* dst, uint32_t t_hi, float pre) {
     const float4 a = *reinterpret_cast<const float4*>(srow + staged_index(base + n0));              // x[n0 .. n0+3]
     const float4 c = *reinterpret_cast<const float4*>(srow + staged_index(base + 200 + n0));        // x[200+n0 .. 200+n0+3]
     const float4 b = *reinterpret_cast<const float4*>(srow + staged_index(base + 196 - n0));        // x[196-n0 .. 199-n0]
@@ -403,7 +426,7 @@ __device__ __forceinline__ void build_a_slices4(const float* __restrict__ srow, 
     const float4 wf = *reinterpret_cast<const float4*>(s_wf + n0), wr = *reinterpret_cast<const float4*>(s_wr + n0);
     const float xa[4] = {a.x, a.y, a.z, a.w}, xc[4] = {c.x, c.y, c.z, c.w};
     const float xb[4] = {b4, b.w, b.z, b.y}, xe[4] = {e4, e.w, e.z, e.y};
-    const float wa[4] = {wf.x, wf.y, wf.z, wf.w}, wb[4] = {wr.x, wr.y, wr.z, wr.w};
+    const float wa[4] = {wf.x * pre, wf.y * pre, wf.z * pre, wf.w * pre}, wb[4] = {wr.x * pre, wr.y * pre, wr.z * pre, wr.w * pre};
     float se[4], so[4], de[4], dd[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -462,6 +485,15 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
     for (int i = tid; i < kKpad; i += kThreads) { s_wf[i] = p.win_fwd[i]; s_wr[i] = p.win_rev[i]; }
     for (int i = tid; i < p.n_mels; i += kThreads) s_band[i] = p.bands[i];
     for (int i = tid; i < p.n_mel_w; i += kThreads) s_melw[i] = p.mel_w[i];
+    float2* s_aff = reinterpret_cast<float2*>(smem + kOffAff);
+    float2* s_mom = reinterpret_cast<float2*>(smem + kOffMom);
+    for (int i = tid; i < p.n_mels; i += kThreads) {
+        float sc = p.aff_scale, sh = p.aff_shift;
+        if (p.bin_mean) { sc = 1.f / __ldg(p.bin_std + i); sh = -__ldg(p.bin_mean + i) * sc; }
+        s_aff[i] = make_float2(sc, sh);
+        s_mom[i] = make_float2(0.f, 0.f);
+        s_mom[kMaxMels + i] = make_float2(0.f, 0.f);
+    }
     if (tid == 0) {
         mbar_init(bar_smp, 1);
         mbar_init(bar_bfull0, 1);
@@ -586,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
             const float* src;
             long long g0;
             if (tile_source(p, tile, src, g0)) return true;
-            const long long L = p.length;
+            const long long L = p.clip_length ? __ldg(p.clip_length + tile / p.tiles_per_clip) : p.length;
 #pragma unroll 8
             for (int i = wtid; i < kBlocks * kHop; i += kWorkerThreads) {
                 long long idx = g0 + i;
@@ -605,13 +637,28 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
 
         for (; tile < n_tiles; tile += gridDim.x, ++tile_iter) {
             const int clip = tile / p.tiles_per_clip, tic = tile - clip * p.tiles_per_clip;
+            // geometry and scaling of this tile's clip: own length (ragged batches are rows padded to p.length), frames that exist,
+            // power-of-two pre-scale of the samples and the factor that undoes it (and applies the peak-normalisation gain) on the mel powers
+            const long long clip_len = p.clip_length ? __ldg(p.clip_length + clip) : p.length;
+            const int clip_frames = min(p.frames_out, (int)(clip_len / kHop) + (p.drop_last_frame ? 0 : 1));
+            float pre = 1.f, post = 1.f;
+            if (p.clip_peak) {
+                const float peak = __ldg(p.clip_peak + clip);
+                if (peak > 0.f && peak < 3.0e38f) {
+                    int e;
+                    frexpf(peak, &e);                                   // peak = m 2^e, 0.5 <= m < 1: |x 2^-e| < 1
+                    pre = exp2f((float)-e);
+                    const float g = p.peak_norm ? (0.95f / (peak + 1e-8f)) * exp2f((float)e) : exp2f((float)e);
+                    post = g * g;
+                }
+            }
             if (smp_async) {
                 ok = mbar_wait(bar_smp, smp_uses & 1) && ok;
                 ++smp_uses;
                 // positions outside the clip (reflection about sample 0 / L - 1: torch.stft center=True, pad_mode="reflect") are
                 // patched over what the tensor copy brought in; only the first and the last tiles of a clip have any
                 const float* src = p.wav + (long long)clip * p.clip_stride;
-                const long long g0 = (long long)(tic * kTileFrames - 2) * kHop, L = p.length;
+                const long long g0 = (long long)(tic * kTileFrames - 2) * kHop, L = clip_len;
                 const long long e0 = L - g0;                        // first staged position beyond the clip
                 if (g0 < 0 || e0 < kBlocks * kHop) {                // CTA-uniform
                     if (g0 < 0)
@@ -642,11 +689,11 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                     if (kPrepWarps == 8)
                         build_a_slices(s_samples, base, 16 * ks + 8 * hsel, s_wf, s_wr,
                                        s_a + st * kAStageBytes + hsel * (kTileFrames * 16) + row * 16,
-                                       tmem + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(kAhiCols + st * 32 + hsel * 4));
+                                       tmem + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(kAhiCols + st * 32 + hsel * 4), pre);
                     else
                         build_a_slices4(s_samples, base, 16 * ks + 4 * qsel, s_wf, s_wr,
                                         s_a + st * kAStageBytes + (qsel >> 1) * (kTileFrames * 16) + row * 16 + (qsel & 1) * 8,
-                                        tmem + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(kAhiCols + st * 32 + qsel * 2));
+                                        tmem + ((uint32_t)((warp & 3) << 5) << 16) + (uint32_t)(kAhiCols + st * 32 + qsel * 2), pre);
                     if (ACBG_ABLATE != 1) fence_async_smem();      // generic-proxy writes of A -> visible to the tensor core's async proxy
                     tc_fence_before();       // (and the tensor-memory stores of A_hi, completed by tcgen05.wait::st, ordered before the arrive)
                     __syncwarp();
@@ -701,14 +748,14 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 // mel pass: lane = 4 consecutive frames (one 16-byte load per bin), warp = one group of bands (weights are
                 // warp-uniform broadcast loads); a warp stores 32 x 4 consecutive frames of one band = 512 contiguous bytes
                 const int frame0 = tic * kTileFrames + 4 * lane;
-                const int n_valid = p.frames_out - frame0;            // frames of this lane that exist (<= 0: none)
+                const int n_valid = clip_frames - frame0;             // frames of this lane that exist (<= 0: none)
+                const int n_store = p.frames_out - frame0;            // frames of this lane inside the row (the rest of them get fill_value)
                 const int b_begin = p.band_group[warp], b_end = p.band_group[warp + 1];
                 long long out_col = (long long)clip * p.out_clip_stride + (long long)b_begin * cap + frame0;    // element index in out
                 const int esize = p.out_bf16 ? 2 : 4;
                 // four consecutive frames of a band go out as one 16-byte (fp32) / 8-byte (bf16) store when every row keeps them aligned
                 const bool vec_store = n_valid >= 4 && ((reinterpret_cast<uintptr_t>(p.out) | (uintptr_t)(p.out_clip_stride * esize) | (uintptr_t)(cap * esize)) & (4 * esize - 1)) == 0;
-                float vmax = -3.0e38f, vmin = 3.0e38f;
-                const float aff_scale = p.aff_scale, aff_shift = p.aff_shift;
+                float vmax = -3.0e38f, vmin = 3.0e38f, chk = 0.f;
                 const float4* pow4 = reinterpret_cast<const float4*>(s_pow) + lane;
                 for (int b = b_begin; b < b_end; ++b, out_col += cap) {
                     const int4 bd = s_band[b];
@@ -724,16 +771,34 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                         a.z = fmaf(w, q.z, a.z);
                         a.w = fmaf(w, q.w, a.w);
                     }
+                    a.x *= post; a.y *= post; a.z *= post; a.w *= post;      // undo the pre-scale (exact power of two) / apply the peak gain
                     float4 v;
                     v.x = (a.x > clamp_min) ? lg2_normal(a.x) * log_scale : log_floor;
                     v.y = (a.y > clamp_min) ? lg2_normal(a.y) * log_scale : log_floor;
                     v.z = (a.z > clamp_min) ? lg2_normal(a.z) * log_scale : log_floor;
                     v.w = (a.w > clamp_min) ? lg2_normal(a.w) * log_scale : log_floor;
-                    // the affine is applied here; the dynamic-range floor commutes with it: max(v, M - r) * s + t = max(v s + t, (M s + t) - r s)
-                    v.x = fmaf(v.x, aff_scale, aff_shift);
-                    v.y = fmaf(v.y, aff_scale, aff_shift);
-                    v.z = fmaf(v.z, aff_scale, aff_shift);
-                    v.w = fmaf(v.w, aff_scale, aff_shift);
+                    const float raw[4] = {v.x, v.y, v.z, v.w};          // un-normalised log-mel: maximum / minimum tracking, moments
+                    if (p.moments_partial) {                            // CTA-uniform: per-band sums over the frames that exist
+                        float sm = 0.f, sq = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if (j < n_valid) { sm += raw[j]; sq = fmaf(raw[j], raw[j], sq); }
+#pragma unroll
+                        for (int o = 16; o >= 1; o >>= 1) {
+                            sm += __shfl_xor_sync(0xffffffffu, sm, o);
+                            sq += __shfl_xor_sync(0xffffffffu, sq, o);
+                        }
+                        if (lane == 0) {                                // every band has exactly one owner warp
+                            two_sum_add(s_mom[b], sm);
+                            two_sum_add(s_mom[kMaxMels + b], sq);
+                        }
+                    }
+                    // the affine is applied here; the dynamic-range floor commutes with it: max(v, M - r) * s + t = max(v s + t, (M - r) s + t)
+                    const float2 af = s_aff[b];
+                    v.x = fmaf(v.x, af.x, af.y);
+                    v.y = fmaf(v.y, af.x, af.y);
+                    v.z = fmaf(v.z, af.x, af.y);
+                    v.w = fmaf(v.w, af.x, af.y);
                     if (vec_store) {
                         if (p.out_bf16) {
                             const __nv_bfloat162 lo2 = __floats2bfloat162_rn(v.x, v.y), hi2 = __floats2bfloat162_rn(v.z, v.w);
@@ -742,20 +807,28 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                         } else {
                             *reinterpret_cast<float4*>(static_cast<float*>(p.out) + out_col) = v;
                         }
-                        vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
-                        vmin = fminf(fminf(vmin, fminf(v.x, v.y)), fminf(v.z, v.w));
+                        vmax = fmaxf(fmaxf(vmax, fmaxf(raw[0], raw[1])), fmaxf(raw[2], raw[3]));
+                        vmin = fminf(fminf(vmin, fminf(raw[0], raw[1])), fminf(raw[2], raw[3]));
+                        chk += (raw[0] + raw[1]) + (raw[2] + raw[3]);
                     } else {
                         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            if (j < n_valid) {
-                                if (p.out_bf16) static_cast<__nv_bfloat16*>(p.out)[out_col + j] = __float2bfloat16_rn(vv[j]);
-                                else static_cast<float*>(p.out)[out_col + j] = vv[j];
-                                vmax = fmaxf(vmax, vv[j]);
-                                vmin = fminf(vmin, vv[j]);
+                            if (j < n_store) {
+                                const float o = j < n_valid ? vv[j] : p.fill_value;
+                                if (p.out_bf16) static_cast<__nv_bfloat16*>(p.out)[out_col + j] = __float2bfloat16_rn(o);
+                                else static_cast<float*>(p.out)[out_col + j] = o;
+                                if (j < n_valid) {
+                                    vmax = fmaxf(vmax, raw[j]);
+                                    vmin = fminf(vmin, raw[j]);
+                                    chk += raw[j];
+                                }
                             }
                     }
                 }
+                // a sample beyond the fp16 range of the split operands (|x| >= ~4 without a pre-scale) turns into inf / NaN features:
+                // flag it (bit 1) instead of returning garbage silently
+                if (!(fabsf(chk) < 3.0e38f)) atomicOr(p.error_flag, 2);
                 if (p.clip_max) {
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
@@ -773,9 +846,17 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
         }
     }
 
-    if (!ok && p.error_flag) atomicExch(p.error_flag, 1);
+    if (!ok && p.error_flag) atomicOr(p.error_flag, 1);
     tc_fence_before();
     __syncthreads();
+    if (p.moments_partial) {     // per-CTA partial sums (compensated fp32 pairs -> fp64 once), combined in a fixed order afterwards
+        const float2* s_mom = reinterpret_cast<const float2*>(smem + kOffMom);
+        double* dst = p.moments_partial + (size_t)blockIdx.x * 2 * p.n_mels;
+        for (int i = tid; i < p.n_mels; i += kThreads) {
+            dst[i] = (double)s_mom[i].x + (double)s_mom[i].y;
+            dst[p.n_mels + i] = (double)s_mom[kMaxMels + i].x + (double)s_mom[kMaxMels + i].y;
+        }
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemCols));
 }
 
@@ -791,18 +872,27 @@ __device__ __forceinline__ void store_out(__nv_bfloat16* q, float v) { *q = __fl
 template <typename T>
 __global__ void __launch_bounds__(256) dftgemm_floor_kernel(T* __restrict__ out, long long out_clip_stride, long long frame_capacity, int n_mels,
                                                             int frames, int tiles_per_clip, const int* __restrict__ clip_max,
-                                                            const int* __restrict__ tile_min, float range) {
+                                                            const int* __restrict__ tile_min, float range, float aff_scale, float aff_shift,
+                                                            const float* __restrict__ bin_mean, const float* __restrict__ bin_std,
+                                                            const long long* __restrict__ clip_length, int drop_last_frame) {
     const int clip = blockIdx.y;
-    const float floor_v = key_float(__ldg(clip_max + clip)) - range;
+    const float floor_raw = key_float(__ldg(clip_max + clip)) - range;      // on the un-normalised log-mel; stored values carry the affine
+    if (clip_length) frames = min(frames, (int)(__ldg(clip_length + clip) / kHop) + (drop_last_frame ? 0 : 1));
+    auto floor_of = [&](int b) {
+        if (bin_mean == nullptr) return fmaf(floor_raw, aff_scale, aff_shift);
+        const float sc = 1.f / __ldg(bin_std + b);
+        return fmaf(floor_raw, sc, -__ldg(bin_mean + b) * sc);
+    };
     const int t_end = min(tiles_per_clip, (int)(blockIdx.x + 1) * kFloorTilesPerCta);
     for (int tic = blockIdx.x * kFloorTilesPerCta; tic < t_end; ++tic) {
-        if (!(-key_float(__ldg(tile_min + clip * tiles_per_clip + tic)) < floor_v)) continue;     // CTA-uniform: nothing below the floor
+        if (!(-key_float(__ldg(tile_min + clip * tiles_per_clip + tic)) < floor_raw)) continue;     // CTA-uniform: nothing below the floor
         const int f0 = tic * kTileFrames, nf = min(kTileFrames, frames - f0);
         T* base = out + (long long)clip * out_clip_stride + f0;
         if (sizeof(T) == 4 && nf == kTileFrames && ((reinterpret_cast<uintptr_t>(base) | (uintptr_t)(frame_capacity * 4)) & 15) == 0) {
 #pragma unroll 4
             for (int i = threadIdx.x; i < n_mels * (kTileFrames / 4); i += blockDim.x) {
                 const int b = i / (kTileFrames / 4), f4 = i - b * (kTileFrames / 4);
+                const float floor_v = floor_of(b);
                 float4* q = reinterpret_cast<float4*>(base + (long long)b * frame_capacity) + f4;
                 float4 v = *q;
                 if (fminf(fminf(v.x, v.y), fminf(v.z, v.w)) < floor_v) {
@@ -814,12 +904,24 @@ __global__ void __launch_bounds__(256) dftgemm_floor_kernel(T* __restrict__ out,
             for (int i = threadIdx.x; i < n_mels * kTileFrames; i += blockDim.x) {
                 const int b = i / kTileFrames, f = i - b * kTileFrames;
                 if (f < nf) {
+                    const float floor_v = floor_of(b);
                     T* q = base + (long long)b * frame_capacity + f;
                     if (load_out(q) < floor_v) store_out(q, floor_v);
                 }
             }
         }
     }
+}
+
+// Sum the per-CTA moment partials in a fixed order and add them into the running accumulators: one warp per value
+__global__ void __launch_bounds__(256) dftgemm_moments_reduce_kernel(const double* __restrict__ partial, int n_parts, int n_vals, double* __restrict__ acc) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= n_vals) return;
+    double s = 0.0;
+    for (int k = lane; k < n_parts; k += 32) s += partial[(size_t)k * n_vals + i];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) acc[i] += s;
 }
 
 }  // namespace acbg
@@ -1022,6 +1124,11 @@ static bool make_sample_map(CUtensorMap* tm, const float* base, long long rows, 
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+int64_t acb_dftgemm_moments_workspace_bytes(const acb_dftgemm* fe) {
+    if (!fe) return fail(ACB_ERR_INVALID, "acb_dftgemm_moments_workspace_bytes: null handle");
+    return (int64_t)fe->num_sms * 2 * fe->n_mels * (int64_t)sizeof(double);
+}
+
 int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* stream) {
     if (!fe || !a) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: null argument");
     if (!a->wav || !a->out) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: wav and out must be device pointers");
@@ -1034,7 +1141,14 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     if (a->clip_stride < a->length) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: clip_stride < length");
     if (a->out_clip_stride < (int64_t)fe->n_mels * a->frame_capacity) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: out_clip_stride too small");
     if (a->dyn_range > 0.f && !a->clip_max) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: dyn_range needs the clip_max workspace");
-    if (a->affine && !(a->affine_std > 0.f)) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: affine_std must be positive");
+    if (a->affine < 0 || a->affine > 2) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: bad affine mode");
+    if (a->affine == 1 && !(a->affine_std > 0.f)) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: affine_std must be positive");
+    if (a->affine == 2 && (!a->bin_mean || !a->bin_std)) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: per-bin affine needs bin_mean / bin_std");
+    if (a->peak_norm && !a->clip_peak) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: peak_norm needs clip_peak (acb_peak_abs)");
+    if (a->moments && !a->moments_workspace) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: moments need a workspace");
+    if (a->moments && a->dyn_range > 0.f)
+        return fail(ACB_ERR_UNSUPPORTED, "acb_dftgemm_forward: fused moments describe the features before the per-clip dynamic-range floor; "
+                                         "with dyn_range > 0 run acb_moments_accumulate over the stored features instead");
     const int64_t tiles_per_clip = (T + kTileFrames - 1) / kTileFrames;
     if (tiles_per_clip * a->n_clips > INT32_MAX) return fail(ACB_ERR_INVALID, "acb_dftgemm_forward: more than 2^31 tiles in one call");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1063,14 +1177,22 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
     p.frame_capacity = a->frame_capacity;
     p.clip_max = a->dyn_range > 0.f ? a->clip_max : nullptr;
     p.tile_min = p.clip_max ? a->clip_max + a->n_clips : nullptr;
-    p.aff_scale = a->affine ? 1.f / a->affine_std : 1.f;
-    p.aff_shift = a->affine ? -a->affine_mean / a->affine_std : 0.f;
+    p.aff_scale = a->affine == 1 ? 1.f / a->affine_std : 1.f;
+    p.aff_shift = a->affine == 1 ? -a->affine_mean / a->affine_std : 0.f;
+    p.bin_mean = a->affine == 2 ? a->bin_mean : nullptr;
+    p.bin_std = a->affine == 2 ? a->bin_std : nullptr;
+    p.clip_length = reinterpret_cast<const long long*>(a->clip_length);
+    p.clip_peak = a->clip_peak;
+    p.peak_norm = a->peak_norm;
+    p.drop_last_frame = a->drop_last_frame;
+    p.fill_value = a->fill_value;
     p.error_flag = fe->d_err;
     p.trace = fe->d_trace;
     if (p.clip_max)   // one fill for both arrays: keys below every float (tile_min holds keys of the negated minimum)
         ACBG_CUDA(cudaMemsetAsync(p.clip_max, 0x80, sizeof(int) * (size_t)a->n_clips * (size_t)(1 + tiles_per_clip), s));
     const int64_t n_tiles = tiles_per_clip * a->n_clips;
     const int grid = (int)std::min<int64_t>(n_tiles, fe->num_sms);
+    p.moments_partial = a->moments ? static_cast<double*>(a->moments_workspace) : nullptr;
     // tensor maps of the sample buffer: usable when every tile start is a whole 128-byte row of a 16-byte aligned buffer
     CUtensorMap tm128, tm16;
     std::memset(&tm128, 0, sizeof(tm128));
@@ -1087,10 +1209,17 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
         const dim3 fgrid((unsigned)((tiles_per_clip + kFloorTilesPerCta - 1) / kFloorTilesPerCta), (unsigned)a->n_clips);
         if (p.out_bf16)
             dftgemm_floor_kernel<__nv_bfloat16><<<fgrid, 256, 0, s>>>(static_cast<__nv_bfloat16*>(a->out), a->out_clip_stride, a->frame_capacity, fe->n_mels,
-                                                                     (int)T, (int)tiles_per_clip, p.clip_max, p.tile_min, a->dyn_range * p.aff_scale);
+                                                                     (int)T, (int)tiles_per_clip, p.clip_max, p.tile_min, a->dyn_range, p.aff_scale,
+                                                                     p.aff_shift, p.bin_mean, p.bin_std, p.clip_length, p.drop_last_frame);
         else
             dftgemm_floor_kernel<float><<<fgrid, 256, 0, s>>>(static_cast<float*>(a->out), a->out_clip_stride, a->frame_capacity, fe->n_mels, (int)T,
-                                                             (int)tiles_per_clip, p.clip_max, p.tile_min, a->dyn_range * p.aff_scale);
+                                                             (int)tiles_per_clip, p.clip_max, p.tile_min, a->dyn_range, p.aff_scale, p.aff_shift,
+                                                             p.bin_mean, p.bin_std, p.clip_length, p.drop_last_frame);
+        ACBG_CUDA(cudaGetLastError());
+    }
+    if (a->moments) {
+        const int n_vals = 2 * fe->n_mels;
+        dftgemm_moments_reduce_kernel<<<(n_vals + 7) / 8, 256, 0, s>>>(p.moments_partial, grid, n_vals, a->moments);
         ACBG_CUDA(cudaGetLastError());
     }
     return ACB_OK;
@@ -1112,7 +1241,9 @@ int acb_dftgemm_check(const acb_dftgemm* fe, void* stream) {
     ACBG_CUDA(cudaMemcpy(&flag, fe->d_err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag) {
         cudaMemset(fe->d_err, 0, sizeof(int));
-        return fail(ACB_ERR_CUDA, "acb_dftgemm_check: a tensor-core pipeline barrier timed out inside the kernel (results are invalid)");
+        if (flag & 1) return fail(ACB_ERR_CUDA, "acb_dftgemm_check: a tensor-core pipeline barrier timed out inside the kernel (results are invalid)");
+        return fail(ACB_ERR_INVALID, "acb_dftgemm_check: non-finite features -- a sample beyond the fp16 operand range (|x| >= ~4) or a NaN input; "
+                                     "pass clip_peak (acb_peak_abs) so that every clip is pre-scaled by a power of two");
     }
     return ACB_OK;
 }

@@ -320,11 +320,21 @@ class LogMelFrontend:
         T4 = padded_frames(self.frames_for_length(L), pad_multiple)
         if out_host is None:
             out_host = torch.empty((B, self.n_mels, T4), dtype=out_dtype, pin_memory=True)
+        # the C side writes B * n_mels * T4 elements of out_host's dtype through raw pointers: shapes, dtypes, devices and
+        # contiguity are checked here, once
+        if out_host.is_cuda or not out_host.is_contiguous() or tuple(out_host.shape) != (B, self.n_mels, T4) \
+                or out_host.dtype not in (torch.float32, torch.bfloat16):
+            raise ValueError(f"out_host must be a contiguous host float32 / bfloat16 tensor of shape {(B, self.n_mels, T4)}")
         if staging is None:
             staging = (torch.empty((B, L), dtype=torch.float32, device=self.device),
                        torch.empty((B, self.n_mels, T4), dtype=out_host.dtype, device=self.device))
         if pcm and len(staging) < 3:
             staging = (staging[0], staging[1], torch.empty((B, L), dtype=torch.int16, device=self.device))
+        want = [((B, L), torch.float32), ((B, self.n_mels, T4), out_host.dtype)] + ([((B, L), torch.int16)] if pcm else [])
+        for t, (shape, dtype) in zip(staging, want):
+            if t.device != self.device or not t.is_contiguous() or tuple(t.shape) != shape or t.dtype != dtype:
+                raise ValueError(f"staging buffers must be contiguous tensors on {self.device}: wav float32 {want[0][0]}, out "
+                                 f"{out_host.dtype} {want[1][0]}" + (", pcm int16 " + str(want[2][0]) if pcm else ""))
         a = LogmelArgs()
         a.frame_capacity = T4
         keep = self._fill_common(a, staging[1], "mel_major", pad_multiple, False, 0.0, affine, None, None)

@@ -29,7 +29,7 @@ extern "C" {
 #define ACB_ERR_CUDA (-2)         /* a CUDA runtime call failed; message carries cudaGetErrorString */
 #define ACB_ERR_UNSUPPORTED (-3)  /* valid request this build has no kernel for */
 
-#define ACB_ABI_VERSION 1
+#define ACB_ABI_VERSION 2
 
 /* output element type */
 #define ACB_F32 0
@@ -224,18 +224,36 @@ typedef struct acb_dftgemm_args {
     int64_t out_clip_stride;   /* elements */
     int64_t frame_capacity;    /* >= frames */
     float dyn_range;           /* > 0: out = max(out, max over the clip - dyn_range) (Whisper: 8.0); <= 0: none */
-    int32_t affine;            /* !=0: out = (out - affine_mean) / affine_std afterwards (Whisper: mean -4, std 4) */
+    int32_t affine;            /* 1: out = (out - affine_mean) / affine_std afterwards (Whisper: mean -4, std 4); 2: per band with bin_mean / bin_std */
     float affine_mean;
     float affine_std;
     int32_t* clip_max;         /* device workspace of acb_dftgemm_workspace_ints() int32 (per-clip maximum and per-tile minimum keys),
                                 * needed when dyn_range > 0 */
     int32_t out_dtype;         /* ACB_F32 | ACB_BF16 (the affine is applied in fp32 before the single rounding) */
+    /* ---- the fields below mirror acb_logmel_args (ABI version 2) ---- */
+    const int64_t* clip_length;  /* device [n_clips]: samples of clip i (200 < clip_length[i] <= length; rows are padded to `length` with
+                                  * finite values); reflection happens at each clip's own end, frames beyond a clip's count get
+                                  * fill_value; NULL => every clip has `length` samples */
+    const float* clip_peak;      /* device [n_clips] max|x| (acb_peak_abs) or NULL.  Given: every clip is pre-scaled by the power of two
+                                  * that brings its peak into [0.5, 1) and the mel powers are scaled back exactly, so ANY amplitude fits the
+                                  * fp16 operands.  NULL: the caller vouches for |x| <= 2; acb_dftgemm_check reports violations. */
+    int32_t peak_norm;           /* !=0 (needs clip_peak): fused process_audio_chunk gain 0.95 / (peak + 1e-8) (preprocess/core.py:108-110) */
+    float fill_value;            /* frames [frames of the clip, frames of `length`) of a shorter clip */
+    const float* bin_mean;       /* device [n_mels] when affine == 2 (the stored per-bin statistics) */
+    const float* bin_std;
+    double* moments;             /* device [2 * n_mels], ACCUMULATED into: per-bin sum and sum of squares of the un-normalised log-mel over
+                                  * the frames that exist (compute_mel_stats.py:26-27).  Only with dyn_range <= 0: the per-clip floor is
+                                  * applied after the kernel; floored features go through acb_moments_accumulate. */
+    void* moments_workspace;     /* device, acb_dftgemm_moments_workspace_bytes() bytes, when moments != NULL */
 } acb_dftgemm_args;
+/* bytes of device workspace the fused moments of acb_dftgemm_forward need */
+int64_t acb_dftgemm_moments_workspace_bytes(const acb_dftgemm* fe);
 
 /* One persistent tcgen05 launch on `stream`, plus -- when dyn_range > 0 -- a pass that rewrites only the tiles holding values below
  * their clip's floor (the kernel records every tile's minimum). */
 int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* args, void* stream);
-/* Synchronises `stream` and reports whether any in-kernel pipeline barrier timed out since the last check. */
+/* Synchronises `stream` and reports what the launches since the last check flagged: ACB_ERR_CUDA when an in-kernel pipeline barrier
+ * timed out, ACB_ERR_INVALID when features came out non-finite (a sample beyond the fp16 operand range without clip_peak, or NaN input). */
 int acb_dftgemm_check(const acb_dftgemm* fe, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -60,6 +60,17 @@ def synth_clip(n: int, seed: int) -> np.ndarray:
     return x
 
 
+def bench_clip(n: int, seed: int) -> np.ndarray:
+    """A clip of the BENCHMARK's distribution (bench.synth_batch: N(0, 0.1^2) noise under the slow envelope, clipped to +-1, last 5 %
+    exact zeros) made RNG-independent: the Gaussian is the sum of four hash-noise uniforms scaled to sigma = 0.1."""
+    t = np.arange(n, dtype=np.float64) / SAMPLE_RATE
+    env = 0.25 + 0.75 * np.sin(2.0 * np.pi * 0.7 * t) ** 2
+    g = sum(hash_noise(n, seed + 1000 * k).astype(np.float64) for k in range(4)) * (0.1 / np.sqrt(4.0 / 12.0))
+    x = np.clip(g * env, -1.0, 1.0).astype(np.float32)
+    x[n - n // 20:] = 0.0
+    return x
+
+
 # ---------------------------------------------------------------------------------------------
 # tables (fp64 derivations; the product builds its fp32 tables with torch so that they are
 # bit-identical to torchaudio's -- tests compare both)

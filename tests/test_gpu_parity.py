@@ -3,6 +3,8 @@ the fp64 oracle on seeded inputs, and size-independent properties at the BASELIN
 
 Tolerances (BASELINE.json north_star): frame counts and lengths bit-exact; log-mel within 1e-4 absolute in fp32,
 1e-2 for bf16 output (on normalised features -- raw ln-mel cannot be represented in bf16 to 1e-2)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -449,6 +451,36 @@ def test_host_buffer_path_matches_device_path(fe):
     y = fe.forward_host(x, n_chunks=3, affine=(acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT))
     ref = fe.forward(x.cuda(), affine=(acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT)).cpu()
     assert torch.equal(y, ref)
+
+
+def test_host_buffer_path_validates_its_buffers(fe):
+    x = torch.from_numpy(np.stack([o.synth_clip(16000, 1), o.synth_clip(16000, 2)])).pin_memory()
+    T = 1 + 16000 // 256
+    for bad in (torch.empty((2, 80, T + 1)), torch.empty((2, 80, T), dtype=torch.float64), torch.empty((2, 80, T), device="cuda"),
+                torch.empty((2, T, 80)).transpose(1, 2)):
+        with pytest.raises(ValueError):
+            fe.forward_host(x, bad)
+    good = torch.empty((2, 80, T), dtype=torch.bfloat16, pin_memory=True)
+    with pytest.raises(ValueError):      # the device-side output buffer must have the host buffer's dtype
+        fe.forward_host(x, good, staging=(torch.empty((2, 16000), device="cuda"), torch.empty((2, 80, T), device="cuda")))
+    y = fe.forward_host(x, good, affine=(acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT))
+    ref = fe.forward(x.cuda(), affine=(acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT), out_dtype=torch.bfloat16).cpu()
+    assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("seed", [101, 202, 303])
+def test_benchmark_distribution_goldens_at_30s(fe, seed):
+    """configs[1] at its own size and distribution, against vectors the reference minted (oracle/gen_golden_bench.py): 30 s clips
+    of the benchmark's Gaussian-under-envelope signal -> scalar-normalised log-mel [80, 1876]."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_cases.npz"))
+    x = o.bench_clip(480000, seed)
+    batch = dev(np.stack([x, x[::-1].copy(), x]))                           # the clip among others, as in a batch
+    y = fe.forward(batch, affine=(acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT))
+    assert tuple(y.shape) == (3, 80, 1876) and torch.equal(y[0], y[2])
+    got = y[0].cpu().numpy()
+    assert float(np.max(np.abs(got[:, ::7] - g[f"norm_bench_30s_s{seed}_sub7"]))) < EXPECT
+    mn, mx, mean = g[f"norm_bench_30s_s{seed}_stats"]
+    assert abs(got.min() - mn) < EXPECT and abs(got.max() - mx) < EXPECT and abs(float(got.astype(np.float64).mean()) - mean) < EXPECT
 
 
 # ----------------------------------------------------------------------------------- BASELINE sizes: properties

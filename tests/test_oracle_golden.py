@@ -123,3 +123,17 @@ def test_hash_noise_known_answer():
     x = o.hash_noise(16000, 1)
     assert np.allclose(x[:4], [0.26630175, -0.37396902, 0.20093119, 0.13287622], atol=1e-8)
     assert abs(float(np.abs(x).max()) - 0.49997401) < 1e-7
+
+
+def test_oracle_matches_the_benchmark_distribution_goldens():
+    """configs[1] at its own size: 30 s clips of the benchmark's signal through the reference (oracle/gen_golden_bench.py)."""
+    import os
+    import audio_calm_b200 as acb
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bench_cases.npz"))
+    w, fb = acb.tables.calm_tables()
+    x = o.bench_clip(480000, 202)
+    y = o.normalise_global(o.logmel(x, w.numpy(), fb.numpy()))
+    assert y.shape == (80, 1876)
+    assert float(np.max(np.abs(y[:, ::7] - g["norm_bench_30s_s202_sub7"]))) < 1e-5
+    mn, mx, mean = g["norm_bench_30s_s202_stats"]
+    assert abs(y.min() - mn) < 1e-5 and abs(y.max() - mx) < 1e-5 and abs(float(y.mean()) - mean) < 1e-6

@@ -214,3 +214,80 @@ def test_tonal_high_dynamic_range(fe, gw):
     assert d.max() < TOL, d.max()
     assert np.all(y[:, 150:] == y[0, -1])                    # the zero-padded tail sits on the dynamic-range floor
     assert abs((y.max() - y.min()) - 2.0) < 1e-5             # max - floor = 8 / 4
+
+
+# ----------------------------------------------------------------------------------- round 2: the fields of the 1024 route
+def test_any_amplitude_with_the_peak_prescale(fe, gw):
+    """A clip scaled to +-30 000 (un-normalised PCM-scale floats): WhisperFeatureExtractor takes it; so does extract(), which
+    pre-scales every clip by a power of two.  The dynamic-range floor and the affine are shift-invariant up to the clamp, so the
+    expected features are the golden ones shifted by log10(s^2) / 4 wherever the clamp (1e-10) was not active."""
+    x = o.synth_clip(32000, 3)
+    s = 30000.0
+    ref = wo.whisper_logmel(x * s, fe.window.numpy(), fe.fb.numpy())
+    y = fe.forward(dev(x * np.float32(s))[None], check=True, peak=True)[0].cpu().numpy()
+    assert y.shape == ref.shape and np.abs(y - ref).max() < EXPECT
+    y30 = fe.extract([dev(o.synth_clip(48000, 5) * np.float32(s))])[0].cpu().numpy()
+    ref30 = wo.whisper_logmel(wo.pad_or_trim(o.synth_clip(48000, 5) * np.float32(s)), fe.window.numpy(), fe.fb.numpy())
+    assert np.abs(y30 - ref30).max() < EXPECT
+    # the same clip in [-1, 1] is unchanged by the pre-scale (exact powers of two)
+    y1 = fe.forward(dev(x)[None], check=True, peak=True)[0].cpu().numpy()
+    assert np.abs(y1 - gw["raw_synth_2s_s3"]).max() < EXPECT
+
+
+def test_out_of_range_samples_are_reported_not_returned(fe):
+    x = dev(o.synth_clip(32000, 3) * np.float32(50.0))[None]         # |x| up to ~50: beyond the fp16 operand range without a pre-scale
+    with pytest.raises(acb._lib.AcbError):
+        fe.forward(x, check=True)
+    fe.forward(x)
+    with pytest.raises(acb._lib.AcbError):
+        fe.check()
+    fe.check()                                                        # the flag is cleared by the report
+    with pytest.raises(acb._lib.AcbError):
+        fe.forward_host(x.cpu().pin_memory())
+
+
+def test_ragged_batch_matches_per_clip_features(fe):
+    """Ragged input: every clip keeps its own frame count, its own reflected end and its own dynamic-range floor."""
+    lens = (20011, 70000, 16000, 3001, 48000)
+    waves = [o.synth_clip(n, 60 + i) for i, n in enumerate(lens)]
+    out, frames = fe.forward_ragged([dev(w) for w in waves], check=True, fill_value=-7.0)
+    assert frames.tolist() == [n // 160 for n in lens] and out.shape[2] == max(frames.tolist())
+    for i, w in enumerate(waves):
+        ref = wo.whisper_logmel(w, fe.window.numpy(), fe.fb.numpy())
+        T = ref.shape[1]
+        assert np.abs(out[i, :, :T].cpu().numpy() - ref).max() < EXPECT, i
+        if T < out.shape[2]:
+            assert bool((out[i, :, T:] == -7.0).all())
+
+
+def test_peak_norm_affine_and_moments(gw):
+    """The 1024 route's fields on the 400 / 160 transform: fused process_audio_chunk gain, per-bin affine from stored statistics,
+    fused per-bin moments (no dynamic-range floor), and moments of floored features through the standalone reduction."""
+    fe0 = acb.WhisperLogMel("cuda", dyn_range=0.0, affine_mean=None)                 # plain log10-mel of the 400 / 160 transform
+    waves = [o.synth_clip(n, 80 + i) * np.float32(0.3 + 0.2 * i) for i, n in enumerate((32000, 20011, 48000))]
+    window, fb = fe0.window.numpy(), fe0.fb.numpy()
+    normed = [o.process_audio_chunk(w[None])[0] for w in waves]
+    refs = [wo.whisper_logmel(w, window, fb, dyn_range=None, affine=None) for w in normed]
+    acc = acb.MelStatsAccumulator(80, "cuda")
+    out, frames = fe0.forward_ragged([dev(w) for w in waves], check=True, peak=True, peak_norm=True, moments=acc)
+    for i, r in enumerate(refs):
+        assert np.abs(out[i, :, :r.shape[1]].cpu().numpy() - r).max() < EXPECT, i
+    s, s2, n = o.stats_per_bin(refs)
+    bm, bs = o.stats_per_bin_finalise(s, s2, n)
+    st = acc.finalize()
+    assert st.frames == n and np.max(np.abs(st.bin_mean - bm)) < 1e-5 and np.max(np.abs(st.bin_std - bs)) < 1e-5
+    # per-bin affine with those statistics
+    out2, _ = fe0.forward_ragged([dev(w) for w in waves], check=True, peak=True, peak_norm=True, affine=st.affine())
+    for i, r in enumerate(refs):
+        want = (r - bm[:, None]) / bs[:, None]
+        assert np.abs(out2[i, :, :r.shape[1]].cpu().numpy() - want).max() < 1e-4, i
+    # with the Whisper floor the moments come from the stored (floored, un-normalised) features
+    fe8 = acb.WhisperLogMel("cuda", affine_mean=None)
+    acc8 = acb.MelStatsAccumulator(80, "cuda")
+    fe8.forward_ragged([dev(w) for w in waves], check=True, moments=acc8)
+    refs8 = [wo.whisper_logmel(w, window, fb, affine=None) for w in waves]
+    s, s2, n = o.stats_per_bin(refs8)
+    bm8, _ = o.stats_per_bin_finalise(s, s2, n)
+    assert acc8.finalize().frames == n and np.max(np.abs(acc8.finalize().bin_mean - bm8)) < 1e-5
+    with pytest.raises(ValueError):
+        acb.WhisperLogMel("cuda").forward_ragged([dev(waves[0])], moments=acb.MelStatsAccumulator(80, "cuda"))
