@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 // patched over what the tensor copy brought in; only the first and the last tiles of a clip have any
                 const float* src = p.wav + (long long)clip * p.clip_stride;
                 const long long g0 = (long long)(tic * kTileFrames - 2) * kHop, L = clip_len;
-                const long long e0 = L - g0;                        // first staged position beyond the clip
+                const long long e0 = max(0LL, L - g0);              // first staged position beyond the clip (0: the whole tile lies beyond a short clip of a ragged batch)
                 if (g0 < 0 || e0 < kBlocks * kHop) {                // CTA-uniform
                     if (g0 < 0)
                         for (int i = wtid; i < (int)-g0; i += kWorkerThreads) {
@@ -772,6 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                         a.w = fmaf(w, q.w, a.w);
                     }
                     a.x *= post; a.y *= post; a.z *= post; a.w *= post;      // undo the pre-scale (exact power of two) / apply the peak gain
+                    chk += (a.x + a.y) + (a.z + a.w);                        // inf / NaN powers (operand overflow) must not hide behind the clamp
                     float4 v;
                     v.x = (a.x > clamp_min) ? lg2_normal(a.x) * log_scale : log_floor;
                     v.y = (a.y > clamp_min) ? lg2_normal(a.y) * log_scale : log_floor;
@@ -809,7 +810,6 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                         }
                         vmax = fmaxf(fmaxf(vmax, fmaxf(raw[0], raw[1])), fmaxf(raw[2], raw[3]));
                         vmin = fminf(fminf(vmin, fminf(raw[0], raw[1])), fminf(raw[2], raw[3]));
-                        chk += (raw[0] + raw[1]) + (raw[2] + raw[3]);
                     } else {
                         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -821,14 +821,13 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                                 if (j < n_valid) {
                                     vmax = fmaxf(vmax, raw[j]);
                                     vmin = fminf(vmin, raw[j]);
-                                    chk += raw[j];
                                 }
                             }
                     }
                 }
                 // a sample beyond the fp16 range of the split operands (|x| >= ~4 without a pre-scale) turns into inf / NaN features:
                 // flag it (bit 1) instead of returning garbage silently
-                if (!(fabsf(chk) < 3.0e38f)) atomicOr(p.error_flag, 2);
+                if (!(fabsf(chk) < 3.0e38f) && n_valid > 0) atomicOr(p.error_flag, 2);
                 if (p.clip_max) {
 #pragma unroll
                     for (int o = 16; o >= 1; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
