@@ -63,6 +63,12 @@ constexpr int kTileFrames = 128;
 #undef ACBG_ABLATE
 #define ACBG_ABLATE 0
 #endif
+#ifndef ACBG_CHK
+#define ACBG_CHK 1
+#endif
+#ifndef ACBG_PRESCALE
+#define ACBG_PRESCALE 1
+#endif
 #ifndef ACBG_A_HI_TMEM
 #define ACBG_A_HI_TMEM 1        // 1: the A_hi slices live in the 64 TMEM columns the accumulators leave free (.ts MMAs); 0: all operands in shared memory
 #endif
@@ -368,7 +374,7 @@ __device__ __forceinline__ void build_a_slices(const float* __restrict__ srow, i
         const float4 wr0 = *reinterpret_cast<const float4*>(s_wr + n0), wr1 = *reinterpret_cast<const float4*>(s_wr + n0 + 4);
         float wa[8] = {wf0.x, wf0.y, wf0.z, wf0.w, wf1.x, wf1.y, wf1.z, wf1.w};
         float wb[8] = {wr0.x, wr0.y, wr0.z, wr0.w, wr1.x, wr1.y, wr1.z, wr1.w};
-        if (pre != 1.f) {      // warp-uniform: the clip's power-of-two pre-scale (exact), folded into the window
+        if (ACBG_PRESCALE && pre != 1.f) {      // warp-uniform: the clip's power-of-two pre-scale (exact), folded into the window
 #pragma unroll
             for (int i = 0; i < 8; ++i) { wa[i] *= pre; wb[i] *= pre; }
         }
@@ -455,6 +461,7 @@ __device__ __forceinline__ bool tile_source(const Params& p, int tile, const flo
 // Warp roles: 16 worker warps run the epilogue and gather edge tiles, the first 8 of them (thread = frame row x k-half) also build
 // the A slices; warp 16 (one elected lane) issues the MMAs, warp 17 streams the B slices and prefetches sample tiles.  All hand-offs are mbarriers: no
 // CTA-wide barrier sits inside the K loop.
+template <bool kMoments>
 __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Params p, const __grid_constant__ CUtensorMap tm_box128,
                                                                      const __grid_constant__ CUtensorMap tm_box16) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -756,6 +763,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 // four consecutive frames of a band go out as one 16-byte (fp32) / 8-byte (bf16) store when every row keeps them aligned
                 const bool vec_store = n_valid >= 4 && ((reinterpret_cast<uintptr_t>(p.out) | (uintptr_t)(p.out_clip_stride * esize) | (uintptr_t)(cap * esize)) & (4 * esize - 1)) == 0;
                 float vmax = -3.0e38f, vmin = 3.0e38f, chk = 0.f;
+                const float clamp_eff = clamp_min / post, log_post = post == 1.f ? 0.f : log2f(post) * log_scale;
                 const float4* pow4 = reinterpret_cast<const float4*>(s_pow) + lane;
                 for (int b = b_begin; b < b_end; ++b, out_col += cap) {
                     const int4 bd = s_band[b];
@@ -771,15 +779,16 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                         a.z = fmaf(w, q.z, a.z);
                         a.w = fmaf(w, q.w, a.w);
                     }
-                    a.x *= post; a.y *= post; a.z *= post; a.w *= post;      // undo the pre-scale (exact power of two) / apply the peak gain
-                    chk += (a.x + a.y) + (a.z + a.w);                        // inf / NaN powers (operand overflow) must not hide behind the clamp
+                    if (ACBG_CHK) chk += (a.x + a.y) + (a.z + a.w);          // inf / NaN powers (operand overflow) must not hide behind the clamp
+                    // the factor that undoes the pre-scale / applies the peak gain moves through the log: log(a post) = log a + log post,
+                    // and the clamp is compared against clamp_min / post
                     float4 v;
-                    v.x = (a.x > clamp_min) ? lg2_normal(a.x) * log_scale : log_floor;
-                    v.y = (a.y > clamp_min) ? lg2_normal(a.y) * log_scale : log_floor;
-                    v.z = (a.z > clamp_min) ? lg2_normal(a.z) * log_scale : log_floor;
-                    v.w = (a.w > clamp_min) ? lg2_normal(a.w) * log_scale : log_floor;
+                    v.x = (a.x > clamp_eff) ? fmaf(lg2_normal(a.x), log_scale, log_post) : log_floor;
+                    v.y = (a.y > clamp_eff) ? fmaf(lg2_normal(a.y), log_scale, log_post) : log_floor;
+                    v.z = (a.z > clamp_eff) ? fmaf(lg2_normal(a.z), log_scale, log_post) : log_floor;
+                    v.w = (a.w > clamp_eff) ? fmaf(lg2_normal(a.w), log_scale, log_post) : log_floor;
                     const float raw[4] = {v.x, v.y, v.z, v.w};          // un-normalised log-mel: maximum / minimum tracking, moments
-                    if (p.moments_partial) {                            // CTA-uniform: per-band sums over the frames that exist
+                    if (kMoments) {                                     // per-band sums over the frames that exist (compiled out of the plain kernel)
                         float sm = 0.f, sq = 0.f;
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
@@ -848,7 +857,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
     if (!ok && p.error_flag) atomicOr(p.error_flag, 1);
     tc_fence_before();
     __syncthreads();
-    if (p.moments_partial) {     // per-CTA partial sums (compensated fp32 pairs -> fp64 once), combined in a fixed order afterwards
+    if (kMoments) {              // per-CTA partial sums (compensated fp32 pairs -> fp64 once), combined in a fixed order afterwards
         const float2* s_mom = reinterpret_cast<const float2*>(smem + kOffMom);
         double* dst = p.moments_partial + (size_t)blockIdx.x * 2 * p.n_mels;
         for (int i = tid; i < p.n_mels; i += kThreads) {
@@ -1078,7 +1087,8 @@ int acb_dftgemm_create(acb_dftgemm** out, int device, int n_fft, int hop, int n_
                 cudaMemcpy(d + b_bytes + 2 * w_bytes, bands.data(), bd_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
                 cudaMemcpy(d + b_bytes + 2 * w_bytes + bd_bytes, melw.data(), mw_bytes, cudaMemcpyHostToDevice) == cudaSuccess &&
                 cudaMemset(fe->d_err, 0, 16) == cudaSuccess &&
-                cudaFuncSetAttribute(dftgemm_logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess;
+                cudaFuncSetAttribute(dftgemm_logmel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess &&
+                cudaFuncSetAttribute(dftgemm_logmel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess;
     if (!good) {
         cudaFree(fe->d_blob);
         return bail(fail(ACB_ERR_CUDA, std::string("acb_dftgemm_create: table upload failed: ") + cudaGetErrorString(cudaGetLastError())));
@@ -1202,7 +1212,8 @@ int acb_dftgemm_forward(const acb_dftgemm* fe, const acb_dftgemm_args* a, void* 
         const long long rows = ((long long)(a->n_clips - 1) * a->clip_stride + a->length + 31) / 32;
         p.use_tma = rows > 0 && make_sample_map(&tm128, a->wav, rows, kBoxRows) && make_sample_map(&tm16, a->wav, rows, 16);
     }
-    dftgemm_logmel_kernel<<<grid, kThreads, kSmemBytes, s>>>(p, tm128, tm16);
+    if (a->moments) dftgemm_logmel_kernel<true><<<grid, kThreads, kSmemBytes, s>>>(p, tm128, tm16);
+    else dftgemm_logmel_kernel<false><<<grid, kThreads, kSmemBytes, s>>>(p, tm128, tm16);
     ACBG_CUDA(cudaGetLastError());
     if (p.clip_max) {
         const dim3 fgrid((unsigned)((tiles_per_clip + kFloorTilesPerCta - 1) / kFloorTilesPerCta), (unsigned)a->n_clips);

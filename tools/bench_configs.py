@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 import audio_calm_b200 as acb
-from bench import SAMPLE_RATE, measured_peak, synth_batch
+from bench import SAMPLE_RATE, measured_peak, stats_pass, synth_batch
 
 
 def timed(fn, steps, warmup=3, flush=None):
@@ -77,56 +77,11 @@ def config1(args, fe, device):
 
 
 def config3(args, fe, device, rank, world, dist):
-    """compute_mel_stats over variable-length clips: fused extraction + per-bin fp64 moments, ONE all-reduce."""
-    n_total = args.clips
-    rng = np.random.default_rng(0)
-    lengths = rng.integers(SAMPLE_RATE, 30 * SAMPLE_RATE + 1, size=n_total).astype(np.int64)
-    mine = np.arange(rank, n_total, world)                     # round-robin: i.i.d. lengths are balanced in expectation
-    pool_len = 64 * 30 * SAMPLE_RATE                           # 123 MB of synthetic audio; clips are windows into it
-    pool = synth_batch(1, pool_len, device, seed=99 + rank)[0]
-    starts = (rng.integers(0, (pool_len - 30 * SAMPLE_RATE) // 4, size=n_total) * 4).astype(np.int64)
-    per_launch = args.clips_per_launch
-    acc = acb.MelStatsAccumulator(80, device)
-    t_frames = 0
-    # plan every launch on the host first (the planning is part of the product path, its cost is reported separately)
-    t0 = time.perf_counter()
-    launches = []
-    for lo in range(0, len(mine), per_launch):
-        idx = mine[lo:lo + per_launch]
-        lens = lengths[idx]
-        launches.append(acb.RaggedBatch(pool, torch.from_numpy(starts[idx]).to(device), torch.from_numpy(lens).to(device), lens))
-    plan_s = time.perf_counter() - t0
-
-    def run_pass():
-        acc.moments.zero_()
-        acc.frames = 0
-        for batch in launches:   # statistics-only launches: no features are stored
-            fe.forward_ragged(batch, pad_multiple=4, peak=fe.peak_abs_ragged(batch), moments=acc, stats_only=True)
-        acc.all_reduce()
-
-    run_pass()                                                  # warm-up (also sizes the workspace)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run_pass()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    st = acc.finalize()
-    t4 = np.array([acb.padded_frames(1 + int(n) // 256, 4) for n in lengths], dtype=np.int64)
-    exact_frames = int(t4.sum())
+    """compute_mel_stats over variable-length clips: fused extraction + per-bin fp64 moments, ONE all-reduce.  The clip set is the
+    globally defined one of bench.stats_clip_set (same seeds at every world size), so the statistics of N = 1 and N = 8 compare."""
+    rec = stats_pass(acb, fe, device, rank, world, dist, args.clips, per_launch=args.clips_per_launch, reps=2)
     if rank == 0:
-        audio_s = float(lengths.sum()) / SAMPLE_RATE
-        emit(config=3, workload=f"mel stats pass over {n_total} clips of 1-30 s ({audio_s / 3600:.1f} audio-hours), peak-norm + log-mel + pad-to-4 + "
-             f"per-bin fp64 moments fused (statistics-only launches, no feature store), {len(launches)} launches/rank, 1 all-reduce of 161 fp64", n_gpus=world, ms=ms,
-             audio_hours_per_s=audio_s / 3600 / (ms * 1e-3), count=st.count, count_expected=80 * exact_frames,
-             count_exact=bool(st.count == 80 * exact_frames), mel_mean=st.mel_mean, mel_std=st.mel_std, host_plan_s=plan_s)
+        emit(config=3, **rec)
 
 
 def config4(args, fe, device, rank, world, dist):

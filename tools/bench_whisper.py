@@ -22,7 +22,7 @@ if ROOT not in sys.path:
 import numpy as np
 import torch
 
-from bench import ClockSampler, measured_peak, ncu_traffic, synth_batch  # noqa: E402
+from bench import ClockSampler, measured_peak, ncu_record as ncu_traffic, synth_batch  # noqa: E402
 
 SAMPLE_RATE = 16000
 

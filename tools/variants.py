@@ -17,6 +17,9 @@ OUT = os.path.join(ROOT, "tools", "_variants")
 
 VARIANTS = {
     "base": [],
+    "wnopre": ["-DACBG_PRESCALE=0"],
+    "wnochk": ["-DACBG_CHK=0"],
+    "wnone": ["-DACBG_CHK=0", "-DACBG_PRESCALE=0"],
     "win00": ["-DACB_WIN_FUSE=0", "-DACB_WIN_T=0"],
     "win10": ["-DACB_WIN_FUSE=1", "-DACB_WIN_T=0"],
     "win01": ["-DACB_WIN_FUSE=0", "-DACB_WIN_T=1"],
@@ -94,7 +97,35 @@ def run_one(name, steps=50):
                       "frac": 256 * (4 * 480000 + 320 * 1876) / (ms * 1e-3) / 1e9 / 6537.6, "max_abs_err": worst, "cfg2_err": d2}), flush=True)
 
 
+def whisper_one(name, steps=50):
+    import torch
+    import audio_calm_b200 as acb
+    from bench import synth_batch
+    acb._lib.LIB_PATH = os.path.join(OUT, f"lib_{name}.so")
+    fe = acb.WhisperLogMel("cuda")
+    x = synth_batch(256, 480000, "cuda")
+    out = torch.empty((256, 80, 3000), device="cuda")
+    for _ in range(5):
+        fe.forward(x, out=out)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fe.forward(x, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    fe.check()
+    print(json.dumps({"variant": name, "whisper_ms": e0.elapsed_time(e1) / steps}), flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "whisper":
+        for n in sys.argv[2:]:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "whisper_one", n], check=False)
+        sys.exit(0)
+    if sys.argv[1] == "whisper_one":
+        whisper_one(sys.argv[2])
+        sys.exit(0)
     names = sys.argv[2:] or list(VARIANTS)
     if sys.argv[1] == "build":
         build(names)
