@@ -1,0 +1,67 @@
+"""Throughput of the dataset driver mirror (preprocess/process_dataset.py) end to end: files on disk -> decode threads -> ragged
+GPU batches -> {"mel"} payloads on disk.  One JSON line.
+
+    python tools/bench_dataset_driver.py [--files 2000] [--seconds 10] [--decode-threads 8]
+
+Synthetic 16-bit PCM .wav files (what LibriSpeech-style corpora hold once decoded) are written to a scratch directory first; the
+timed region is ShardRunner.run over them, i.e. what `python preprocess/process_dataset.py --mel_only` does per GPU process."""
+import argparse
+import json
+import os
+import shutil
+import sys
+import tempfile
+import time
+import types
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--files", type=int, default=2000)
+    ap.add_argument("--seconds", type=float, default=10.0)
+    ap.add_argument("--decode-threads", type=int, default=8)
+    args = ap.parse_args()
+    from scipy.io import wavfile
+    from audio_calm_b200.preprocess import process_dataset as pd
+    from oracle.logmel_oracle import hash_noise          # deterministic input only (a tool, not the product path)
+    root = tempfile.mkdtemp(prefix="acb_driver_")
+    try:
+        in_dir, out_dir = os.path.join(root, "in"), os.path.join(root, "out")
+        n = int(args.seconds * 16000)
+        rng = np.random.default_rng(0)
+        base = (hash_noise(n + 4096, 5) * 0.8 * 32767).astype(np.int16)
+        for i in range(args.files):
+            d = os.path.join(in_dir, f"spk{i % 40:03d}", f"chap{i % 7}")
+            os.makedirs(d, exist_ok=True)
+            off = int(rng.integers(0, 4096))
+            wavfile.write(os.path.join(d, f"utt{i:06d}.wav"), 16000, base[off:off + n - int(rng.integers(0, n // 2))])
+        files = pd.scan_files(in_dir)
+        audio_s = sum(os.path.getsize(f) - 44 for f in files) / 2 / 16000
+        a = types.SimpleNamespace(dataset_name="librispeech", in_dir=in_dir, out_dir=out_dir, vae_ckpt=None, mel_only=True, cv_tsv=None,
+                                  num_gpus=1, workers_per_gpu=args.decode_threads, force=False)
+        torch.set_num_threads(1)
+        runner = pd.ShardRunner(a, 0, decode_threads=args.decode_threads)
+        runner.run(files[:32])                              # warm-up: kernels, allocator, thread pools
+        shutil.rmtree(out_dir, ignore_errors=True)
+        runner = pd.ShardRunner(a, 0, decode_threads=args.decode_threads)
+        t0 = time.perf_counter()
+        runner.run(files)
+        dt = time.perf_counter() - t0
+        written = sum(len(fs) for _, _, fs in os.walk(out_dir))
+        print(json.dumps({"tool": "bench_dataset_driver", "files": len(files), "written": written, "errors": len(runner.errors),
+                          "audio_hours": audio_s / 3600, "seconds": dt, "files_per_s": len(files) / dt,
+                          "audio_hours_per_s": audio_s / 3600 / dt, "decode_threads": args.decode_threads,
+                          "host_cpus": os.cpu_count(), "payload": '{"mel": FloatTensor[80, T4]} per file, torch.save',
+                          "note": "end to end per GPU process: scipy/torchaudio decode -> int16 H2D -> peak + fused log-mel (+ pad-to-4) -> D2H -> torch.save"}))
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()
