@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     lib = ctypes.CDLL(built_lib)
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, missing
-    assert _lib.load().acb_abi_version() == 1
+    assert _lib.load().acb_abi_version() == 2
 
 
 def test_args_struct_matches_header():
