@@ -20,6 +20,10 @@ namespace acb {
 int fail(int code, const std::string& msg);   // acb_kernels.cu: sets the thread-local message behind acb_last_error()
 }
 
+#ifndef ACB_STFT_RPC
+#define ACB_STFT_RPC 16      // rows staged per CTA (upper bound)
+#endif
+
 namespace acb_spectral {
 
 using namespace acb;
@@ -186,7 +190,7 @@ static int launch(const float* x, int64_t rows, int T, int hop, int n_frames, co
     int dev = 0, optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return fail(ACB_ERR_CUDA, "acb_stft_mag: cannot query the device");
-    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, 16384 / T));
+    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(ACB_STFT_RPC, 16384 / T));
     while (rpc > 1 && spectral_smem(R, rpc, T, n_frames).total_bytes > std::min(optin, 160 * 1024)) rpc >>= 1;
     const SpectralSmem L = spectral_smem(R, rpc, T, n_frames);
     if (L.total_bytes > optin)

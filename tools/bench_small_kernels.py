@@ -89,5 +89,21 @@ def main():
          "512 x (384, 128) fp32 latents -> [512, 128, 384] (read + write)")
 
 
+    # VAE-side STFT magnitudes over the mel time axis (models/modeling_vae.py:271-305): a 4x training batch so that the working set exceeds L2
+    from audio_calm_b200 import spectral
+    xs = torch.randn(1024, 80, 256, device="cuda") * 3.0 - 6.0
+    for n_fft, hop in spectral.STFT_LOSS_SPECS:
+        frames = spectral.stft_frames(256, n_fft, hop)
+        o = torch.empty((1024, 80, n_fft // 2 + 1, frames), device="cuda")
+        w = spectral._window(n_fft, xs.device)
+        x2 = xs.reshape(-1, 256)
+        ref_ms = timed(lambda: torch.stft(x2, n_fft=n_fft, hop_length=hop, win_length=n_fft, window=w, return_complex=True, normalized=False,
+                                          center=False).abs())
+        emit(f"stft_mag_kernel (n_fft {n_fft}, hop {hop})",
+             timed(lambda: lib.acb_stft_mag(xs.data_ptr(), 1024 * 80, 256, n_fft, hop, w.data_ptr(), o.data_ptr(), cs())),
+             xs.numel() * 4 + o.numel() * 4, f"[1024, 80, 256] fp32 -> [1024, 80, {n_fft // 2 + 1}, {frames}] magnitudes (read + write); "
+             f"torch.stft + abs on the same device (the reference's _stft_mag, cuFFT): {ref_ms:.4f} ms")
+
+
 if __name__ == "__main__":
     main()

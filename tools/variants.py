@@ -17,6 +17,9 @@ OUT = os.path.join(ROOT, "tools", "_variants")
 
 VARIANTS = {
     "base": [],
+    "rpc4": ["-DACB_STFT_RPC=4"],
+    "rpc8": ["-DACB_STFT_RPC=8"],
+    "rpc32": ["-DACB_STFT_RPC=32"],
     "wnopre": ["-DACBG_PRESCALE=0"],
     "wnochk": ["-DACBG_CHK=0"],
     "wnone": ["-DACBG_CHK=0", "-DACBG_PRESCALE=0"],
@@ -118,7 +121,42 @@ def whisper_one(name, steps=50):
     print(json.dumps({"variant": name, "whisper_ms": e0.elapsed_time(e1) / steps}), flush=True)
 
 
+def stft_one(name, steps=20):
+    import torch
+    import audio_calm_b200 as acb
+    acb._lib.LIB_PATH = os.path.join(OUT, f"lib_{name}.so")
+    from audio_calm_b200 import spectral
+    lib = acb._lib.load()
+    xs = torch.randn(1024, 80, 256, device="cuda") * 3.0 - 6.0
+    res = {"variant": name}
+    for n_fft, hop in spectral.STFT_LOSS_SPECS:
+        frames = spectral.stft_frames(256, n_fft, hop)
+        o = torch.empty((1024, 80, n_fft // 2 + 1, frames), device="cuda")
+        w = spectral._window(n_fft, xs.device)
+        call = lambda: lib.acb_stft_mag(xs.data_ptr(), 1024 * 80, 256, n_fft, hop, w.data_ptr(), o.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            call()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            call()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        res[f"ms_{n_fft}"] = ms
+        res[f"frac_{n_fft}"] = (xs.numel() + o.numel()) * 4 / (ms * 1e-3) / 1e9 / 6537.6
+    print(json.dumps(res), flush=True)
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "stft":
+        for n in sys.argv[2:]:
+            subprocess.run([sys.executable, os.path.abspath(__file__), "stft_one", n], check=False)
+        sys.exit(0)
+    if sys.argv[1] == "stft_one":
+        stft_one(sys.argv[2])
+        sys.exit(0)
     if sys.argv[1] == "whisper":
         for n in sys.argv[2:]:
             subprocess.run([sys.executable, os.path.abspath(__file__), "whisper_one", n], check=False)
