@@ -171,7 +171,7 @@ def run_reference(args) -> None:
     if rank != 0:
         return
     from oracle.ref_torch_port import RefMelExtractor, normalise
-    threads = os.cpu_count() or 1
+    threads = len(os.sched_getaffinity(0)) or os.cpu_count() or 1          # the host cores this process may actually use
     n_clips, length = args.ref_clips, args.seconds * SAMPLE_RATE
     x = synth_batch(n_clips, length, "cpu")
     workers = ReferenceWorkers(x, threads, args.warmup + args.steps)       # forked before this process spins up its own thread pool
@@ -217,6 +217,7 @@ def pin_to_gpu_cpus(local_rank: int, world_local: int):
     info = {"pinned": False}
     try:
         allowed = sorted(os.sched_getaffinity(0))
+        info["original"] = allowed
         cpus = None
         try:
             import pynvml
@@ -491,7 +492,7 @@ def main() -> None:
         e2e = {"value": audio_s_per_step * e2e_steps / dt / 3600.0, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps, "ms_per_step": dt / e2e_steps * 1e3,
                "api": f"LogMelFrontend.forward_host -> acb_logmel_forward_host (pinned host in/out, {n_chunks} chunks, 3 streams)",
-               "cpu_affinity": affinity}
+               "cpu_affinity": {k: v for k, v in affinity.items() if k != "original"}}
         # copy-only control: the same chunked copies without the kernel (per rank, all ranks at once) -> the platform's ceiling
         barrier()
         ctl = copy_only_control(x_host, out_host, staging[0], staging[1], n_chunks, e2e_steps, device)
@@ -564,9 +565,10 @@ def main() -> None:
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         # a bounded sample of the reference arm (3 steps of the same 256-clip batch) in a process that never touched CUDA
         try:
+            everything = set(affinity.get("original") or os.sched_getaffinity(0))     # the CPU arm gets every host core back, not this rank's slice
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3", "--warmup", "1",
                                 "--seconds", str(args.seconds), "--ref-clips", str(args.ref_clips), "--cpu-seconds", str(args.cpu_seconds)],
-                               capture_output=True, text=True, timeout=600)
+                               capture_output=True, text=True, timeout=600, preexec_fn=lambda: os.sched_setaffinity(0, everything))
             cpu = json.loads(r.stdout.strip().splitlines()[-1])["cpu_baseline"]
             cpu["sample"] += " x 3 steps"
         except Exception as e:  # noqa: BLE001
