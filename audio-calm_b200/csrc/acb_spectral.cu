@@ -63,6 +63,35 @@ __device__ __forceinline__ void small_fft(float2 (&v)[R]) {
     }
 }
 
+// The complex FFT of N = 32 R points that a group of R lanes computes together.  Stage 1: the lane's 32 stride-R inputs (packed,
+// bit-reversed order: see fft32_packed) -> in-register FFT-32, twiddle W_N^(r k1), hand-over to the group's exchange buffer at index
+// k1 + 33 r.  Stage 2 (after a __syncwarp): an R-point FFT across the group's lanes, in place; Z[k1 + 32 k2] ends up at index k1 + 33 k2.
+template <int R>
+__device__ __forceinline__ void group_fft_stage1(float2 (&pr)[16], float2 (&pi)[16], float2* buf, const float2* s_tw, int r) {
+    fft32_packed(pr, pi);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const float2 t0 = s_tw[r * k], t1 = s_tw[r * (k + 16)];
+        buf[k + 33 * r] = make_float2(fmaf(pr[k].x, t0.x, -pi[k].x * t0.y), fmaf(pr[k].x, t0.y, pi[k].x * t0.x));
+        buf[k + 16 + 33 * r] = make_float2(fmaf(pr[k].y, t1.x, -pi[k].y * t1.y), fmaf(pr[k].y, t1.y, pi[k].y * t1.x));
+    }
+}
+template <int R>
+__device__ __forceinline__ void group_fft_stage2(float2* buf, int r) {
+    constexpr int kPerLane = 32 / R;
+#pragma unroll
+    for (int t = 0; t < kPerLane; ++t) {
+        const int k1 = r * kPerLane + t;
+        float2 v[R];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) v[rr] = buf[k1 + 33 * rr];
+        small_fft<R>(v);
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) buf[k1 + 33 * rr] = v[rr];
+    }
+}
+__device__ __forceinline__ int buf_index(int k) { return (k & 31) + 33 * (k >> 5); }
+
 struct SpectralSmem {
     int x, win, tw, buf, out, total_bytes;
 };
@@ -137,27 +166,10 @@ __global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restr
                 pr[q] = make_float2(pa[n0] * w0, pa[n1] * w1);
                 pi[q] = valid_b ? make_float2(pb[n0] * w0, pb[n1] * w1) : make_float2(0.f, 0.f);
             }
-            fft32_packed(pr, pi);                       // over the lane's stride-R samples -> k1 (natural order)
-#pragma unroll
-            for (int k = 0; k < 16; ++k) {              // twiddle W_N^(r k1) and hand over: index k1 + 33 * r
-                const float2 t0 = s_tw[r * k], t1 = s_tw[r * (k + 16)];
-                buf[k + 33 * r] = make_float2(fmaf(pr[k].x, t0.x, -pi[k].x * t0.y), fmaf(pr[k].x, t0.y, pi[k].x * t0.x));
-                buf[k + 16 + 33 * r] = make_float2(fmaf(pr[k].y, t1.x, -pi[k].y * t1.y), fmaf(pr[k].y, t1.y, pi[k].y * t1.x));
-            }
+            group_fft_stage1<R>(pr, pi, buf, s_tw, r);
         }
         __syncwarp();
-        if (valid) {                                    // R-point FFT across the group's lanes, in place: Z[k1 + 32 k2] at index k1 + 33 k2
-#pragma unroll
-            for (int t = 0; t < kPerLane; ++t) {
-                const int k1 = r * kPerLane + t;
-                float2 v[R];
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) v[rr] = buf[k1 + 33 * rr];
-                small_fft<R>(v);
-#pragma unroll
-                for (int rr = 0; rr < R; ++rr) buf[k1 + 33 * rr] = v[rr];
-            }
-        }
+        if (valid) group_fft_stage2<R>(buf, r);
         __syncwarp();
         if (valid) {                                    // separate the two real spectra, magnitudes
             float* oa = s_out + (size_t)row_a * kFreq * n_frames + fa;
@@ -204,6 +216,154 @@ static int launch(const float* x, int64_t rows, int T, int hop, int n_frames, co
     return ACB_OK;
 }
 
+// Backward of stft_mag: grad_x[row][n] = sum over the frames that cover n of w * Re( sum_k g[k] conj(X[k] / |X[k]|) e^(-2 pi i k n' / N) ).
+// Per pair of frames: the forward transform again (X is not kept), then ONE more complex FFT of the same size: the one-sided
+// sums of both frames are the real and the imaginary part of the transform of H_A + i H_B, where H is the Hermitian extension of
+// h[k] = g[k] conj(X[k]) / |X[k]| (a bin with |X| = 0 passes no gradient, like torch's abs).  The windowed results are accumulated
+// in a shared-memory copy of the rows' gradients (frames overlap: shared-memory atomics) and written out once.
+struct SpectralBwdSmem {
+    int x, gx, g, win, tw, buf, total_bytes;
+};
+__host__ __device__ inline SpectralBwdSmem spectral_bwd_smem(int R, int rows_per_cta, int T, int n_frames) {
+    const int N = 32 * R, n_freq = N / 2 + 1;
+    SpectralBwdSmem L;
+    int off = 0;
+    L.x = off; off += (rows_per_cta * T + 3) & ~3;
+    L.gx = off; off += (rows_per_cta * T + 3) & ~3;
+    L.g = off; off += (rows_per_cta * n_freq * n_frames + 3) & ~3;
+    L.win = off; off += N;
+    L.tw = off; off += 2 * N;
+    L.buf = off; off += (kThreads / R) * (2 * 33 * R);
+    L.total_bytes = off * 4;
+    return L;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads) stft_mag_backward_kernel(const float* __restrict__ x, const float* __restrict__ grad_mag, long long rows, int T,
+                                                                     int hop, int n_frames, const float* __restrict__ window,
+                                                                     float* __restrict__ grad_x, int rows_per_cta) {
+    constexpr int N = 32 * R, kFreq = N / 2 + 1, kGroups = kThreads / R;
+    extern __shared__ __align__(16) float smem[];
+    const SpectralBwdSmem L = spectral_bwd_smem(R, rows_per_cta, T, n_frames);
+    float* s_x = smem + L.x;
+    float* s_gx = smem + L.gx;
+    float* s_g = smem + L.g;
+    float* s_win = smem + L.win;
+    float2* s_tw = reinterpret_cast<float2*>(smem + L.tw);
+    const int tid = threadIdx.x;
+    const long long row0 = (long long)blockIdx.x * rows_per_cta;
+    const int n_rows = (int)min((long long)rows_per_cta, rows - row0);
+    for (int i = tid; i < n_rows * T; i += kThreads) { s_x[i] = x[row0 * T + i]; s_gx[i] = 0.f; }
+    for (int i = tid; i < n_rows * kFreq * n_frames; i += kThreads) s_g[i] = grad_mag[row0 * kFreq * n_frames + i];
+    for (int i = tid; i < N; i += kThreads) {
+        s_win[i] = window[i];
+        float sn, cs;
+        sincospif(2.f * (float)i / (float)N, &sn, &cs);
+        s_tw[i] = make_float2(cs, -sn);
+    }
+    __syncthreads();
+
+    const int g = tid / R, r = tid % R;
+    float2* buf = reinterpret_cast<float2*>(smem + L.buf) + g * (33 * R);
+    const int total_frames = n_rows * n_frames;
+    const int n_items = (total_frames + 1) / 2;
+    const int n_iter = (n_items + kGroups - 1) / kGroups;
+    for (int it = 0; it < n_iter; ++it) {
+        const int item = it * kGroups + g;
+        const bool valid = item < n_items;
+        const int qa = 2 * item, qb = qa + 1;
+        const bool valid_b = valid && qb < total_frames;
+        const int row_a = valid ? qa / n_frames : 0, fa = valid ? qa - row_a * n_frames : 0;
+        const int row_b = valid_b ? qb / n_frames : 0, fb = valid_b ? qb - row_b * n_frames : 0;
+        float2 pr[16], pi[16];
+        if (valid) {                                    // forward transform of the pair, as in stft_mag_kernel
+            const float* pa = s_x + row_a * T + fa * hop;
+            const float* pb = s_x + row_b * T + fb * hop;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int j0 = brev5(q);
+                const int n0 = R * j0 + r, n1 = R * (j0 + 1) + r;
+                const float w0 = s_win[n0], w1 = s_win[n1];
+                pr[q] = make_float2(pa[n0] * w0, pa[n1] * w1);
+                pi[q] = valid_b ? make_float2(pb[n0] * w0, pb[n1] * w1) : make_float2(0.f, 0.f);
+            }
+            group_fft_stage1<R>(pr, pi, buf, s_tw, r);
+        }
+        __syncwarp();
+        if (valid) group_fft_stage2<R>(buf, r);
+        __syncwarp();
+        if (valid) {                                    // h = g conj(X) / |X| per frame; C = H_A + i H_B written over Z in place
+            const float* ga = s_g + (size_t)row_a * kFreq * n_frames + fa;
+            const float* gb = s_g + (size_t)row_b * kFreq * n_frames + fb;
+            for (int k = r; k < kFreq; k += R) {
+                const int kc = (N - k) & (N - 1);
+                const float2 z = buf[buf_index(k)], zc = buf[buf_index(kc)];
+                const float xar = 0.5f * (z.x + zc.x), xai = 0.5f * (z.y - zc.y);          // X_A[k]
+                const float xbr = 0.5f * (z.y + zc.y), xbi = -0.5f * (z.x - zc.x);         // X_B[k]
+                const float ma = sqrtf(fmaf(xar, xar, xai * xai)), mb = sqrtf(fmaf(xbr, xbr, xbi * xbi));
+                const float sa = ma > 0.f ? ga[(size_t)k * n_frames] / ma : 0.f;
+                const float sb = (valid_b && mb > 0.f) ? gb[(size_t)k * n_frames] / mb : 0.f;
+                const float har = sa * xar, hai = -sa * xai;                                // h_A = g conj(X_A) / |X_A|
+                const float hbr = sb * xbr, hbi = -sb * xbi;
+                if (k == 0 || 2 * k == N) {
+                    buf[buf_index(k)] = make_float2(har, hbr);                              // Re h_A + i Re h_B
+                } else {
+                    buf[buf_index(k)] = make_float2(0.5f * (har - hbi), 0.5f * (hai + hbr));        // (h_A + i h_B) / 2
+                    buf[buf_index(kc)] = make_float2(0.5f * (har + hbi), 0.5f * (-hai + hbr));      // (conj h_A + i conj h_B) / 2
+                }
+            }
+        }
+        __syncwarp();
+        if (valid) {                                    // second transform: the lane gathers its stride-R inputs from the buffer
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int j0 = brev5(q);
+                const float2 c0 = buf[buf_index(R * j0 + r)], c1 = buf[buf_index(R * (j0 + 1) + r)];
+                pr[q] = make_float2(c0.x, c1.x);
+                pi[q] = make_float2(c0.y, c1.y);
+            }
+        }
+        __syncwarp();
+        if (valid) group_fft_stage1<R>(pr, pi, buf, s_tw, r);
+        __syncwarp();
+        if (valid) group_fft_stage2<R>(buf, r);
+        __syncwarp();
+        if (valid) {                                    // windowed overlap-add into the rows' gradients
+            float* da = s_gx + row_a * T + fa * hop;
+            float* db = s_gx + row_b * T + fb * hop;
+            for (int n = r; n < N; n += R) {
+                const float2 y = buf[buf_index(n)];
+                const float w = s_win[n];
+                atomicAdd(da + n, w * y.x);
+                if (valid_b) atomicAdd(db + n, w * y.y);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int i = tid; i < n_rows * T; i += kThreads) grad_x[row0 * T + i] = s_gx[i];
+}
+
+template <int R>
+static int launch_backward(const float* x, const float* grad_mag, int64_t rows, int T, int hop, int n_frames, const float* window, float* grad_x,
+                           cudaStream_t st) {
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return fail(ACB_ERR_CUDA, "acb_stft_mag_backward: cannot query the device");
+    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(ACB_STFT_RPC, 16384 / T));
+    while (rpc > 1 && spectral_bwd_smem(R, rpc, T, n_frames).total_bytes > std::min(optin, 160 * 1024)) rpc >>= 1;
+    const SpectralBwdSmem L = spectral_bwd_smem(R, rpc, T, n_frames);
+    if (L.total_bytes > optin)
+        return fail(ACB_ERR_UNSUPPORTED, "acb_stft_mag_backward: a row of " + std::to_string(T) + " frames does not fit in shared memory");
+    cudaError_t e = cudaFuncSetAttribute(stft_mag_backward_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) return fail(ACB_ERR_CUDA, std::string("acb_stft_mag_backward: ") + cudaGetErrorString(e));
+    const unsigned grid = (unsigned)((rows + rpc - 1) / rpc);
+    stft_mag_backward_kernel<R><<<grid, kThreads, L.total_bytes, st>>>(x, grad_mag, rows, T, hop, n_frames, window, grad_x, rpc);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ACB_ERR_CUDA, std::string("acb_stft_mag_backward launch: ") + cudaGetErrorString(e));
+    return ACB_OK;
+}
+
 }  // namespace acb_spectral
 
 extern "C" {
@@ -232,6 +392,26 @@ int acb_stft_mag(const float* x, int64_t rows, int64_t length, int n_fft, int ho
         case 1024: return launch<32>(x, rows, (int)length, hop, n_frames, window, out, st);
         default:
             return fail(ACB_ERR_UNSUPPORTED, "acb_stft_mag: n_fft must be 64, 128, 256, 512 or 1024 (got " + std::to_string(n_fft) + ")");
+    }
+}
+
+int acb_stft_mag_backward(const float* x, const float* grad_mag, int64_t rows, int64_t length, int n_fft, int hop, const float* window,
+                          float* grad_x, void* stream) {
+    using namespace acb_spectral;
+    if (rows <= 0) return ACB_OK;
+    if (!x || !grad_mag || !window || !grad_x) return fail(ACB_ERR_INVALID, "acb_stft_mag_backward: null argument");
+    if (hop < 1 || length < n_fft) return fail(ACB_ERR_INVALID, "acb_stft_mag_backward: bad hop / length");
+    if (length > (1 << 24) || rows > ((int64_t)1 << 40)) return fail(ACB_ERR_UNSUPPORTED, "acb_stft_mag_backward: input too large");
+    const int n_frames = (int)acb_stft_mag_frames(length, n_fft, hop);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    switch (n_fft) {
+        case 64: return launch_backward<2>(x, grad_mag, rows, (int)length, hop, n_frames, window, grad_x, st);
+        case 128: return launch_backward<4>(x, grad_mag, rows, (int)length, hop, n_frames, window, grad_x, st);
+        case 256: return launch_backward<8>(x, grad_mag, rows, (int)length, hop, n_frames, window, grad_x, st);
+        case 512: return launch_backward<16>(x, grad_mag, rows, (int)length, hop, n_frames, window, grad_x, st);
+        case 1024: return launch_backward<32>(x, grad_mag, rows, (int)length, hop, n_frames, window, grad_x, st);
+        default:
+            return fail(ACB_ERR_UNSUPPORTED, "acb_stft_mag_backward: n_fft must be 64, 128, 256, 512 or 1024 (got " + std::to_string(n_fft) + ")");
     }
 }
 

@@ -6,7 +6,9 @@ center=False, normalized=False)`` followed by ``torch.abs`` -- as one launch of 
 window multiply, a cuFFT call and an ``abs`` pass.  ``multires_stft_mags`` and ``stft_loss`` follow ``stft_loss`` (``:291-305``):
 the resolutions ``(256, 64), (128, 32), (64, 16)`` that fit the sequence, L1 distance of the magnitudes, averaged.
 
-Forward only: the loss value is what evaluation needs; training through it (autograd) is not wired yet.
+Differentiable: ``stft_mag`` is a ``torch.autograd.Function`` whose backward is the adjoint kernel ``acb_stft_mag_backward`` (the
+transform is recomputed, the one-sided sums of two frames come out of one more complex FFT), so ``stft_loss`` can replace the
+reference's method in ``AcousticVAE.forward`` for training as well as for evaluation.
 """
 from __future__ import annotations
 
@@ -39,9 +41,41 @@ def stft_frames(length: int, n_fft: int, hop_length: int) -> int:
     return 1 + (length - n_fft) // hop_length
 
 
+class _StftMag(torch.autograd.Function):
+    """rows ``[R, T]`` float32 -> ``[R, n_fft // 2 + 1, frames]``; backward through ``acb_stft_mag_backward``."""
+
+    @staticmethod
+    def forward(ctx, x2: torch.Tensor, n_fft: int, hop: int) -> torch.Tensor:
+        rows, T = int(x2.shape[0]), int(x2.shape[1])
+        frames = stft_frames(T, n_fft, hop)
+        out = torch.empty((rows, n_fft // 2 + 1, frames), dtype=torch.float32, device=x2.device)
+        if rows:
+            lib = _lib.load()
+            with torch.cuda.device(x2.device):
+                _lib.check(lib.acb_stft_mag(x2.data_ptr(), rows, T, int(n_fft), int(hop), _window(n_fft, x2.device).data_ptr(),
+                                            out.data_ptr(), torch.cuda.current_stream(x2.device).cuda_stream), "acb_stft_mag")
+        ctx.save_for_backward(x2)
+        ctx.n_fft, ctx.hop = int(n_fft), int(hop)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out: torch.Tensor):
+        (x2,) = ctx.saved_tensors
+        rows, T = int(x2.shape[0]), int(x2.shape[1])
+        grad_x = torch.empty_like(x2)
+        if rows:
+            g = grad_out.to(torch.float32).contiguous()
+            lib = _lib.load()
+            with torch.cuda.device(x2.device):
+                _lib.check(lib.acb_stft_mag_backward(x2.data_ptr(), g.data_ptr(), rows, T, ctx.n_fft, ctx.hop,
+                                                     _window(ctx.n_fft, x2.device).data_ptr(), grad_x.data_ptr(),
+                                                     torch.cuda.current_stream(x2.device).cuda_stream), "acb_stft_mag_backward")
+        return grad_x, None, None
+
+
 def stft_mag(x: torch.Tensor, n_fft: int = 1024, hop_length: int = 256, win_length: Optional[int] = None) -> torch.Tensor:
     """``x[B, C, T]`` (device; any float dtype, computed in float32 like the reference's ``.float()``) ->
-    ``[B, C, n_fft // 2 + 1, frames]`` float32 magnitudes."""
+    ``[B, C, n_fft // 2 + 1, frames]`` float32 magnitudes.  Differentiable with respect to ``x``."""
     if x.dim() != 3:
         raise ValueError("stft_mag expects [B, C, T]")
     if not x.is_cuda:
@@ -51,15 +85,10 @@ def stft_mag(x: torch.Tensor, n_fft: int = 1024, hop_length: int = 256, win_leng
     if n_fft not in SUPPORTED_N_FFT:
         raise NotImplementedError(f"stft_mag: n_fft must be one of {SUPPORTED_N_FFT}")
     B, C, T = (int(v) for v in x.shape)
-    frames = stft_frames(T, n_fft, hop_length)
+    stft_frames(T, n_fft, hop_length)                        # raises like torch.stft when T < n_fft
     x2 = x.reshape(B * C, T).float().contiguous()
-    out = torch.empty((B, C, n_fft // 2 + 1, frames), dtype=torch.float32, device=x.device)
-    if B * C:
-        lib = _lib.load()
-        with torch.cuda.device(x.device):
-            _lib.check(lib.acb_stft_mag(x2.data_ptr(), B * C, T, int(n_fft), int(hop_length), _window(n_fft, x.device).data_ptr(),
-                                        out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream), "acb_stft_mag")
-    return out
+    out = _StftMag.apply(x2, int(n_fft), int(hop_length))
+    return out.view(B, C, n_fft // 2 + 1, out.shape[-1])
 
 
 def multires_stft_mags(x: torch.Tensor) -> List[torch.Tensor]:

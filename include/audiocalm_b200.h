@@ -267,6 +267,11 @@ int acb_dftgemm_check(const acb_dftgemm* fe, void* stream);
  * n_fft in {64, 128, 256, 512, 1024}; length < n_fft returns ACB_ERR_INVALID (torch.stft raises for center=False). */
 int64_t acb_stft_mag_frames(int64_t length, int n_fft, int hop);
 int acb_stft_mag(const float* x, int64_t rows, int64_t length, int n_fft, int hop, const float* window, float* out, void* stream);
+/* Its adjoint (what autograd computes through torch.stft + abs in stft_loss, models/modeling_vae.py:291-305): given grad_mag (device
+ * [rows][n_fft / 2 + 1][frames]) writes grad_x (device [rows][length]).  X is recomputed, not stored; a bin with |X| = 0 passes no
+ * gradient (torch's abs does the same). */
+int acb_stft_mag_backward(const float* x, const float* grad_mag, int64_t rows, int64_t length, int n_fft, int hop, const float* window,
+                          float* grad_x, void* stream);
 
 #ifdef __cplusplus
 }
