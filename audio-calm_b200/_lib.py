@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "acb_logmel_forward", "acb_frontend_check", "acb_frontend_set_kernel", "acb_peak_abs", "acb_process_audio_chunk", "acb_mixdown_peak", "acb_moments_accumulate",
     "acb_moments_finalize", "acb_normalize_per_utterance", "acb_logmel_forward_host", "acb_crop_pad", "acb_pad_transpose",
     "acb_moments_accumulate_workspace_bytes", "acb_pcm16_to_float", "acb_logmel_forward_host_pcm16",
-    "acb_stft_mag_frames", "acb_stft_mag", "acb_stft_mag_backward",
+    "acb_stft_mag_frames", "acb_stft_mag", "acb_stft_mag_backward", "acb_stft_complex", "acb_istft",
     "acb_dftgemm_frames", "acb_dftgemm_workspace_ints", "acb_dftgemm_create", "acb_dftgemm_destroy", "acb_dftgemm_forward", "acb_dftgemm_check", "acb_dftgemm_moments_workspace_bytes",
 ]
 
@@ -209,6 +209,10 @@ def load() -> ctypes.CDLL:
         lib.acb_stft_mag.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.c_int, vp, vp, vp]
         lib.acb_stft_mag_backward.restype = ctypes.c_int
         lib.acb_stft_mag_backward.argtypes = [vp, vp, i64, i64, ctypes.c_int, ctypes.c_int, vp, vp, vp]
+        lib.acb_stft_complex.restype = ctypes.c_int
+        lib.acb_stft_complex.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, f32, vp]
+        lib.acb_istft.restype = ctypes.c_int
+        lib.acb_istft.argtypes = [vp, i64, i64, ctypes.c_int, ctypes.c_int, vp, vp, i64, vp]
         lib.acb_dftgemm_frames.restype = i64
         lib.acb_dftgemm_frames.argtypes = [i64, ctypes.c_int]
         lib.acb_dftgemm_workspace_ints.restype = i64

@@ -2125,7 +2125,8 @@ int acb_pcm16_to_float(const int16_t* pcm, float* out, int64_t n, void* stream) 
 // dev_pcm and widened on the device (half the bytes over PCIe).
 static int forward_host_impl(const acb_frontend* fe_c, const void* wav_host, int32_t n_clips, int64_t length, void* out_host,
                              acb_logmel_args* tmpl, int16_t* dev_pcm, float* dev_in, void* dev_out, int32_t n_chunks, void* stream) {
-    if (!fe_c || !wav_host || !out_host || !tmpl || !dev_in || !dev_out) return fail(ACB_ERR_INVALID, "acb_logmel_forward_host: null argument");
+    // out_host may be NULL: the features stay in dev_out (a training feed consumes them on the device; no D2H at all)
+    if (!fe_c || !wav_host || !tmpl || !dev_in || !dev_out) return fail(ACB_ERR_INVALID, "acb_logmel_forward_host: null argument");
     if (n_clips <= 0) return ACB_OK;
     auto* fe = const_cast<acb_frontend*>(fe_c);
     const int64_t T = acb_frames_for_length(length, fe->n_fft, fe->hop);
@@ -2183,6 +2184,7 @@ static int forward_host_impl(const acb_frontend* fe_c, const void* wav_host, int
         if (a.clip_peak) a.clip_peak = tmpl->clip_peak + c0;
         rc = acb_logmel_forward(fe, &a, st);
         if (rc != ACB_OK) break;
+        if (!out_host) continue;
         ACB_TRY(cudaEventRecord(fe->ev[2 * c + 1], st));
         ACB_TRY(cudaStreamWaitEvent(fe->s_out, fe->ev[2 * c + 1], 0));
         ACB_TRY(cudaMemcpyAsync(static_cast<unsigned char*>(out_host) + (size_t)c0 * out_clip * esz,

@@ -364,6 +364,243 @@ static int launch_backward(const float* x, const float* grad_mag, int64_t rows, 
     return ACB_OK;
 }
 
+// --------------------------------------------------------------------------------------------
+// Griffin-Lim building blocks (the vocoder fallback of eval/eval_calm.py:184-208 -> torchaudio GriffinLim(n_fft=1024)):
+// a complex STFT with centred, reflect-padded frames (torch.stft center=True) whose epilogue can apply the phase update of one
+// Griffin-Lim iteration, an inverse STFT (torch.istft: inverse transform, window, overlap-add, division by the window envelope,
+// centre trimmed), both on the same group FFT; long rows are cut into chunks of frames per CTA.
+// --------------------------------------------------------------------------------------------
+struct ChunkSmem {
+    int x, spec, win, tw, buf, total_bytes;
+};
+__host__ __device__ inline ChunkSmem chunk_smem(int R, int frames_per_cta, int hop, bool with_spec) {
+    const int N = 32 * R, n_freq = N / 2 + 1;
+    ChunkSmem L;
+    int off = 0;
+    L.x = off; off += with_spec ? 0 : (((frames_per_cta - 1) * hop + N + 3) & ~3);
+    L.spec = off; off += with_spec ? 2 * n_freq * frames_per_cta : 0;
+    L.win = off; off += N;
+    L.tw = off; off += 2 * N;
+    L.buf = off; off += (kThreads / R) * (2 * 33 * R);
+    L.total_bytes = off * 4;
+    return L;
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads) stft_complex_kernel(const float* __restrict__ x, long long length, int hop, int n_frames,
+                                                                const float* __restrict__ window, float2* __restrict__ spec_out,
+                                                                float2* __restrict__ tprev, const float* __restrict__ mag, float momentum,
+                                                                int frames_per_cta) {
+    constexpr int N = 32 * R, kFreq = N / 2 + 1, kGroups = kThreads / R;
+    extern __shared__ __align__(16) float smem[];
+    const ChunkSmem L = chunk_smem(R, frames_per_cta, hop, false);
+    float* s_x = smem + L.x;
+    float* s_win = smem + L.win;
+    float2* s_tw = reinterpret_cast<float2*>(smem + L.tw);
+    const int tid = threadIdx.x;
+    const long long row = blockIdx.y;
+    const int t0 = blockIdx.x * frames_per_cta, n_loc = min(frames_per_cta, n_frames - t0);
+    const float* src = x + row * length;
+    {   // the chunk's samples with torch.stft's centred reflect padding
+        const long long g0 = (long long)t0 * hop - N / 2;
+        const int n = (n_loc - 1) * hop + N;
+        for (int i = tid; i < n; i += kThreads) {
+            long long idx = g0 + i;
+            if (idx < 0) idx = -idx;
+            if (idx >= length) idx = 2 * (length - 1) - idx;
+            s_x[i] = (idx >= 0 && idx < length) ? __ldg(src + idx) : 0.f;
+        }
+        for (int i = tid; i < N; i += kThreads) {
+            s_win[i] = window[i];
+            float sn, cs;
+            sincospif(2.f * (float)i / (float)N, &sn, &cs);
+            s_tw[i] = make_float2(cs, -sn);
+        }
+    }
+    __syncthreads();
+    const int g = tid / R, r = tid % R;
+    float2* buf = reinterpret_cast<float2*>(smem + L.buf) + g * (33 * R);
+    const int n_items = (n_loc + 1) / 2, n_iter = (n_items + kGroups - 1) / kGroups;
+    for (int it = 0; it < n_iter; ++it) {
+        const int item = it * kGroups + g;
+        const bool valid = item < n_items;
+        const int fa = 2 * item, fb = fa + 1;
+        const bool valid_b = valid && fb < n_loc;
+        if (valid) {
+            const float* pa = s_x + fa * hop;
+            const float* pb = s_x + (valid_b ? fb : fa) * hop;
+            float2 pr[16], pi[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int j0 = brev5(q);
+                const int n0 = R * j0 + r, n1 = R * (j0 + 1) + r;
+                const float w0 = s_win[n0], w1 = s_win[n1];
+                pr[q] = make_float2(pa[n0] * w0, pa[n1] * w1);
+                pi[q] = valid_b ? make_float2(pb[n0] * w0, pb[n1] * w1) : make_float2(0.f, 0.f);
+            }
+            group_fft_stage1<R>(pr, pi, buf, s_tw, r);
+        }
+        __syncwarp();
+        if (valid) group_fft_stage2<R>(buf, r);
+        __syncwarp();
+        if (valid) {
+            for (int k = r; k < kFreq; k += R) {
+                const int kc = (N - k) & (N - 1);
+                const float2 z = buf[buf_index(k)], zc = buf[buf_index(kc)];
+                float2 xs[2] = {make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y)), make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x))};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h == 1 && !valid_b) break;
+                    const size_t o = ((size_t)row * kFreq + k) * n_frames + t0 + fa + h;
+                    float2 v = xs[h];
+                    if (mag != nullptr) {      // one Griffin-Lim phase update: angles = (rebuilt - m * previous) / (|.| + 1e-16); out = angles * magnitude
+                        const float2 prev = tprev[o];
+                        tprev[o] = v;
+                        float ar = fmaf(-momentum, prev.x, v.x), ai = fmaf(-momentum, prev.y, v.y);
+                        const float inv = 1.f / (sqrtf(fmaf(ar, ar, ai * ai)) + 1e-16f);
+                        const float m = mag[o];
+                        v = make_float2(ar * inv * m, ai * inv * m);
+                    }
+                    spec_out[o] = v;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int R>
+__global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restrict__ spec, int n_frames, int hop, const float* __restrict__ window,
+                                                         float* __restrict__ out, long long length, int frames_per_cta) {
+    constexpr int N = 32 * R, kFreq = N / 2 + 1, kGroups = kThreads / R;
+    extern __shared__ __align__(16) float smem[];
+    const ChunkSmem L = chunk_smem(R, frames_per_cta, hop, true);
+    float2* s_spec = reinterpret_cast<float2*>(smem + L.spec);      // [k][frame of the chunk]
+    float* s_win = smem + L.win;
+    float2* s_tw = reinterpret_cast<float2*>(smem + L.tw);
+    const int tid = threadIdx.x;
+    const long long row = blockIdx.y;
+    const int t0 = blockIdx.x * frames_per_cta, n_loc = min(frames_per_cta, n_frames - t0);
+    for (int i = tid; i < kFreq * frames_per_cta; i += kThreads) {
+        const int k = i / frames_per_cta, t = i - k * frames_per_cta;
+        s_spec[i] = t < n_loc ? spec[((size_t)row * kFreq + k) * n_frames + t0 + t] : make_float2(0.f, 0.f);
+    }
+    for (int i = tid; i < N; i += kThreads) {
+        s_win[i] = window[i];
+        float sn, cs;
+        sincospif(2.f * (float)i / (float)N, &sn, &cs);
+        s_tw[i] = make_float2(cs, -sn);
+    }
+    __syncthreads();
+    const int g = tid / R, r = tid % R;
+    float2* buf = reinterpret_cast<float2*>(smem + L.buf) + g * (33 * R);
+    float* dst = out + row * length;
+    const float inv_n = 1.f / (float)N;
+    const int n_items = (n_loc + 1) / 2, n_iter = (n_items + kGroups - 1) / kGroups;
+    for (int it = 0; it < n_iter; ++it) {
+        const int item = it * kGroups + g;
+        const bool valid = item < n_items;
+        const int fa = 2 * item, fb = fa + 1;
+        const bool valid_b = valid && fb < n_loc;
+        if (valid) {
+            // y_A + i y_B = IFFT(X_A + i X_B) = conj(FFT(conj(D))) / N with D the Hermitian extension of both one-sided spectra
+            for (int k = r; k < kFreq; k += R) {
+                const float2 a = s_spec[k * frames_per_cta + fa];
+                const float2 b = valid_b ? s_spec[k * frames_per_cta + fb] : make_float2(0.f, 0.f);
+                if (k == 0 || 2 * k == N) {
+                    buf[buf_index(k)] = make_float2(a.x, -b.x);                  // irfft ignores the imaginary part of DC / Nyquist
+                } else {
+                    buf[buf_index(k)] = make_float2(a.x - b.y, -(a.y + b.x));
+                    buf[buf_index(N - k)] = make_float2(a.x + b.y, a.y - b.x);
+                }
+            }
+        }
+        __syncwarp();
+        float2 pr[16], pi[16];
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int j0 = brev5(q);
+                const float2 c0 = buf[buf_index(R * j0 + r)], c1 = buf[buf_index(R * (j0 + 1) + r)];
+                pr[q] = make_float2(c0.x, c1.x);
+                pi[q] = make_float2(c0.y, c1.y);
+            }
+        }
+        __syncwarp();
+        if (valid) group_fft_stage1<R>(pr, pi, buf, s_tw, r);
+        __syncwarp();
+        if (valid) group_fft_stage2<R>(buf, r);
+        __syncwarp();
+        if (valid) {                                    // window, overlap-add, centre trimmed (torch.istft center=True)
+            for (int n = r; n < N; n += R) {
+                const float2 y = buf[buf_index(n)];
+                const float w = s_win[n] * inv_n;
+                const long long pa = (long long)(t0 + fa) * hop + n - N / 2, pb = pa + hop;
+                if (pa >= 0 && pa < length) atomicAdd(dst + pa, w * y.x);
+                if (valid_b && pb >= 0 && pb < length) atomicAdd(dst + pb, -w * y.y);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// division by the window envelope sum_t w^2[i + N/2 - t hop] (torch.istft; positions whose envelope is below 1e-11 are left as they are)
+__global__ void __launch_bounds__(256) istft_normalize_kernel(float* __restrict__ out, long long rows, long long length, int n_fft, int hop, int n_frames,
+                                                              const float* __restrict__ window) {
+    const long long total = rows * length;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long pos = i % length + n_fft / 2;
+        const long long t_hi = min((long long)n_frames - 1, pos / hop);
+        const long long t_lo = max(0LL, (pos - n_fft + hop) / hop);
+        float env = 0.f;
+        for (long long t = t_lo; t <= t_hi; ++t) {
+            const long long n = pos - t * hop;
+            if (n >= 0 && n < n_fft) { const float w = __ldg(window + n); env = fmaf(w, w, env); }
+        }
+        if (env > 1e-11f) out[i] = out[i] / env;
+    }
+}
+
+template <int R>
+static int launch_stft_complex(const float* x, int64_t rows, int64_t length, int hop, int n_frames, const float* window, float2* spec, float2* tprev,
+                               const float* mag, float momentum, cudaStream_t st) {
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return fail(ACB_ERR_CUDA, "acb_stft_complex: cannot query the device");
+    int fpc = 16;
+    while (fpc > 2 && chunk_smem(R, fpc, hop, false).total_bytes > std::min(optin, 128 * 1024)) fpc >>= 1;
+    const ChunkSmem L = chunk_smem(R, fpc, hop, false);
+    if (L.total_bytes > optin) return fail(ACB_ERR_UNSUPPORTED, "acb_stft_complex: hop too large for shared memory");
+    cudaError_t e = cudaFuncSetAttribute(stft_complex_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) return fail(ACB_ERR_CUDA, std::string("acb_stft_complex: ") + cudaGetErrorString(e));
+    const dim3 grid((unsigned)((n_frames + fpc - 1) / fpc), (unsigned)rows);
+    stft_complex_kernel<R><<<grid, kThreads, L.total_bytes, st>>>(x, length, hop, n_frames, window, spec, tprev, mag, momentum, fpc);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ACB_ERR_CUDA, std::string("acb_stft_complex launch: ") + cudaGetErrorString(e));
+    return ACB_OK;
+}
+
+template <int R>
+static int launch_istft(const float2* spec, int64_t rows, int n_frames, int hop, const float* window, float* out, int64_t length, cudaStream_t st) {
+    int dev = 0, optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return fail(ACB_ERR_CUDA, "acb_istft: cannot query the device");
+    int fpc = 16;
+    while (fpc > 2 && chunk_smem(R, fpc, hop, true).total_bytes > std::min(optin, 128 * 1024)) fpc >>= 1;
+    const ChunkSmem L = chunk_smem(R, fpc, hop, true);
+    if (L.total_bytes > optin) return fail(ACB_ERR_UNSUPPORTED, "acb_istft: transform too large for shared memory");
+    cudaError_t e = cudaFuncSetAttribute(istft_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaMemsetAsync(out, 0, sizeof(float) * (size_t)rows * (size_t)length, st);
+    if (e != cudaSuccess) return fail(ACB_ERR_CUDA, std::string("acb_istft: ") + cudaGetErrorString(e));
+    const dim3 grid((unsigned)((n_frames + fpc - 1) / fpc), (unsigned)rows);
+    istft_kernel<R><<<grid, kThreads, L.total_bytes, st>>>(spec, n_frames, hop, window, out, length, fpc);
+    const long long total = (long long)rows * length;
+    istft_normalize_kernel<<<(unsigned)std::min<long long>(4096, (total + 255) / 256), 256, 0, st>>>(out, rows, length, 32 * R, hop, n_frames, window);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ACB_ERR_CUDA, std::string("acb_istft launch: ") + cudaGetErrorString(e));
+    return ACB_OK;
+}
+
 }  // namespace acb_spectral
 
 extern "C" {
@@ -412,6 +649,42 @@ int acb_stft_mag_backward(const float* x, const float* grad_mag, int64_t rows, i
         case 1024: return launch_backward<32>(x, grad_mag, rows, (int)length, hop, n_frames, window, grad_x, st);
         default:
             return fail(ACB_ERR_UNSUPPORTED, "acb_stft_mag_backward: n_fft must be 64, 128, 256, 512 or 1024 (got " + std::to_string(n_fft) + ")");
+    }
+}
+
+int acb_stft_complex(const float* x, int64_t rows, int64_t length, int n_fft, int hop, const float* window, float* spec, float* gl_previous,
+                     const float* gl_magnitude, float gl_momentum, void* stream) {
+    using namespace acb_spectral;
+    if (rows <= 0) return ACB_OK;
+    if (!x || !window || !spec) return fail(ACB_ERR_INVALID, "acb_stft_complex: null argument");
+    if ((gl_previous == nullptr) != (gl_magnitude == nullptr)) return fail(ACB_ERR_INVALID, "acb_stft_complex: gl_previous and gl_magnitude go together");
+    if (hop < 1 || length <= n_fft / 2) return fail(ACB_ERR_INVALID, "acb_stft_complex: reflect padding needs rows longer than n_fft / 2");
+    if (rows > 65535) return fail(ACB_ERR_UNSUPPORTED, "acb_stft_complex: at most 65535 rows per call");
+    const int n_frames = (int)(1 + length / hop);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    float2* sp = reinterpret_cast<float2*>(spec);
+    float2* tp = reinterpret_cast<float2*>(gl_previous);
+    switch (n_fft) {
+        case 256: return launch_stft_complex<8>(x, rows, length, hop, n_frames, window, sp, tp, gl_magnitude, gl_momentum, st);
+        case 512: return launch_stft_complex<16>(x, rows, length, hop, n_frames, window, sp, tp, gl_magnitude, gl_momentum, st);
+        case 1024: return launch_stft_complex<32>(x, rows, length, hop, n_frames, window, sp, tp, gl_magnitude, gl_momentum, st);
+        default: return fail(ACB_ERR_UNSUPPORTED, "acb_stft_complex: n_fft must be 256, 512 or 1024");
+    }
+}
+
+int acb_istft(const float* spec, int64_t rows, int64_t n_frames, int n_fft, int hop, const float* window, float* out, int64_t length, void* stream) {
+    using namespace acb_spectral;
+    if (rows <= 0) return ACB_OK;
+    if (!spec || !window || !out) return fail(ACB_ERR_INVALID, "acb_istft: null argument");
+    if (hop < 1 || n_frames < 1 || length < 1) return fail(ACB_ERR_INVALID, "acb_istft: bad hop / frames / length");
+    if (rows > 65535 || n_frames > (1 << 24)) return fail(ACB_ERR_UNSUPPORTED, "acb_istft: input too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float2* sp = reinterpret_cast<const float2*>(spec);
+    switch (n_fft) {
+        case 256: return launch_istft<8>(sp, rows, (int)n_frames, hop, window, out, length, st);
+        case 512: return launch_istft<16>(sp, rows, (int)n_frames, hop, window, out, length, st);
+        case 1024: return launch_istft<32>(sp, rows, (int)n_frames, hop, window, out, length, st);
+        default: return fail(ACB_ERR_UNSUPPORTED, "acb_istft: n_fft must be 256, 512 or 1024");
     }
 }
 

@@ -305,50 +305,58 @@ class LogMelFrontend:
     # ------------------------------------------------------------------ host-buffer path (pinned memory in/out)
     def forward_host(self, wav_host: torch.Tensor, out_host: Optional[torch.Tensor] = None, *, out_dtype=torch.float32,
                      pad_multiple: int = 1, affine: Affine = None, n_chunks: int = 8,
-                     staging: Optional[Tuple[torch.Tensor, ...]] = None) -> torch.Tensor:
+                     staging: Optional[Tuple[torch.Tensor, ...]] = None, keep_on_device: bool = False) -> torch.Tensor:
         """Host ``wav[B, L]`` (pinned for full speed) -> host ``[B, n_mels, T4]``: chunked H2D copy, fused kernel and
         D2H copy overlapped on three streams inside ``acb_logmel_forward_host``.
 
         ``wav_host`` is float32 (what the reference moves, process_dataset.py:135-140) or **int16 PCM**: 16-bit samples are
         widened on the device to ``x / 32768`` -- the exact values ``torchaudio.load`` yields for 16-bit files -- so the result is
         bit-identical while the host->device traffic, which bounds this path, halves.
-        ``staging``: optional device buffers ``(wav fp32 [B, L], out [B, n_mels, T4][, pcm int16 [B, L]])`` to reuse across calls."""
+        ``staging``: optional device buffers ``(wav fp32 [B, L], out [B, n_mels, T4][, pcm int16 [B, L]])`` to reuse across calls.
+        ``keep_on_device``: skip the D2H copy and return the DEVICE features (``staging[1]``): the training-feed case, where the
+        consumer is a model on the same GPU (``out_dtype`` / ``staging[1].dtype`` decide the feature type)."""
         pcm = wav_host.dtype == torch.int16
         if wav_host.is_cuda or wav_host.dtype not in (torch.float32, torch.int16) or wav_host.dim() != 2 or not wav_host.is_contiguous():
             raise ValueError("forward_host expects a contiguous host float32 or int16 [B, L] tensor")
         B, L = int(wav_host.shape[0]), int(wav_host.shape[1])
         T4 = padded_frames(self.frames_for_length(L), pad_multiple)
-        if out_host is None:
+        if keep_on_device:
+            if staging is None:
+                staging = (torch.empty((B, L), dtype=torch.float32, device=self.device),
+                           torch.empty((B, self.n_mels, T4), dtype=out_dtype, device=self.device))
+            out_host = None
+        elif out_host is None:
             out_host = torch.empty((B, self.n_mels, T4), dtype=out_dtype, pin_memory=True)
+        out_dt = staging[1].dtype if keep_on_device else out_host.dtype
         # the C side writes B * n_mels * T4 elements of out_host's dtype through raw pointers: shapes, dtypes, devices and
         # contiguity are checked here, once
-        if out_host.is_cuda or not out_host.is_contiguous() or tuple(out_host.shape) != (B, self.n_mels, T4) \
-                or out_host.dtype not in (torch.float32, torch.bfloat16):
+        if out_host is not None and (out_host.is_cuda or not out_host.is_contiguous() or tuple(out_host.shape) != (B, self.n_mels, T4)
+                                     or out_host.dtype not in (torch.float32, torch.bfloat16)):
             raise ValueError(f"out_host must be a contiguous host float32 / bfloat16 tensor of shape {(B, self.n_mels, T4)}")
         if staging is None:
             staging = (torch.empty((B, L), dtype=torch.float32, device=self.device),
-                       torch.empty((B, self.n_mels, T4), dtype=out_host.dtype, device=self.device))
+                       torch.empty((B, self.n_mels, T4), dtype=out_dt, device=self.device))
         if pcm and len(staging) < 3:
             staging = (staging[0], staging[1], torch.empty((B, L), dtype=torch.int16, device=self.device))
-        want = [((B, L), torch.float32), ((B, self.n_mels, T4), out_host.dtype)] + ([((B, L), torch.int16)] if pcm else [])
+        want = [((B, L), torch.float32), ((B, self.n_mels, T4), out_dt)] + ([((B, L), torch.int16)] if pcm else [])
         for t, (shape, dtype) in zip(staging, want):
             if t.device != self.device or not t.is_contiguous() or tuple(t.shape) != shape or t.dtype != dtype:
                 raise ValueError(f"staging buffers must be contiguous tensors on {self.device}: wav float32 {want[0][0]}, out "
-                                 f"{out_host.dtype} {want[1][0]}" + (", pcm int16 " + str(want[2][0]) if pcm else ""))
+                                 f"{out_dt} {want[1][0]}" + (", pcm int16 " + str(want[2][0]) if pcm else ""))
         a = LogmelArgs()
         a.frame_capacity = T4
         keep = self._fill_common(a, staging[1], "mel_major", pad_multiple, False, 0.0, affine, None, None)
         if pcm:
-            _lib.check(self._lib.acb_logmel_forward_host_pcm16(self._handle, wav_host.data_ptr(), B, L, out_host.data_ptr(), ctypes.byref(a),
+            _lib.check(self._lib.acb_logmel_forward_host_pcm16(self._handle, wav_host.data_ptr(), B, L, _ptr(out_host), ctypes.byref(a),
                                                                staging[2].data_ptr(), staging[0].data_ptr(), staging[1].data_ptr(),
                                                                int(n_chunks), _stream_ptr(self.device)), "acb_logmel_forward_host_pcm16")
         else:
-            _lib.check(self._lib.acb_logmel_forward_host(self._handle, wav_host.data_ptr(), B, L, out_host.data_ptr(), ctypes.byref(a),
+            _lib.check(self._lib.acb_logmel_forward_host(self._handle, wav_host.data_ptr(), B, L, _ptr(out_host), ctypes.byref(a),
                                                          staging[0].data_ptr(), staging[1].data_ptr(), int(n_chunks),
                                                          _stream_ptr(self.device)), "acb_logmel_forward_host")
         self.launches += min(int(n_chunks), B) * (2 if pcm else 1)
         del keep
-        return out_host
+        return staging[1] if keep_on_device else out_host
 
     def pcm16_to_float(self, pcm: torch.Tensor) -> torch.Tensor:
         """Device int16 PCM -> float32 ``x / 32768`` (``acb_pcm16_to_float``), any shape."""

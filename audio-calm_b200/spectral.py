@@ -105,3 +105,98 @@ def stft_loss(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         return torch.tensor(0.0, device=x.device, dtype=x.dtype)
     loss = sum((a - b).abs().mean() for a, b in zip(mx, my))
     return loss / len(mx)
+
+
+# ------------------------------------------------------------------------------------------------ Griffin-Lim (vocoder fallback)
+def stft_complex(x: torch.Tensor, n_fft: int = 1024, hop_length: Optional[int] = None) -> torch.Tensor:
+    """``torch.stft(x, n_fft, hop, window=hann, center=True, pad_mode="reflect", return_complex=True)`` for ``x[rows, L]`` on the
+    device -> complex64 ``[rows, n_fft // 2 + 1, 1 + L // hop]`` (``acb_stft_complex``)."""
+    hop = int(hop_length) if hop_length is not None else n_fft // 2
+    if not x.is_cuda or x.dim() != 2:
+        raise RuntimeError("stft_complex expects a CUDA tensor [rows, L] (no CPU fallback)")
+    x = x.float().contiguous()
+    rows, L = int(x.shape[0]), int(x.shape[1])
+    spec = torch.empty((rows, n_fft // 2 + 1, 1 + L // hop), dtype=torch.complex64, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.acb_stft_complex(x.data_ptr(), rows, L, int(n_fft), hop, _window(n_fft, x.device).data_ptr(), spec.data_ptr(),
+                                        None, None, 0.0, torch.cuda.current_stream(x.device).cuda_stream), "acb_stft_complex")
+    return spec
+
+
+def istft(spec: torch.Tensor, n_fft: int = 1024, hop_length: Optional[int] = None, length: Optional[int] = None) -> torch.Tensor:
+    """``torch.istft(spec, n_fft, hop, window=hann, center=True, length=length)`` for complex64 ``spec[rows, n_fft // 2 + 1, T]``."""
+    hop = int(hop_length) if hop_length is not None else n_fft // 2
+    if not spec.is_cuda or spec.dim() != 3 or spec.dtype != torch.complex64:
+        raise RuntimeError("istft expects a CUDA complex64 tensor [rows, n_freq, frames] (no CPU fallback)")
+    spec = spec.contiguous()
+    rows, frames = int(spec.shape[0]), int(spec.shape[2])
+    L = int(length) if length is not None else hop * (frames - 1)
+    out = torch.empty((rows, L), dtype=torch.float32, device=spec.device)
+    lib = _lib.load()
+    with torch.cuda.device(spec.device):
+        _lib.check(lib.acb_istft(spec.data_ptr(), rows, frames, int(n_fft), hop, _window(n_fft, spec.device).data_ptr(), out.data_ptr(), L,
+                                 torch.cuda.current_stream(spec.device).cuda_stream), "acb_istft")
+    return out
+
+
+def griffin_lim(specgram: torch.Tensor, n_fft: int = 1024, hop_length: Optional[int] = None, power: float = 2.0, n_iter: int = 32,
+                momentum: float = 0.99, length: Optional[int] = None, rand_init: bool = True,
+                init_angles: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``torchaudio.transforms.GriffinLim(n_fft)(specgram)`` (what the reference's vocoder fallback calls, eval/eval_calm.py:188,208) on
+    the device: ``specgram[..., n_fft // 2 + 1, T]`` -> waveform ``[..., hop * (T - 1)]``.  Every iteration is an inverse STFT and a
+    forward STFT whose epilogue applies the phase update (``angles = rebuilt - m * previous; angles /= |angles| + 1e-16``).
+    ``init_angles`` (complex64, the shape of ``specgram``) replaces torchaudio's ``torch.rand`` start for reproducible runs."""
+    if not 0 <= momentum < 1:
+        raise ValueError(f"momentum must be in range [0, 1). Found: {momentum}")
+    if not specgram.is_cuda:
+        raise RuntimeError("griffin_lim (B200 build) needs a CUDA tensor: there is no CPU fallback")
+    hop = int(hop_length) if hop_length is not None else n_fft // 2
+    m = momentum / (1 + momentum)
+    shape = specgram.shape
+    mag = specgram.reshape(-1, shape[-2], shape[-1]).float().pow(1.0 / power).contiguous()
+    rows, n_freq, frames = (int(v) for v in mag.shape)
+    if n_freq != n_fft // 2 + 1:
+        raise ValueError("specgram must have n_fft // 2 + 1 frequency bins")
+    if init_angles is not None:
+        angles = init_angles.reshape(mag.shape).to(mag.device, torch.complex64)
+    elif rand_init:
+        angles = torch.rand(mag.shape, dtype=torch.complex64, device=mag.device)
+    else:
+        angles = torch.ones(mag.shape, dtype=torch.complex64, device=mag.device)
+    L = int(length) if length is not None else hop * (frames - 1)
+    spec = (mag * angles).contiguous()
+    prev = torch.zeros_like(spec)
+    wave = torch.empty((rows, L), dtype=torch.float32, device=mag.device)
+    lib = _lib.load()
+    w = _window(n_fft, mag.device)
+    with torch.cuda.device(mag.device):
+        stream = torch.cuda.current_stream(mag.device).cuda_stream
+        for _ in range(int(n_iter)):
+            _lib.check(lib.acb_istft(spec.data_ptr(), rows, frames, int(n_fft), hop, w.data_ptr(), wave.data_ptr(), L, stream), "acb_istft")
+            _lib.check(lib.acb_stft_complex(wave.data_ptr(), rows, L, int(n_fft), hop, w.data_ptr(), spec.data_ptr(), prev.data_ptr(),
+                                            mag.data_ptr(), float(m), stream), "acb_stft_complex")
+        _lib.check(lib.acb_istft(spec.data_ptr(), rows, frames, int(n_fft), hop, w.data_ptr(), wave.data_ptr(), L, stream), "acb_istft")
+    return wave.reshape(tuple(shape[:-2]) + (L,))
+
+
+class PinvMelVocoder:
+    """The reference's Griffin-Lim fallback vocoder (``Vocoder.decode``, eval/eval_calm.py:184-208): log-mel ``[B, 80, T]`` ->
+    ``exp`` -> magnitude through the pseudo-inverse of torchaudio's default (HTK, un-normalised) ``MelScale(n_mels=80,
+    sample_rate=16000, n_stft=513)`` bank, clamped at 1e-8, square root -> ``GriffinLim(n_fft=1024)``."""
+
+    def __init__(self, device="cuda", n_mels: int = 80, sample_rate: int = 16000, n_fft: int = 1024):
+        import torchaudio
+        self.device = torch.device(device)
+        self.n_fft = n_fft
+        fb = torchaudio.functional.melscale_fbanks(n_fft // 2 + 1, 0.0, float(sample_rate // 2), n_mels, sample_rate, norm=None, mel_scale="htk")
+        self.mel_fb = fb.to(self.device)                                    # [513, 80], the buffer of MelScale(...).fb
+        self.inverse_mel_basis = torch.linalg.pinv(fb).to(self.device)      # [80, 513] (computed on the host like the table it is)
+
+    def magnitude(self, mel: torch.Tensor) -> torch.Tensor:
+        mel = mel.to(self.device).float()
+        energy = torch.exp(mel)
+        return torch.sqrt(torch.clamp(torch.matmul(energy.transpose(1, 2), self.inverse_mel_basis).transpose(1, 2), min=1e-8))
+
+    def decode(self, mel: torch.Tensor, **kw) -> torch.Tensor:
+        return griffin_lim(self.magnitude(mel), n_fft=self.n_fft, **kw)

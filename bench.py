@@ -519,6 +519,11 @@ def main() -> None:
                                     "ms_per_step": dtb / e2e_steps * 1e3,
                                     "note": "the real-data transport: 16-bit PCM files in (process_dataset.py:135-140), normalised bf16 "
                                             "features out (the training feed's dtype, config 4); 1e-2 tolerance class"}
+        # the training-feed case (config 4's consumer is a model on the same GPU): PCM in, bf16 features stay on the device -- no D2H
+        dtd = time_host(lambda: fe.forward_host(pcm_host, None, affine=affine, n_chunks=n_chunks, staging=staging16b, keep_on_device=True), e2e_steps)
+        e2e["pcm16_in_device_bf16"] = {"value": audio_s_per_step * e2e_steps / dtd / 3600.0, "unit": UNIT,
+                                       "h2d_bytes_per_step": int(pcm_host.numel() * 2), "d2h_bytes_per_step": 0, "ms_per_step": dtd / e2e_steps * 1e3,
+                                       "note": "features consumed on the device (training feed): only the H2D copy of the PCM remains"}
         del x_host, out_host, staging, pcm_host, staging16, out_host16, staging16b
 
     # ------------------------------------------------------------------ the statistics pass + its single NCCL all-reduce (configs[2])

@@ -178,7 +178,8 @@ int acb_pad_transpose(const void* feat_tm, int32_t dtype, const int64_t* row_off
 /* Host-buffer convenience path (pinned or pageable host memory): H2D copy, acb_logmel_forward on uniform
  * clips [n_clips][length], D2H copy, chunked over `n_chunks` so copies overlap compute.  dev_in/dev_out
  * are caller-provided device staging buffers (n_clips*length floats / n_clips*n_mels*frame_capacity
- * elements).  Synchronises `stream` before returning. */
+ * elements).  out_host == NULL keeps the features on the device (dev_out) and skips the D2H copies: the training-feed
+ * case, where the consumer is a model on the same GPU.  Synchronises `stream` before returning. */
 int acb_logmel_forward_host(const acb_frontend* fe, const float* wav_host, int32_t n_clips, int64_t length,
                             void* out_host, acb_logmel_args* args_template, float* dev_in, void* dev_out,
                             int32_t n_chunks, void* stream);
@@ -272,6 +273,19 @@ int acb_stft_mag(const float* x, int64_t rows, int64_t length, int n_fft, int ho
  * gradient (torch's abs does the same). */
 int acb_stft_mag_backward(const float* x, const float* grad_mag, int64_t rows, int64_t length, int n_fft, int hop, const float* window,
                           float* grad_x, void* stream);
+
+/* Griffin-Lim building blocks: the vocoder fallback of eval/eval_calm.py:184-208 runs torchaudio.transforms.GriffinLim(n_fft=1024)
+ * (torchaudio.functional.griffinlim: n_iter x [torch.istft, torch.stft(center=True, reflect), phase update with momentum]).
+ *   acb_stft_complex: x device [rows][length] -> spec device complex64 [rows][n_fft/2+1][1 + length/hop] (interleaved re, im), frames
+ *     centred with reflect padding like torch.stft(center=True).  With gl_previous / gl_magnitude (same shape as spec: complex /
+ *     real) the epilogue applies one Griffin-Lim update instead: rebuilt = STFT; angles = rebuilt - gl_momentum * gl_previous;
+ *     gl_previous = rebuilt; spec = angles / (|angles| + 1e-16) * gl_magnitude.
+ *   acb_istft: spec -> out device [rows][length] like torch.istft(center=True, length=length): inverse transform, window,
+ *     overlap-add, division by the window envelope, n_fft/2 trimmed at the start.
+ * n_fft in {256, 512, 1024}; window device [n_fft]. */
+int acb_stft_complex(const float* x, int64_t rows, int64_t length, int n_fft, int hop, const float* window, float* spec, float* gl_previous,
+                     const float* gl_magnitude, float gl_momentum, void* stream);
+int acb_istft(const float* spec, int64_t rows, int64_t n_frames, int n_fft, int hop, const float* window, float* out, int64_t length, void* stream);
 
 #ifdef __cplusplus
 }

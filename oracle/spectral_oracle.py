@@ -38,3 +38,47 @@ def stft_loss(x: np.ndarray, y: np.ndarray) -> float:
     if not specs:
         return 0.0
     return float(sum(np.mean(np.abs(stft_mag(x, n, h) - stft_mag(y, n, h))) for n, h in specs) / len(specs))
+
+
+# ---------------------------------------------------------------------------------------------
+# Griffin-Lim (torchaudio.functional.griffinlim as called by eval/eval_calm.py:188,208), restated in numpy fp64
+# ---------------------------------------------------------------------------------------------
+def stft_centered(x: np.ndarray, n_fft: int, hop: int) -> np.ndarray:
+    """torch.stft(center=True, pad_mode="reflect", onesided): ``x[L]`` -> complex ``[n_fft // 2 + 1, 1 + L // hop]``."""
+    w = hann_periodic(n_fft)
+    xp = np.pad(x.astype(np.float64), (n_fft // 2, n_fft // 2), mode="reflect")
+    frames = 1 + len(x) // hop
+    idx = np.arange(n_fft)[None, :] + hop * np.arange(frames)[:, None]
+    return np.fft.rfft(xp[idx] * w[None, :], axis=-1).T
+
+
+def istft_centered(spec: np.ndarray, n_fft: int, hop: int, length=None) -> np.ndarray:
+    """torch.istft(center=True): inverse transform, window, overlap-add, division by the window envelope, centre trimmed."""
+    w = hann_periodic(n_fft)
+    frames = spec.shape[1]
+    full = n_fft + hop * (frames - 1)
+    y, env = np.zeros(full), np.zeros(full)
+    seg = np.fft.irfft(spec.T, n=n_fft, axis=-1) * w[None, :]
+    for t in range(frames):
+        y[t * hop:t * hop + n_fft] += seg[t]
+        env[t * hop:t * hop + n_fft] += w * w
+    L = hop * (frames - 1) if length is None else length
+    y, env = y[n_fft // 2:n_fft // 2 + L], env[n_fft // 2:n_fft // 2 + L]
+    return np.where(env > 1e-11, y / np.where(env > 1e-11, env, 1.0), y)
+
+
+def griffin_lim(specgram: np.ndarray, init_angles: np.ndarray, n_fft: int = 1024, hop=None, power: float = 2.0, n_iter: int = 32,
+                momentum: float = 0.99) -> np.ndarray:
+    """``specgram[n_freq, T]`` and the initial complex ``angles`` (torchaudio draws them with torch.rand) -> waveform."""
+    hop = n_fft // 2 if hop is None else hop
+    m = momentum / (1 + momentum)
+    mag = specgram.astype(np.float64) ** (1.0 / power)
+    angles = init_angles.astype(np.complex128)
+    prev = 0.0
+    for _ in range(n_iter):
+        inverse = istft_centered(mag * angles, n_fft, hop)
+        rebuilt = stft_centered(inverse, n_fft, hop)
+        angles = rebuilt - m * prev
+        angles = angles / (np.abs(angles) + 1e-16)
+        prev = rebuilt
+    return istft_centered(mag * angles, n_fft, hop)

@@ -466,6 +466,8 @@ def test_host_buffer_path_validates_its_buffers(fe):
     y = fe.forward_host(x, good, affine=(acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT))
     ref = fe.forward(x.cuda(), affine=(acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT), out_dtype=torch.bfloat16).cpu()
     assert torch.equal(y, ref)
+    yd = fe.forward_host(x, None, affine=(acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT), out_dtype=torch.bfloat16, keep_on_device=True)
+    assert yd.is_cuda and torch.equal(yd.cpu(), ref)                 # training-feed case: no D2H, the features stay on the device
 
 
 @pytest.mark.parametrize("seed", [101, 202, 303])

@@ -132,3 +132,60 @@ def test_stft_loss_trains_like_the_reference(g):
     d, scale = float((x.grad - x2.grad).abs().mean()), float(x2.grad.abs().mean())
     assert d < 1e-3 * scale, (d, scale)
     assert float((x.grad - x2.grad).abs().max()) < 0.05 * float(x2.grad.abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ Griffin-Lim vocoder fallback
+GL_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "griffinlim_cases.npz")
+
+
+def test_griffin_lim_oracle_matches_torchaudio_goldens():
+    """numpy restatement of torchaudio.functional.griffinlim (istft / stft / phase update) against outputs of the reference's call
+    sequence (oracle/gen_golden_griffinlim.py), started from the stored torch.rand draw."""
+    g = np.load(GL_GOLDEN)
+    spec = so.stft_centered(g["rt_wave"][0].astype(np.float64), 1024, 512)
+    assert np.max(np.abs(so.istft_centered(g["rt_spec"][0], 1024, 512) - g["rt_wave"][0])) < 1e-5
+    assert spec.shape == (513, 12)
+    w2 = so.griffin_lim(g["mag"][0], g["init_angles"][0], n_iter=2)
+    assert w2.shape == g["wave_2"][0].shape and np.max(np.abs(w2 - g["wave_2"][0])) < 1e-4 * max(1.0, np.abs(g["wave_2"]).max())
+    w32 = so.griffin_lim(g["mag"][0], g["init_angles"][0], n_iter=32)
+    ref = g["wave_32"][0]
+    assert np.max(np.abs(w32 - ref)) < 2e-2 * np.abs(ref).max()          # 32 phase-retrieval iterations amplify fp32-vs-fp64 rounding
+
+
+@pytest.mark.gpu
+def test_istft_and_stft_complex_match_torch():
+    g = np.load(GL_GOLDEN)
+    spec = torch.from_numpy(g["rt_spec"]).cuda()
+    y = spectral.istft(spec, 1024, 512)
+    assert tuple(y.shape) == g["rt_wave"].shape and float(np.max(np.abs(y.cpu().numpy() - g["rt_wave"]))) < 1e-5
+    x = torch.randn(3, 7001, device="cuda") * 0.1
+    for n_fft, hop in ((1024, 512), (1024, 256), (512, 128), (256, 64)):
+        w = torch.hann_window(n_fft, device="cuda")
+        ref = torch.stft(x, n_fft, hop, n_fft, w, center=True, pad_mode="reflect", return_complex=True)
+        got = spectral.stft_complex(x, n_fft, hop)
+        assert got.shape == ref.shape and float((got - ref).abs().max()) < 1e-4 * max(1.0, float(ref.abs().max())), (n_fft, hop)
+        back = spectral.istft(got, n_fft, hop, length=7001)
+        ref_back = torch.istft(ref, n_fft, hop, n_fft, w, length=7001)
+        assert float((back - ref_back).abs().max()) < 1e-5, (n_fft, hop)
+
+
+@pytest.mark.gpu
+def test_griffin_lim_matches_the_reference_call_sequence():
+    """eval/eval_calm.py:184-208 (pinv-mel magnitude + GriffinLim(n_fft=1024)) from the same initial phases as the stored torchaudio run."""
+    g = np.load(GL_GOLDEN)
+    voc = spectral.PinvMelVocoder("cuda")
+    mag = voc.magnitude(torch.from_numpy(g["mel"]).cuda())
+    # pinv-mel magnitude: the pseudo-inverse has negative entries, so bins that cancel to ~0 sit on the 1e-8 clamp and their square
+    # root (1e-4) is decided by summation order; the comparison is therefore on the energies, relative to the largest one
+    e_got, e_ref = mag.cpu().numpy().astype(np.float64) ** 2, g["mag"].astype(np.float64) ** 2
+    assert float(np.max(np.abs(e_got - e_ref))) < 1e-5 * float(e_ref.max())
+    init = torch.from_numpy(g["init_angles"]).cuda()
+    w2 = spectral.griffin_lim(torch.from_numpy(g["mag"]).cuda(), n_iter=2, init_angles=init).cpu().numpy()
+    assert w2.shape == g["wave_2"].shape and float(np.max(np.abs(w2 - g["wave_2"]))) < 1e-4 * max(1.0, float(np.abs(g["wave_2"]).max()))
+    w32 = spectral.griffin_lim(torch.from_numpy(g["mag"]).cuda(), init_angles=init).cpu().numpy()
+    ref = g["wave_32"]
+    assert float(np.max(np.abs(w32 - ref))) < 2e-2 * float(np.abs(ref).max())
+    # end to end through the vocoder object, random start like the reference: a waveform of the right length and scale
+    wav = voc.decode(torch.from_numpy(g["mel"]).cuda())
+    assert tuple(wav.shape) == (1, 512 * (g["mel"].shape[2] - 1)) and bool(torch.isfinite(wav).all())
+    assert 0.2 < float(wav.abs().max()) / float(np.abs(ref).max()) < 5.0
