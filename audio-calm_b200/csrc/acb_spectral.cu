@@ -371,14 +371,15 @@ static int launch_backward(const float* x, const float* grad_mag, int64_t rows, 
 // centre trimmed), both on the same group FFT; long rows are cut into chunks of frames per CTA.
 // --------------------------------------------------------------------------------------------
 struct ChunkSmem {
-    int x, spec, win, tw, buf, total_bytes;
+    int x, spec, y, win, tw, buf, total_bytes;
 };
 __host__ __device__ inline ChunkSmem chunk_smem(int R, int frames_per_cta, int hop, bool with_spec) {
     const int N = 32 * R, n_freq = N / 2 + 1;
     ChunkSmem L;
     int off = 0;
     L.x = off; off += with_spec ? 0 : (((frames_per_cta - 1) * hop + N + 3) & ~3);
-    L.spec = off; off += with_spec ? 2 * n_freq * frames_per_cta : 0;
+    L.spec = off; off += 2 * n_freq * frames_per_cta;                                   // [k][frame of the chunk] complex: istft input / stft output
+    L.y = off; off += with_spec ? (((frames_per_cta - 1) * hop + N + 3) & ~3) : 0;     // istft: the chunk's overlap-added output
     L.win = off; off += N;
     L.tw = off; off += 2 * N;
     L.buf = off; off += (kThreads / R) * (2 * 33 * R);
@@ -395,6 +396,7 @@ __global__ void __launch_bounds__(kThreads) stft_complex_kernel(const float* __r
     extern __shared__ __align__(16) float smem[];
     const ChunkSmem L = chunk_smem(R, frames_per_cta, hop, false);
     float* s_x = smem + L.x;
+    float2* s_spec = reinterpret_cast<float2*>(smem + L.spec);
     float* s_win = smem + L.win;
     float2* s_tw = reinterpret_cast<float2*>(smem + L.tw);
     const int tid = threadIdx.x;
@@ -443,29 +445,47 @@ __global__ void __launch_bounds__(kThreads) stft_complex_kernel(const float* __r
         __syncwarp();
         if (valid) group_fft_stage2<R>(buf, r);
         __syncwarp();
-        if (valid) {
+        if (valid) {                                    // separate the two spectra into the chunk's staged output [k][frame]
             for (int k = r; k < kFreq; k += R) {
                 const int kc = (N - k) & (N - 1);
                 const float2 z = buf[buf_index(k)], zc = buf[buf_index(kc)];
-                float2 xs[2] = {make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y)), make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x))};
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h == 1 && !valid_b) break;
-                    const size_t o = ((size_t)row * kFreq + k) * n_frames + t0 + fa + h;
-                    float2 v = xs[h];
-                    if (mag != nullptr) {      // one Griffin-Lim phase update: angles = (rebuilt - m * previous) / (|.| + 1e-16); out = angles * magnitude
-                        const float2 prev = tprev[o];
-                        tprev[o] = v;
-                        float ar = fmaf(-momentum, prev.x, v.x), ai = fmaf(-momentum, prev.y, v.y);
-                        const float inv = 1.f / (sqrtf(fmaf(ar, ar, ai * ai)) + 1e-16f);
-                        const float m = mag[o];
-                        v = make_float2(ar * inv * m, ai * inv * m);
-                    }
-                    spec_out[o] = v;
-                }
+                s_spec[k * frames_per_cta + fa] = make_float2(0.5f * (z.x + zc.x), 0.5f * (z.y - zc.y));
+                if (valid_b) s_spec[k * frames_per_cta + fb] = make_float2(0.5f * (z.y + zc.y), -0.5f * (z.x - zc.x));
             }
         }
         __syncwarp();
+    }
+    __syncthreads();
+    // one coalesced pass over the chunk's [k][frames] block: every k row is a contiguous run of the chunk's frames in global memory
+    // (four elements per thread and step, all loads issued before the first store: the read-modify-write of `previous` would
+    // otherwise serialise on memory latency)
+    const int total = kFreq * frames_per_cta;
+    for (int i0 = tid; i0 < total; i0 += 4 * kThreads) {
+        size_t o[4];
+        float2 v[4], prev[4];
+        float m[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * kThreads;
+            const int k = i / frames_per_cta, t = i - k * frames_per_cta;
+            ok[u] = i < total && t < n_loc;
+            o[u] = ((size_t)row * kFreq + k) * n_frames + t0 + t;
+            v[u] = ok[u] ? s_spec[i] : make_float2(0.f, 0.f);
+            if (mag != nullptr && ok[u]) { prev[u] = tprev[o[u]]; m[u] = mag[o[u]]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            float2 w = v[u];
+            if (mag != nullptr) {      // one Griffin-Lim phase update: angles = (rebuilt - m * previous) / (|.| + 1e-16); out = angles * magnitude
+                tprev[o[u]] = w;
+                const float ar = fmaf(-momentum, prev[u].x, w.x), ai = fmaf(-momentum, prev[u].y, w.y);
+                const float inv = 1.f / (sqrtf(fmaf(ar, ar, ai * ai)) + 1e-16f);
+                w = make_float2(ar * inv * m[u], ai * inv * m[u]);
+            }
+            spec_out[o[u]] = w;
+        }
     }
 }
 
@@ -495,6 +515,10 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
     const int g = tid / R, r = tid % R;
     float2* buf = reinterpret_cast<float2*>(smem + L.buf) + g * (33 * R);
     float* dst = out + row * length;
+    float* s_y = smem + L.y;                            // overlap-add of the chunk's frames: shared-memory atomics, global ones only at the chunk's rims
+    const int span = (n_loc - 1) * hop + N;
+    for (int i = tid; i < span; i += kThreads) s_y[i] = 0.f;
+    __syncthreads();
     const float inv_n = 1.f / (float)N;
     const int n_items = (n_loc + 1) / 2, n_iter = (n_items + kGroups - 1) / kGroups;
     for (int it = 0; it < n_iter; ++it) {
@@ -531,16 +555,28 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
         __syncwarp();
         if (valid) group_fft_stage2<R>(buf, r);
         __syncwarp();
-        if (valid) {                                    // window, overlap-add, centre trimmed (torch.istft center=True)
+        if (valid) {                                    // window and overlap-add inside the chunk
             for (int n = r; n < N; n += R) {
                 const float2 y = buf[buf_index(n)];
                 const float w = s_win[n] * inv_n;
-                const long long pa = (long long)(t0 + fa) * hop + n - N / 2, pb = pa + hop;
-                if (pa >= 0 && pa < length) atomicAdd(dst + pa, w * y.x);
-                if (valid_b && pb >= 0 && pb < length) atomicAdd(dst + pb, -w * y.y);
+                atomicAdd(s_y + fa * hop + n, w * y.x);
+                if (valid_b) atomicAdd(s_y + fb * hop + n, -w * y.y);
             }
         }
         __syncwarp();
+    }
+    __syncthreads();
+    {   // write the chunk out, centre trimmed (torch.istft center=True): positions that the neighbouring chunks' frames also reach
+        // (the first and last N - hop samples of the span) are combined with global atomics, the rest are plain stores
+        const long long base = (long long)t0 * hop - N / 2;
+        const int rim = N - hop;
+        const bool first = t0 == 0, last = t0 + n_loc >= n_frames;
+        for (int i = tid; i < span; i += kThreads) {
+            const long long pos = base + i;
+            if (pos < 0 || pos >= length) continue;
+            if ((i < rim && !first) || (i >= span - rim && !last)) atomicAdd(dst + pos, s_y[i]);
+            else dst[pos] = s_y[i];
+        }
     }
 }
 
@@ -568,7 +604,7 @@ static int launch_stft_complex(const float* x, int64_t rows, int64_t length, int
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return fail(ACB_ERR_CUDA, "acb_stft_complex: cannot query the device");
     int fpc = 16;
-    while (fpc > 2 && chunk_smem(R, fpc, hop, false).total_bytes > std::min(optin, 128 * 1024)) fpc >>= 1;
+    while (fpc > 2 && chunk_smem(R, fpc, hop, false).total_bytes > std::min(optin, 160 * 1024)) fpc >>= 1;
     const ChunkSmem L = chunk_smem(R, fpc, hop, false);
     if (L.total_bytes > optin) return fail(ACB_ERR_UNSUPPORTED, "acb_stft_complex: hop too large for shared memory");
     cudaError_t e = cudaFuncSetAttribute(stft_complex_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
@@ -586,7 +622,7 @@ static int launch_istft(const float2* spec, int64_t rows, int n_frames, int hop,
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return fail(ACB_ERR_CUDA, "acb_istft: cannot query the device");
     int fpc = 16;
-    while (fpc > 2 && chunk_smem(R, fpc, hop, true).total_bytes > std::min(optin, 128 * 1024)) fpc >>= 1;
+    while (fpc > 2 && chunk_smem(R, fpc, hop, true).total_bytes > std::min(optin, 160 * 1024)) fpc >>= 1;
     const ChunkSmem L = chunk_smem(R, fpc, hop, true);
     if (L.total_bytes > optin) return fail(ACB_ERR_UNSUPPORTED, "acb_istft: transform too large for shared memory");
     cudaError_t e = cudaFuncSetAttribute(istft_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);

@@ -149,7 +149,7 @@ def test_griffin_lim_oracle_matches_torchaudio_goldens():
     assert w2.shape == g["wave_2"][0].shape and np.max(np.abs(w2 - g["wave_2"][0])) < 1e-4 * max(1.0, np.abs(g["wave_2"]).max())
     w32 = so.griffin_lim(g["mag"][0], g["init_angles"][0], n_iter=32)
     ref = g["wave_32"][0]
-    assert np.max(np.abs(w32 - ref)) < 2e-2 * np.abs(ref).max()          # 32 phase-retrieval iterations amplify fp32-vs-fp64 rounding
+    assert np.max(np.abs(w32 - ref)) < 2e-3 * np.abs(ref).max()          # 32 phase-retrieval iterations amplify fp32-vs-fp64 rounding (measured 1e-4)
 
 
 @pytest.mark.gpu
@@ -184,7 +184,7 @@ def test_griffin_lim_matches_the_reference_call_sequence():
     assert w2.shape == g["wave_2"].shape and float(np.max(np.abs(w2 - g["wave_2"]))) < 1e-4 * max(1.0, float(np.abs(g["wave_2"]).max()))
     w32 = spectral.griffin_lim(torch.from_numpy(g["mag"]).cuda(), init_angles=init).cpu().numpy()
     ref = g["wave_32"]
-    assert float(np.max(np.abs(w32 - ref))) < 2e-2 * float(np.abs(ref).max())
+    assert float(np.max(np.abs(w32 - ref))) < 2e-3 * float(np.abs(ref).max())                             # measured 9.5e-5
     # end to end through the vocoder object, random start like the reference: a waveform of the right length and scale
     wav = voc.decode(torch.from_numpy(g["mel"]).cuda())
     assert tuple(wav.shape) == (1, 512 * (g["mel"].shape[2] - 1)) and bool(torch.isfinite(wav).all())
