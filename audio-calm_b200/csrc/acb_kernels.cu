@@ -1213,27 +1213,33 @@ __device__ __forceinline__ float load_feat<float>(const float* p, long long i) {
 template <>
 __device__ __forceinline__ float load_feat<__nv_bfloat16>(const __nv_bfloat16* p, long long i) { return __bfloat162float(p[i]); }
 
-// Eight (fp32) or sixteen (bf16) consecutive features of a row as floats: two 16-byte loads.
+// One 16-byte load of a row as floats: four fp32 or eight bf16 consecutive features.
 template <typename T>
-__device__ __forceinline__ void load_feat_vec(const T* p, float (&f)[8]);
+struct FeatVec;
 template <>
-__device__ __forceinline__ void load_feat_vec<float>(const float* p, float (&f)[8]) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
+struct FeatVec<float> {
+    static constexpr int kPer = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    }
+};
 template <>
-__device__ __forceinline__ void load_feat_vec<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
-    const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
-    const unsigned w[4] = {a.x, a.y, a.z, a.w};
+struct FeatVec<__nv_bfloat16> {
+    static constexpr int kPer = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+        const unsigned w[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { f[2 * k] = __uint_as_float(w[k] << 16); f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
-}
+        for (int k = 0; k < 4; ++k) { f[2 * k] = __uint_as_float(w[k] << 16); f[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+    }
+};
 
-// One warp per (clip, band) row; rows are dealt round-robin to the grid's warps.  A lane takes 8 consecutive values per step
-// (two 16-byte loads for fp32, one for bf16) and keeps 4 steps in flight -- up to 4 KB per lane-step of the warp, enough bytes
-// in flight to cover HBM latency at 8 warps x 8 CTAs per SM.  Every value enters fp64 accumulators (B200 has full-rate fp64
-// units: 2 fp64 operations per 4 bytes read are far below their rate), so the moments are exact to fp64 rounding.  Per-warp fp64
-// accumulators in shared memory, combined in a fixed order -> deterministic partial per CTA.
+// One warp per (clip, band) row; rows are dealt round-robin to the grid's warps.  Lane l takes the 16-byte group l, l + 32, ... of the
+// row (every load instruction of the warp covers 512 contiguous bytes) and keeps 8 loads in flight -- 4 KB per warp, enough bytes in
+// flight to cover HBM latency at 8 warps x 8 CTAs per SM.  Every value enters fp64 accumulators (B200 has full-rate fp64 units: 2 fp64
+// operations per 4 bytes read are far below their rate), so the moments are exact to fp64 rounding.  Per-warp fp64 accumulators in
+// shared memory, combined in a fixed order -> deterministic partial per CTA.
 template <typename T>
 __global__ void __launch_bounds__(256) moments_rows_kernel(const T* __restrict__ feat, int n_clips, int n_mels, long long cap,
                                                            long long clip_stride, const long long* __restrict__ frames,
@@ -1249,30 +1255,31 @@ __global__ void __launch_bounds__(256) moments_rows_kernel(const T* __restrict__
         const long long n_fr = frames ? frames[clip] : cap;
         const T* src = feat + (long long)clip * clip_stride + (long long)b * cap;
         double sa[2] = {0.0, 0.0}, sb[2] = {0.0, 0.0};
-        // scalar head up to the first 32-byte (fp32) / 16-byte (bf16) boundary, vector body, scalar tail
-        const int mis = (int)((reinterpret_cast<uintptr_t>(src) & 31) / sizeof(T));
-        const long long head = min(n_fr, (long long)((mis ? (32 / (int)sizeof(T)) - mis : 0)));
+        // scalar head up to the first 16-byte boundary, vector body, scalar tail
+        constexpr int kPer = FeatVec<T>::kPer, kDeep = 8;
+        const int mis = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(T));
+        const long long head = min(n_fr, (long long)((mis ? (16 / (int)sizeof(T)) - mis : 0)));
         for (long long i = lane; i < head; i += 32) { const double v = (double)load_feat<T>(src, i); sa[0] += v; sb[0] += v * v; }
-        const long long n8 = (n_fr - head) >> 3;
+        const long long nv = (n_fr - head) / kPer;
         const T* body = src + head;
-        for (long long i = lane; i < n8; i += 128) {          // four predicated 8-value groups per lane and trip, all loads up front
-            float f[4][8];
+        for (long long i = lane; i < nv; i += 32 * kDeep) {          // kDeep predicated 16-byte groups per lane and trip, all loads up front
+            float f[kDeep][kPer];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (i + 32 * k < n8) {
-                    load_feat_vec<T>(body + 8 * (i + 32 * k), f[k]);
+            for (int k = 0; k < kDeep; ++k) {
+                if (i + 32 * k < nv) {
+                    FeatVec<T>::load(body + kPer * (i + 32 * k), f[k]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) f[k][j] = 0.f;
+                    for (int j = 0; j < kPer; ++j) f[k][j] = 0.f;
                 }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < kDeep; ++k) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { const double v = (double)f[k][j]; sa[j & 1] += v; sb[j & 1] = fma(v, v, sb[j & 1]); }
+                for (int j = 0; j < kPer; ++j) { const double v = (double)f[k][j]; sa[j & 1] += v; sb[j & 1] = fma(v, v, sb[j & 1]); }
             }
         }
-        for (long long t = head + (n8 << 3) + lane; t < n_fr; t += 32) { const double v = (double)load_feat<T>(src, t); sa[1] += v; sb[1] += v * v; }
+        for (long long t = head + nv * kPer + lane; t < n_fr; t += 32) { const double v = (double)load_feat<T>(src, t); sa[1] += v; sb[1] += v * v; }
         double s = sa[0] + sa[1], s2 = sb[0] + sb[1];
 #pragma unroll
         for (int o = 16; o >= 1; o >>= 1) {
@@ -1289,7 +1296,76 @@ __global__ void __launch_bounds__(256) moments_rows_kernel(const T* __restrict__
     }
 }
 
-// (x - mean_t) / max(std_t, min_std) per (clip, band) row, unbiased std (eval/eval_vae.py:80-82)
+// (x - mean_t) / max(std_t, min_std) per (clip, band) row, unbiased std (eval/eval_vae.py:80-82).
+// Register form: one WARP per row, the row (up to 32 * 4 * kVecs frames) is read from HBM once with all of a lane's 16-byte loads in
+// flight together and stays in registers for the mean, the variance and the write: one read + one write of the features, no barrier.
+// Per-lane partial sums are fp32 (four interleaved accumulators over <= 64 values), the cross-lane reduction and the division are fp64.
+template <int kVecs>
+__global__ void __launch_bounds__(256) normalize_rows_warp_kernel(const float* __restrict__ feat, float* __restrict__ out, long long n_rows,
+                                                                  int n_mels, long long cap, const long long* __restrict__ frames, float min_std) {
+    const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (r >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const long long T = frames ? frames[r / n_mels] : cap;
+    const float4* src = reinterpret_cast<const float4*>(feat + r * cap);
+    float4* dst = reinterpret_cast<float4*>(out + r * cap);
+    const int T4 = (int)((T + 3) >> 2);             // 16-byte groups that hold valid frames (cap % 4 == 0: the last one is inside the row)
+    float4 v[kVecs];
+#pragma unroll
+    for (int k = 0; k < kVecs; ++k) {
+        const int i = k * 32 + lane;
+        v[k] = i < T4 ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // frames beyond T inside the last group do not count
+    const int last = T4 - 1, rem = (int)(T - 4LL * last);      // valid elements of the last group (1..4)
+#pragma unroll
+    for (int k = 0; k < kVecs; ++k)
+        if (k * 32 + lane == last) {
+            if (rem < 2) v[k].y = 0.f;
+            if (rem < 3) v[k].z = 0.f;
+            if (rem < 4) v[k].w = 0.f;
+        }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kVecs; ++k) { a0 += v[k].x; a1 += v[k].y; a2 += v[k].z; a3 += v[k].w; }
+    double s = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = (float)(s / (double)T);
+    a0 = a1 = a2 = a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kVecs; ++k) {
+        const int i = k * 32 + lane;
+        if (i < T4) {
+            const bool is_last = i == last;
+            const float dx = v[k].x - mean, dy = v[k].y - mean, dz = v[k].z - mean, dw = v[k].w - mean;
+            a0 = fmaf(dx, dx, a0);
+            if (!is_last || rem >= 2) a1 = fmaf(dy, dy, a1);
+            if (!is_last || rem >= 3) a2 = fmaf(dz, dz, a2);
+            if (!is_last || rem >= 4) a3 = fmaf(dw, dw, a3);
+        }
+    }
+    double s2 = ((double)a0 + (double)a1) + ((double)a2 + (double)a3);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    const float sd = fmaxf((float)sqrt(s2 / (double)(T > 1 ? T - 1 : 1)), min_std);
+#pragma unroll
+    for (int k = 0; k < kVecs; ++k) {
+        const int i = k * 32 + lane;
+        if (i < T4) {
+            float4 y = make_float4(__fdiv_rn(v[k].x - mean, sd), __fdiv_rn(v[k].y - mean, sd), __fdiv_rn(v[k].z - mean, sd), __fdiv_rn(v[k].w - mean, sd));
+            if (i == last && rem < 4) {              // keep what lies beyond the clip's frames untouched
+                const float4 old = dst[i];
+                if (rem < 2) y.y = old.y;
+                if (rem < 3) y.z = old.z;
+                y.w = old.w;
+            }
+            dst[i] = y;
+        }
+    }
+}
+
+// General form (any length, any alignment): one CTA per row, three passes (the re-reads hit L1 / L2), fp64 sums.
 __global__ void __launch_bounds__(128) normalize_rows_kernel(const float* __restrict__ feat, float* __restrict__ out, int n_mels,
                                                              long long cap, const long long* __restrict__ frames, float min_std) {
     const int clip = blockIdx.x / n_mels;
@@ -2061,8 +2137,17 @@ int acb_normalize_per_utterance(const float* feat, float* out, int32_t n_clips, 
                                 const int64_t* frames, float min_std, void* stream) {
     if (n_clips <= 0) return ACB_OK;
     if (!feat || !out || n_mels < 1 || frame_capacity < 1) return fail(ACB_ERR_INVALID, "acb_normalize_per_utterance: bad argument");
-    normalize_rows_kernel<<<n_clips * n_mels, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        feat, out, n_mels, frame_capacity, reinterpret_cast<const long long*>(frames), min_std);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long n_rows = (long long)n_clips * n_mels;
+    const long long* fr = reinterpret_cast<const long long*>(frames);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(feat) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && frame_capacity % 4 == 0;
+    const unsigned wgrid = (unsigned)((n_rows + 7) / 8);
+    if (aligned && frame_capacity <= 32 * 4 * 8)
+        normalize_rows_warp_kernel<8><<<wgrid, 256, 0, st>>>(feat, out, n_rows, n_mels, frame_capacity, fr, min_std);
+    else if (aligned && frame_capacity <= 32 * 4 * 16)
+        normalize_rows_warp_kernel<16><<<wgrid, 256, 0, st>>>(feat, out, n_rows, n_mels, frame_capacity, fr, min_std);
+    else
+        normalize_rows_kernel<<<n_clips * n_mels, 128, 0, st>>>(feat, out, n_mels, frame_capacity, fr, min_std);
     ACB_CUDA(cudaGetLastError());
     return ACB_OK;
 }

@@ -370,6 +370,21 @@ def test_normalize_per_utterance_symbol(golden):
     assert float(np.max(np.abs(yb[1] - o.normalise_per_utterance(b)))) < 1e-5
     with pytest.raises(RuntimeError):
         acb.normalize_per_utterance(torch.zeros(80, 8))                              # no CPU fallback
+    # row shapes of every kernel form: odd length on an unaligned view (scalar accesses), 1876 frames (the staged 16-byte form),
+    # 7001 frames (longer than the shared-memory budget: three-pass form)
+    rng = np.random.default_rng(5)
+    for T, off in ((63, 1), (1876, 0), (7001, 0)):
+        buf = rng.standard_normal((3, 80, T + off)).astype(np.float32) * 2.0 - 5.0
+        x = dev(buf)[:, :, off:].contiguous() if off == 0 else dev(buf)
+        if off:
+            flat = dev(np.concatenate([np.zeros(1, np.float32), buf[:, :, off:].ravel()]))
+            x = flat[1:].view(3, 80, T)                                                  # base pointer 4 bytes off a 16-byte boundary
+            ref_in = buf[:, :, off:]
+        else:
+            ref_in = buf
+        y = acb.normalize_per_utterance(x).cpu().numpy()
+        for i in range(3):
+            assert float(np.max(np.abs(y[i] - o.normalise_per_utterance(ref_in[i])))) < 2e-5, (T, off, i)
 
 
 def test_process_audio_chunk_edge_cases():

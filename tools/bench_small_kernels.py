@@ -60,10 +60,13 @@ def main():
     emit("moments_rows_kernel", timed(lambda: acc.update(feats)), feats.numel() * 4, "256 x [80, 1876] fp32 features, 320 B/frame read")
     import ctypes
     lib = acb._lib.load()
+    feats_big = torch.randn(2048, 80, 1876, device="cuda")
+    emit("moments_rows_kernel (large)", timed(lambda: acc.update(feats_big)), feats_big.numel() * 4, "2048 x [80, 1876] fp32 features (1.2 GB read)")
+    del feats_big
     o = torch.empty_like(feats)
     cs = lambda: torch.cuda.current_stream().cuda_stream      # inside a graph capture this is the capture stream
     emit("normalize_rows_kernel", timed(lambda: lib.acb_normalize_per_utterance(feats.data_ptr(), o.data_ptr(), 256, 80, 1876, None, 1e-5, cs())),
-         feats.numel() * 4 * 3, "256 x [80, 1876] fp32: mean pass + variance pass + write")
+         feats.numel() * 4 * 2, "256 x [80, 1876] fp32: one read (a warp keeps its row in registers for the mean and the variance) + one write")
     # the two collation kernels are timed through the raw C ABI with every argument already on the device (the Python wrappers
     # compute starts / offsets on the host, which is not kernel time)
     frames = torch.full((256,), 1876, dtype=torch.int64, device="cuda")
@@ -80,6 +83,15 @@ def main():
                                                                    crop_b.data_ptr(), 1024, 0.0, cs())), 2048 * 80 * 1024 * 4 * 2,
          "2048 x [80, 1876] fp32 -> [2048, 80, 1024] centre crops (1.3 GB moved)")
     del big, crop_b
+    nb = 4096
+    lens_b = torch.full((nb,), 384, dtype=torch.int64, device="cuda")
+    offs_b = torch.arange(nb, dtype=torch.int64, device="cuda") * 384
+    lat_b = torch.randn(nb * 384, 128, device="cuda")
+    pt_b = torch.empty((nb, 128, 384), device="cuda")
+    emit("pad_transpose_kernel (large)", timed(lambda: lib.acb_pad_transpose(lat_b.data_ptr(), 0, offs_b.data_ptr(), lens_b.data_ptr(), nb, 128, pt_b.data_ptr(), 384,
+                                                                             0.0, None, None, cs())), lat_b.numel() * 4 * 2,
+         "4096 x (384, 128) fp32 latents -> [4096, 128, 384] (1.6 GB moved)")
+    del lat_b, pt_b
     lens = torch.full((512,), 384, dtype=torch.int64, device="cuda")
     offs = torch.arange(512, dtype=torch.int64, device="cuda") * 384
     lat = torch.randn(512 * 384, 128, device="cuda")

@@ -30,6 +30,10 @@ VARIANTS = {
     "tcab2": ["-DACB_DEV", "-DACB_TC_ABLATE=2"],
     "tcab3": ["-DACB_DEV", "-DACB_TC_ABLATE=3"],
     "tcab7": ["-DACB_DEV", "-DACB_TC_ABLATE=7"],
+    "dev": ["-DACB_DEV"],
+    "b3p16": ["-DACBG_PREP_WARPS=16"],
+    "epi16": ["-DACBG_EPI_WARPS=16"],
+    "epi12": ["-DACBG_EPI_WARPS=12"],
     "g2": ["-DACB_GROUPS=2", "-DACB_SINGLE_PLANE=0"],
     "g2sp": ["-DACB_GROUPS=2", "-DACB_SINGLE_PLANE=1"],
     "g4sp": ["-DACB_GROUPS=4", "-DACB_SINGLE_PLANE=1"],
@@ -108,17 +112,23 @@ def whisper_one(name, steps=50):
     fe = acb.WhisperLogMel("cuda")
     x = synth_batch(256, 480000, "cuda")
     out = torch.empty((256, 80, 3000), device="cuda")
-    for _ in range(5):
-        fe.forward(x, out=out)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        fe.forward(x, out=out)
-    e1.record()
-    torch.cuda.synchronize()
-    fe.check()
-    print(json.dumps({"variant": name, "whisper_ms": e0.elapsed_time(e1) / steps}), flush=True)
+    res = {"variant": name}
+    outs = {}
+    for kind in ("auto",):
+        for _ in range(5):
+            fe.forward(x, out=out)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fe.forward(x, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        fe.check()
+        res[kind + "_ms"] = e0.elapsed_time(e1) / steps
+        outs[kind] = out.clone()
+    res["checksum"] = float(outs["auto"].double().sum())
+    print(json.dumps(res), flush=True)
 
 
 def stft_one(name, steps=20):

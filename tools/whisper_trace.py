@@ -3,6 +3,8 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import audio_calm_b200 as acb
+if os.environ.get("ACB_LIB"):
+    acb._lib.LIB_PATH = os.environ["ACB_LIB"]
 fe = acb.WhisperLogMel("cuda")
 lib = acb._lib.load()
 lib.acb_dftgemm_set_trace.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
