@@ -92,6 +92,36 @@ __device__ __forceinline__ void group_fft_stage2(float2* buf, int r) {
 }
 __device__ __forceinline__ int buf_index(int k) { return (k & 31) + 33 * (k >> 5); }
 
+// Bank swizzle of the staged rows.  The R lanes of a group read samples base + R j + r (j = 0..31), and the 32 / R groups of a warp work on
+// frames whose bases differ by multiples of the hop (8 R floats for hop = n_fft / 4) -- a multiple of 16, 32 or 64 banks: unswizzled,
+// every sample load of the forward transform was an 8-way (R = 2, 4) or 4-way (R = 8) bank conflict.  XOR-ing the index of the
+// 2^s-float block a sample lies in into bits [log2 R, 5) of its position spreads the groups over all 32 banks and keeps 16-byte
+// groups together (R = 2 swaps their halves).  swz() is a bijection on indices (high bits into low bits only).
+template <int R>
+struct Swz {
+    static constexpr int kL = ilog2(R);
+    static constexpr int kS = R == 2 ? 5 : 3 + ilog2(R);
+    static constexpr int kHm = R == 2 ? 7 : (R >= 32 ? 0 : 32 / R - 1);
+    static __device__ __forceinline__ int mask_of(int n) { return ((n >> kS) & kHm) << kL; }
+    static __device__ __forceinline__ int at(int n) { return n ^ mask_of(n); }
+};
+
+// Stage `n` floats of `src` at the swizzled positions of s_x (16-byte accesses when the source allows)
+template <int R>
+__device__ __forceinline__ void stage_rows_swizzled(float* s_x, const float* __restrict__ src, int n, int tid) {
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        for (int i = tid; i < n / 4; i += kThreads) {
+            float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+            const int p = Swz<R>::at(4 * i);
+            if (p & 2) v = make_float4(v.z, v.w, v.x, v.y);          // R = 2: the halves of the group trade places
+            *reinterpret_cast<float4*>(s_x + (p & ~3)) = v;
+        }
+        for (int i = (n & ~3) + tid; i < n; i += kThreads) s_x[Swz<R>::at(i)] = src[i];
+    } else {
+        for (int i = tid; i < n; i += kThreads) s_x[Swz<R>::at(i)] = src[i];
+    }
+}
+
 struct SpectralSmem {
     int x, win, tw, buf, out, total_bytes;
 };
@@ -100,7 +130,7 @@ __host__ __device__ inline SpectralSmem spectral_smem(int R, int rows_per_cta, i
     const int N = 32 * R, n_freq = N / 2 + 1;
     SpectralSmem L;
     int off = 0;   // 4-byte words
-    L.x = off; off += (rows_per_cta * T + 3) & ~3;
+    L.x = off; off += (rows_per_cta * T + 255) & ~255;           // the swizzle permutes inside aligned 256-float blocks
     L.win = off; off += N;
     L.tw = off; off += 2 * N;
     L.buf = off; off += (kThreads / R) * (2 * 33 * R);           // per lane group: N complex values, index k1 + 33 * k2
@@ -123,16 +153,9 @@ __global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restr
     const long long row0 = (long long)blockIdx.x * rows_per_cta;
     const int n_rows = (int)min((long long)rows_per_cta, rows - row0);
 
-    // stage the rows, the window and the twiddles W_N^m = exp(-2 pi i m / N)
+    // stage the rows (bank-swizzled), the window and the twiddles W_N^m = exp(-2 pi i m / N)
     {
-        const float* src = x + row0 * T;
-        const int n = n_rows * T;
-        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-            for (int i = tid; i < n / 4; i += kThreads) reinterpret_cast<float4*>(s_x)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
-            for (int i = (n & ~3) + tid; i < n; i += kThreads) s_x[i] = src[i];
-        } else {
-            for (int i = tid; i < n; i += kThreads) s_x[i] = src[i];
-        }
+        stage_rows_swizzled<R>(s_x, x + row0 * T, n_rows * T, tid);
         for (int i = tid; i < N; i += kThreads) {
             s_win[i] = window[i];
             float sn, cs;
@@ -147,6 +170,14 @@ __global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restr
     const int total_frames = n_rows * n_frames;
     const int n_items = (total_frames + 1) / 2;         // two frames per complex transform
     const int n_iter = (n_items + kGroups - 1) / kGroups;
+    // every frame starts on a multiple of 8 R floats: the 8 R samples of a block share one swizzle mask (one XOR per load)
+    const bool blocked = R < 32 && T % (8 * R) == 0 && hop % (8 * R) == 0;
+    float wreg[32];                                     // this lane's window values, bit-reversed pair order (loop-invariant)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        wreg[2 * q] = s_win[R * brev5(q) + r];
+        wreg[2 * q + 1] = s_win[R * (brev5(q) + 1) + r];
+    }
     for (int it = 0; it < n_iter; ++it) {
         const int item = it * kGroups + g;
         const bool valid = item < n_items;
@@ -155,16 +186,56 @@ __global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restr
         const int row_a = valid ? qa / n_frames : 0, fa = valid ? qa - row_a * n_frames : 0;
         const int row_b = valid_b ? qb / n_frames : 0, fb = valid_b ? qb - row_b * n_frames : 0;
         if (valid) {
-            const float* pa = s_x + row_a * T + fa * hop;
-            const float* pb = s_x + row_b * T + fb * hop;
+            const int base_a = row_a * T + fa * hop, base_b = row_b * T + fb * hop;
             float2 pr[16], pi[16];
+            // frame b = frame a one hop later in the same row (the usual pair): with hop = 8 R its sample j is frame a's sample j + 8,
+            // so 40 loads serve both frames instead of 64
+            const bool shared_loads = blocked && valid_b && base_b == base_a + 8 * R;       // group-uniform
+            if (shared_loads) {
+                float raw[40];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {              // fft32_packed takes bit-reversed input: position q holds elements j0, j0 + 1
-                const int j0 = brev5(q);
-                const int n0 = R * j0 + r, n1 = R * (j0 + 1) + r;
-                const float w0 = s_win[n0], w1 = s_win[n1];
-                pr[q] = make_float2(pa[n0] * w0, pa[n1] * w1);
-                pi[q] = valid_b ? make_float2(pb[n0] * w0, pb[n1] * w1) : make_float2(0.f, 0.f);
+                for (int c = 0; c < 5; ++c) {
+                    const int t_c = base_a + 8 * R * c;
+                    const float* q_c = s_x + t_c + r;
+                    const int m_c = Swz<R>::mask_of(t_c);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) raw[8 * c + u] = q_c[(R * u) ^ m_c];
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {          // fft32_packed takes bit-reversed input: position q holds elements j0, j0 + 1
+                    const int j0 = brev5(q);
+                    pr[q] = make_float2(raw[j0] * wreg[2 * q], raw[j0 + 1] * wreg[2 * q + 1]);
+                    pi[q] = make_float2(raw[j0 + 8] * wreg[2 * q], raw[j0 + 9] * wreg[2 * q + 1]);
+                }
+            } else if (blocked) {                       // two unrelated frames (pairs across rows): per-block masks for each of them
+                float ra[32], rb[32];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int ta = base_a + 8 * R * c, tb = base_b + 8 * R * c;
+                    const float* qa_c = s_x + ta + r;
+                    const float* qb_c = s_x + tb + r;
+                    const int ma = Swz<R>::mask_of(ta), mb = Swz<R>::mask_of(tb);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        ra[8 * c + u] = qa_c[(R * u) ^ ma];
+                        rb[8 * c + u] = valid_b ? qb_c[(R * u) ^ mb] : 0.f;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int j0 = brev5(q);
+                    pr[q] = make_float2(ra[j0] * wreg[2 * q], ra[j0 + 1] * wreg[2 * q + 1]);
+                    pi[q] = make_float2(rb[j0] * wreg[2 * q], rb[j0 + 1] * wreg[2 * q + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int j0 = brev5(q);
+                    const int n0 = R * j0 + r, n1 = R * (j0 + 1) + r;
+                    pr[q] = make_float2(s_x[Swz<R>::at(base_a + n0)] * wreg[2 * q], s_x[Swz<R>::at(base_a + n1)] * wreg[2 * q + 1]);
+                    pi[q] = valid_b ? make_float2(s_x[Swz<R>::at(base_b + n0)] * wreg[2 * q], s_x[Swz<R>::at(base_b + n1)] * wreg[2 * q + 1])
+                                    : make_float2(0.f, 0.f);
+                }
             }
             group_fft_stage1<R>(pr, pi, buf, s_tw, r);
         }
