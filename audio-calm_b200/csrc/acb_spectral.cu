@@ -21,7 +21,10 @@ int fail(int code, const std::string& msg);   // acb_kernels.cu: sets the thread
 }
 
 #ifndef ACB_STFT_RPC
-#define ACB_STFT_RPC 16      // rows staged per CTA (upper bound)
+#define ACB_STFT_RPC 32      // rows staged per CTA (upper bound)
+#endif
+#ifndef ACB_STFT_DIRECT
+#define ACB_STFT_DIRECT 1    // 1: magnitudes go straight to global memory (L2 merges the 4-byte stores of a row block); 0: staged in shared memory
 #endif
 
 namespace acb_spectral {
@@ -134,7 +137,7 @@ __host__ __device__ inline SpectralSmem spectral_smem(int R, int rows_per_cta, i
     L.win = off; off += N;
     L.tw = off; off += 2 * N;
     L.buf = off; off += (kThreads / R) * (2 * 33 * R);           // per lane group: N complex values, index k1 + 33 * k2
-    L.out = off; off += rows_per_cta * n_freq * n_frames;
+    L.out = off; if (!ACB_STFT_DIRECT) off += rows_per_cta * n_freq * n_frames;
     L.total_bytes = off * 4;
     return L;
 }
@@ -243,8 +246,9 @@ __global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restr
         if (valid) group_fft_stage2<R>(buf, r);
         __syncwarp();
         if (valid) {                                    // separate the two real spectra, magnitudes
-            float* oa = s_out + (size_t)row_a * kFreq * n_frames + fa;
-            float* ob = s_out + (size_t)row_b * kFreq * n_frames + fb;
+            float* obase = ACB_STFT_DIRECT ? out + row0 * kFreq * n_frames : s_out;
+            float* oa = obase + (size_t)row_a * kFreq * n_frames + fa;
+            float* ob = obase + (size_t)row_b * kFreq * n_frames + fb;
             for (int k = r; k < kFreq; k += R) {
                 const int kc = (N - k) & (N - 1);
                 const float2 z = buf[(k & 31) + 33 * (k >> 5)], zc = buf[(kc & 31) + 33 * (kc >> 5)];
@@ -255,6 +259,7 @@ __global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restr
         }
         __syncwarp();
     }
+    if (ACB_STFT_DIRECT) return;
     __syncthreads();
     {   // the CTA's rows are one contiguous span of the output
         float* dst = out + row0 * kFreq * n_frames;
@@ -273,7 +278,10 @@ static int launch(const float* x, int64_t rows, int T, int hop, int n_frames, co
     int dev = 0, optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return fail(ACB_ERR_CUDA, "acb_stft_mag: cannot query the device");
-    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(ACB_STFT_RPC, 16384 / T));
+    // rows per CTA: 16 (measured best for 5-13 frames per row), doubled while a CTA's frame pairs would leave lane groups idle
+    // (one frame per row at n_fft = T), halved while the footprint is large
+    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(16, ACB_STFT_RPC), 16384 / T));
+    while (rpc < ACB_STFT_RPC && (rpc * n_frames + 1) / 2 < kThreads / R && 2 * rpc <= 16384 / T) rpc <<= 1;
     while (rpc > 1 && spectral_smem(R, rpc, T, n_frames).total_bytes > std::min(optin, 160 * 1024)) rpc >>= 1;
     const SpectralSmem L = spectral_smem(R, rpc, T, n_frames);
     if (L.total_bytes > optin)
@@ -421,7 +429,7 @@ static int launch_backward(const float* x, const float* grad_mag, int64_t rows, 
     int dev = 0, optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return fail(ACB_ERR_CUDA, "acb_stft_mag_backward: cannot query the device");
-    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(ACB_STFT_RPC, 16384 / T));
+    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, 16384 / T));
     while (rpc > 1 && spectral_bwd_smem(R, rpc, T, n_frames).total_bytes > std::min(optin, 160 * 1024)) rpc >>= 1;
     const SpectralBwdSmem L = spectral_bwd_smem(R, rpc, T, n_frames);
     if (L.total_bytes > optin)

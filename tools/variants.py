@@ -17,6 +17,7 @@ OUT = os.path.join(ROOT, "tools", "_variants")
 
 VARIANTS = {
     "base": [],
+    "sstaged": ["-DACB_STFT_DIRECT=0"],
     "rpc4": ["-DACB_STFT_RPC=4"],
     "rpc8": ["-DACB_STFT_RPC=8"],
     "rpc32": ["-DACB_STFT_RPC=32"],
