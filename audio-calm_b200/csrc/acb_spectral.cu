@@ -125,6 +125,62 @@ __device__ __forceinline__ void stage_rows_swizzled(float* s_x, const float* __r
     }
 }
 
+// The windowed samples of one frame pair in the packed, bit-reversed register order fft32_packed takes (position q holds elements
+// j0 = brev5(q) and j0 + 1 of the lane's stride-R sequence): frame a in pr, frame b in pi.  `blocked`: every frame starts on a multiple
+// of 8 R floats, so the 8 R samples of a block share one swizzle mask (one XOR per load); frame b = frame a one hop later in the same
+// row (the usual pair, hop = 8 R) then needs only 8 loads of its own: its sample j is frame a's sample j + 8.
+template <int R>
+__device__ __forceinline__ void load_pair_windowed(const float* s_x, int base_a, int base_b, bool valid_b, bool blocked, int r, const float (&wreg)[32],
+                                                   float2 (&pr)[16], float2 (&pi)[16]) {
+    const bool shared_loads = blocked && valid_b && base_b == base_a + 8 * R;       // group-uniform
+    if (shared_loads) {
+        float raw[40];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            const int t_c = base_a + 8 * R * c;
+            const float* q_c = s_x + t_c + r;
+            const int m_c = Swz<R>::mask_of(t_c);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) raw[8 * c + u] = q_c[(R * u) ^ m_c];
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int j0 = brev5(q);
+            pr[q] = make_float2(raw[j0] * wreg[2 * q], raw[j0 + 1] * wreg[2 * q + 1]);
+            pi[q] = make_float2(raw[j0 + 8] * wreg[2 * q], raw[j0 + 9] * wreg[2 * q + 1]);
+        }
+    } else if (blocked) {                       // two unrelated frames (pairs across rows): per-block masks for each of them
+        float ra[32], rb[32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int ta = base_a + 8 * R * c, tb = base_b + 8 * R * c;
+            const float* qa_c = s_x + ta + r;
+            const float* qb_c = s_x + tb + r;
+            const int ma = Swz<R>::mask_of(ta), mb = Swz<R>::mask_of(tb);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                ra[8 * c + u] = qa_c[(R * u) ^ ma];
+                rb[8 * c + u] = valid_b ? qb_c[(R * u) ^ mb] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int j0 = brev5(q);
+            pr[q] = make_float2(ra[j0] * wreg[2 * q], ra[j0 + 1] * wreg[2 * q + 1]);
+            pi[q] = make_float2(rb[j0] * wreg[2 * q], rb[j0 + 1] * wreg[2 * q + 1]);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int j0 = brev5(q);
+            const int n0 = R * j0 + r, n1 = R * (j0 + 1) + r;
+            pr[q] = make_float2(s_x[Swz<R>::at(base_a + n0)] * wreg[2 * q], s_x[Swz<R>::at(base_a + n1)] * wreg[2 * q + 1]);
+            pi[q] = valid_b ? make_float2(s_x[Swz<R>::at(base_b + n0)] * wreg[2 * q], s_x[Swz<R>::at(base_b + n1)] * wreg[2 * q + 1])
+                            : make_float2(0.f, 0.f);
+        }
+    }
+}
+
 struct SpectralSmem {
     int x, win, tw, buf, out, total_bytes;
 };
@@ -191,55 +247,7 @@ __global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restr
         if (valid) {
             const int base_a = row_a * T + fa * hop, base_b = row_b * T + fb * hop;
             float2 pr[16], pi[16];
-            // frame b = frame a one hop later in the same row (the usual pair): with hop = 8 R its sample j is frame a's sample j + 8,
-            // so 40 loads serve both frames instead of 64
-            const bool shared_loads = blocked && valid_b && base_b == base_a + 8 * R;       // group-uniform
-            if (shared_loads) {
-                float raw[40];
-#pragma unroll
-                for (int c = 0; c < 5; ++c) {
-                    const int t_c = base_a + 8 * R * c;
-                    const float* q_c = s_x + t_c + r;
-                    const int m_c = Swz<R>::mask_of(t_c);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) raw[8 * c + u] = q_c[(R * u) ^ m_c];
-                }
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {          // fft32_packed takes bit-reversed input: position q holds elements j0, j0 + 1
-                    const int j0 = brev5(q);
-                    pr[q] = make_float2(raw[j0] * wreg[2 * q], raw[j0 + 1] * wreg[2 * q + 1]);
-                    pi[q] = make_float2(raw[j0 + 8] * wreg[2 * q], raw[j0 + 9] * wreg[2 * q + 1]);
-                }
-            } else if (blocked) {                       // two unrelated frames (pairs across rows): per-block masks for each of them
-                float ra[32], rb[32];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int ta = base_a + 8 * R * c, tb = base_b + 8 * R * c;
-                    const float* qa_c = s_x + ta + r;
-                    const float* qb_c = s_x + tb + r;
-                    const int ma = Swz<R>::mask_of(ta), mb = Swz<R>::mask_of(tb);
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        ra[8 * c + u] = qa_c[(R * u) ^ ma];
-                        rb[8 * c + u] = valid_b ? qb_c[(R * u) ^ mb] : 0.f;
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int j0 = brev5(q);
-                    pr[q] = make_float2(ra[j0] * wreg[2 * q], ra[j0 + 1] * wreg[2 * q + 1]);
-                    pi[q] = make_float2(rb[j0] * wreg[2 * q], rb[j0 + 1] * wreg[2 * q + 1]);
-                }
-            } else {
-#pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const int j0 = brev5(q);
-                    const int n0 = R * j0 + r, n1 = R * (j0 + 1) + r;
-                    pr[q] = make_float2(s_x[Swz<R>::at(base_a + n0)] * wreg[2 * q], s_x[Swz<R>::at(base_a + n1)] * wreg[2 * q + 1]);
-                    pi[q] = valid_b ? make_float2(s_x[Swz<R>::at(base_b + n0)] * wreg[2 * q], s_x[Swz<R>::at(base_b + n1)] * wreg[2 * q + 1])
-                                    : make_float2(0.f, 0.f);
-                }
-            }
+            load_pair_windowed<R>(s_x, base_a, base_b, valid_b, blocked, r, wreg, pr, pi);
             group_fft_stage1<R>(pr, pi, buf, s_tw, r);
         }
         __syncwarp();
@@ -307,8 +315,8 @@ __host__ __device__ inline SpectralBwdSmem spectral_bwd_smem(int R, int rows_per
     const int N = 32 * R, n_freq = N / 2 + 1;
     SpectralBwdSmem L;
     int off = 0;
-    L.x = off; off += (rows_per_cta * T + 3) & ~3;
-    L.gx = off; off += (rows_per_cta * T + 3) & ~3;
+    L.x = off; off += (rows_per_cta * T + 255) & ~255;
+    L.gx = off; off += (rows_per_cta * T + 255) & ~255;
     L.g = off; off += (rows_per_cta * n_freq * n_frames + 3) & ~3;
     L.win = off; off += N;
     L.tw = off; off += 2 * N;
@@ -332,8 +340,18 @@ __global__ void __launch_bounds__(kThreads) stft_mag_backward_kernel(const float
     const int tid = threadIdx.x;
     const long long row0 = (long long)blockIdx.x * rows_per_cta;
     const int n_rows = (int)min((long long)rows_per_cta, rows - row0);
-    for (int i = tid; i < n_rows * T; i += kThreads) { s_x[i] = x[row0 * T + i]; s_gx[i] = 0.f; }
-    for (int i = tid; i < n_rows * kFreq * n_frames; i += kThreads) s_g[i] = grad_mag[row0 * kFreq * n_frames + i];
+    stage_rows_swizzled<R>(s_x, x + row0 * T, n_rows * T, tid);               // s_x and s_gx share the bank swizzle of the forward kernel
+    for (int i = tid; i < ((n_rows * T + 255) & ~255); i += kThreads) s_gx[i] = 0.f;     // the swizzle permutes inside aligned blocks: clear whole blocks
+    {
+        const float* gsrc = grad_mag + row0 * kFreq * n_frames;
+        const int n = n_rows * kFreq * n_frames;
+        if ((reinterpret_cast<uintptr_t>(gsrc) & 15) == 0) {
+            for (int i = tid; i < n / 4; i += kThreads) reinterpret_cast<float4*>(s_g)[i] = __ldg(reinterpret_cast<const float4*>(gsrc) + i);
+            for (int i = (n & ~3) + tid; i < n; i += kThreads) s_g[i] = gsrc[i];
+        } else {
+            for (int i = tid; i < n; i += kThreads) s_g[i] = gsrc[i];
+        }
+    }
     for (int i = tid; i < N; i += kThreads) {
         s_win[i] = window[i];
         float sn, cs;
@@ -347,6 +365,13 @@ __global__ void __launch_bounds__(kThreads) stft_mag_backward_kernel(const float
     const int total_frames = n_rows * n_frames;
     const int n_items = (total_frames + 1) / 2;
     const int n_iter = (n_items + kGroups - 1) / kGroups;
+    const bool blocked = R < 32 && T % (8 * R) == 0 && hop % (8 * R) == 0;
+    float wreg[32];                                     // this lane's window values, bit-reversed pair order (loop-invariant)
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        wreg[2 * q] = s_win[R * brev5(q) + r];
+        wreg[2 * q + 1] = s_win[R * (brev5(q) + 1) + r];
+    }
     for (int it = 0; it < n_iter; ++it) {
         const int item = it * kGroups + g;
         const bool valid = item < n_items;
@@ -356,23 +381,14 @@ __global__ void __launch_bounds__(kThreads) stft_mag_backward_kernel(const float
         const int row_b = valid_b ? qb / n_frames : 0, fb = valid_b ? qb - row_b * n_frames : 0;
         float2 pr[16], pi[16];
         if (valid) {                                    // forward transform of the pair, as in stft_mag_kernel
-            const float* pa = s_x + row_a * T + fa * hop;
-            const float* pb = s_x + row_b * T + fb * hop;
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const int j0 = brev5(q);
-                const int n0 = R * j0 + r, n1 = R * (j0 + 1) + r;
-                const float w0 = s_win[n0], w1 = s_win[n1];
-                pr[q] = make_float2(pa[n0] * w0, pa[n1] * w1);
-                pi[q] = valid_b ? make_float2(pb[n0] * w0, pb[n1] * w1) : make_float2(0.f, 0.f);
-            }
+            load_pair_windowed<R>(s_x, row_a * T + fa * hop, row_b * T + fb * hop, valid_b, blocked, r, wreg, pr, pi);
             group_fft_stage1<R>(pr, pi, buf, s_tw, r);
         }
         __syncwarp();
         if (valid) group_fft_stage2<R>(buf, r);
         __syncwarp();
         if (valid) {                                    // h = g conj(X) / |X| per frame; C = H_A + i H_B written over Z in place
-            const float* ga = s_g + (size_t)row_a * kFreq * n_frames + fa;
+            const float* ga = s_g + (size_t)row_a * kFreq * n_frames + fa;       // staged: reading them where they lie in global memory was measured 40 % slower
             const float* gb = s_g + (size_t)row_b * kFreq * n_frames + fb;
             for (int k = r; k < kFreq; k += R) {
                 const int kc = (N - k) & (N - 1);
@@ -408,19 +424,18 @@ __global__ void __launch_bounds__(kThreads) stft_mag_backward_kernel(const float
         if (valid) group_fft_stage2<R>(buf, r);
         __syncwarp();
         if (valid) {                                    // windowed overlap-add into the rows' gradients
-            float* da = s_gx + row_a * T + fa * hop;
-            float* db = s_gx + row_b * T + fb * hop;
+            const int base_a = row_a * T + fa * hop, base_b = row_b * T + fb * hop;
             for (int n = r; n < N; n += R) {
                 const float2 y = buf[buf_index(n)];
                 const float w = s_win[n];
-                atomicAdd(da + n, w * y.x);
-                if (valid_b) atomicAdd(db + n, w * y.y);
+                atomicAdd(s_gx + Swz<R>::at(base_a + n), w * y.x);
+                if (valid_b) atomicAdd(s_gx + Swz<R>::at(base_b + n), w * y.y);
             }
         }
         __syncwarp();
     }
     __syncthreads();
-    for (int i = tid; i < n_rows * T; i += kThreads) grad_x[row0 * T + i] = s_gx[i];
+    for (int i = tid; i < n_rows * T; i += kThreads) grad_x[row0 * T + i] = s_gx[Swz<R>::at(i)];
 }
 
 template <int R>

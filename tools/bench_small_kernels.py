@@ -116,6 +116,35 @@ def main():
              xs.numel() * 4 + o.numel() * 4, f"[1024, 80, 256] fp32 -> [1024, 80, {n_fft // 2 + 1}, {frames}] magnitudes (read + write); "
              f"torch.stft + abs on the same device (the reference's _stft_mag, cuFFT): {ref_ms:.4f} ms")
 
+    # backward of the same op (the loss is trained through): ours = recomputed transform + one more FFT per frame pair + overlap-add
+    # in shared memory; the reference = torch autograd through torch.stft(...).abs() (cuFFT C2R + elementwise + col2im)
+    for n_fft, hop in spectral.STFT_LOSS_SPECS:
+        frames = spectral.stft_frames(256, n_fft, hop)
+        w = spectral._window(n_fft, xs.device)
+        g = torch.randn((1024, 80, n_fft // 2 + 1, frames), device="cuda")
+        gx = torch.empty_like(xs)
+        x2 = xs.reshape(-1, 256).clone().requires_grad_(True)
+        g2 = g.reshape(-1, n_fft // 2 + 1, frames)
+
+        def torch_fwd_bwd():
+            x2.grad = None
+            torch.stft(x2, n_fft=n_fft, hop_length=hop, win_length=n_fft, window=w, return_complex=True, normalized=False, center=False).abs().backward(g2)
+
+        for _ in range(3):
+            torch_fwd_bwd()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            torch_fwd_bwd()
+        e1.record()
+        torch.cuda.synchronize()
+        ref_ms = e0.elapsed_time(e1) / 10
+        emit(f"stft_mag_backward_kernel (n_fft {n_fft}, hop {hop})",
+             timed(lambda: lib.acb_stft_mag_backward(xs.data_ptr(), g.data_ptr(), 1024 * 80, 256, n_fft, hop, w.data_ptr(), gx.data_ptr(), cs())),
+             xs.numel() * 4 * 2 + g.numel() * 4, f"[1024, 80, 256] features + [1024, 80, {n_fft // 2 + 1}, {frames}] magnitude gradients -> feature gradients "
+             f"(2 reads + 1 write); torch autograd forward + backward through torch.stft(...).abs() on the same device: {ref_ms:.4f} ms (eager, includes its forward)")
+
 
 if __name__ == "__main__":
     main()
