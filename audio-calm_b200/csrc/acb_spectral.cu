@@ -23,6 +23,9 @@ int fail(int code, const std::string& msg);   // acb_kernels.cu: sets the thread
 #ifndef ACB_STFT_RPC
 #define ACB_STFT_RPC 32      // rows staged per CTA (upper bound)
 #endif
+#ifndef ACB_STFT_BWD_RPC
+#define ACB_STFT_BWD_RPC 16  // rows per CTA of the backward kernel
+#endif
 #ifndef ACB_STFT_DIRECT
 #define ACB_STFT_DIRECT 1    // 1: magnitudes go straight to global memory (L2 merges the 4-byte stores of a row block); 0: staged in shared memory
 #endif
@@ -444,7 +447,9 @@ static int launch_backward(const float* x, const float* grad_mag, int64_t rows, 
     int dev = 0, optin = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return fail(ACB_ERR_CUDA, "acb_stft_mag_backward: cannot query the device");
-    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(16, 16384 / T));
+    // rows per CTA: 16, or 8 when a row has many frames (measured at T = 256: 13 frames per row run 25 % faster in one pass over 8 rows than
+    // in two passes over 16 with twice the shared memory)
+    int rpc = (int)std::max<int64_t>(1, std::min<int64_t>(n_frames >= 8 ? ACB_STFT_BWD_RPC / 2 : ACB_STFT_BWD_RPC, 16384 / T));
     while (rpc > 1 && spectral_bwd_smem(R, rpc, T, n_frames).total_bytes > std::min(optin, 160 * 1024)) rpc >>= 1;
     const SpectralBwdSmem L = spectral_bwd_smem(R, rpc, T, n_frames);
     if (L.total_bytes > optin)

@@ -18,6 +18,9 @@ OUT = os.path.join(ROOT, "tools", "_variants")
 VARIANTS = {
     "base": [],
     "sstaged": ["-DACB_STFT_DIRECT=0"],
+    "bwd8": ["-DACB_STFT_BWD_RPC=8"],
+    "bwd4": ["-DACB_STFT_BWD_RPC=4"],
+    "bwd32": ["-DACB_STFT_BWD_RPC=32"],
     "rpc4": ["-DACB_STFT_RPC=4"],
     "rpc8": ["-DACB_STFT_RPC=8"],
     "rpc32": ["-DACB_STFT_RPC=32"],
@@ -157,6 +160,17 @@ def stft_one(name, steps=20):
         ms = e0.elapsed_time(e1) / steps
         res[f"ms_{n_fft}"] = ms
         res[f"frac_{n_fft}"] = (xs.numel() + o.numel()) * 4 / (ms * 1e-3) / 1e9 / 6537.6
+        gx = torch.empty_like(xs)
+        callb = lambda: lib.acb_stft_mag_backward(xs.data_ptr(), o.data_ptr(), 1024 * 80, 256, n_fft, hop, w.data_ptr(), gx.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            callb()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            callb()
+        e1.record()
+        torch.cuda.synchronize()
+        res[f"bwd_ms_{n_fft}"] = e0.elapsed_time(e1) / steps
     print(json.dumps(res), flush=True)
 
 
