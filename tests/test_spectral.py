@@ -70,7 +70,8 @@ def test_kernel_matches_the_reference_goldens(g):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_fft,hop,T,B,C", [(64, 16, 256, 3, 80), (128, 32, 256, 3, 80), (256, 64, 256, 3, 80), (256, 64, 1000, 2, 5),
-                                             (512, 128, 777, 1, 3), (1024, 256, 2048, 2, 2), (64, 7, 100, 1, 1), (128, 32, 128, 33, 1)])
+                                             (512, 128, 777, 1, 3), (1024, 256, 2048, 2, 2), (64, 7, 100, 1, 1), (128, 32, 128, 33, 1),
+                                             (512, 128, 1024, 2, 3), (64, 16, 272, 5, 7), (128, 32, 96 * 32, 1, 3)])
 def test_kernel_matches_the_oracle(n_fft, hop, T, B, C):
     rng = np.random.default_rng(n_fft + T)
     x = (rng.normal(-6.0, 3.0, (B, C, T))).astype(np.float32)                        # log-mel-like values
@@ -96,7 +97,8 @@ def test_training_batch_size():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n_fft,hop,T", [(64, 16, 256), (128, 32, 256), (256, 64, 256), (256, 64, 700), (512, 128, 777), (64, 7, 100)])
+@pytest.mark.parametrize("n_fft,hop,T", [(64, 16, 256), (128, 32, 256), (256, 64, 256), (256, 64, 700), (512, 128, 777), (64, 7, 100),
+                                         (512, 128, 1024), (64, 16, 272)])
 def test_backward_matches_autograd_through_torch_stft(n_fft, hop, T):
     """The adjoint kernel against torch's own autograd through torch.stft(...).abs() (what stft_loss differentiates in the reference)."""
     g = torch.Generator(device="cuda").manual_seed(n_fft + T)
