@@ -309,6 +309,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--cv_tsv", type=str, default=None)
     p.add_argument("--num_gpus", type=int, default=torch.cuda.device_count())
     p.add_argument("--workers_per_gpu", type=int, default=4, help="decode threads per GPU process (the reference spawns this many processes)")
+    p.add_argument("--procs_per_gpu", type=int, default=1,
+                   help="processes per GPU, each with --workers_per_gpu decode threads (decoding and torch.save hold the interpreter lock: "
+                        "more processes scale the host side like the reference's num_gpus * workers_per_gpu processes do, rank %% num_gpus "
+                        "picks the device, process_dataset.py:256-275)")
     p.add_argument("--force", action="store_true")
     return p
 
@@ -329,8 +333,9 @@ def main(argv: Optional[Sequence[str]] = None) -> int:
     ctx = mp.get_context("spawn")                                                             # process_dataset.py:267
     queue = ctx.Manager().Queue()
     procs = []
-    for rank in range(args.num_gpus):                                                          # contiguous ceil(N / procs) chunks (:256-259)
-        shard = contiguous_shard(len(files), rank, args.num_gpus)
+    n_procs = args.num_gpus * max(1, int(getattr(args, "procs_per_gpu", 1)))
+    for rank in range(n_procs):                                                                # contiguous ceil(N / procs) chunks (:256-259)
+        shard = contiguous_shard(len(files), rank, n_procs)
         if len(shard) == 0:
             continue
         p = ctx.Process(target=worker_process, args=(rank, rank % args.num_gpus, [files[i] for i in shard], args, cv_mapping, queue))

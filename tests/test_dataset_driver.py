@@ -32,6 +32,7 @@ def test_cli_flags_match_the_reference():
                                       "--num_gpus", "2", "--workers_per_gpu", "3", "--cv_tsv", "x.tsv", "--vae_ckpt", "c"])
     assert (a.dataset_name, a.in_dir, a.out_dir, a.mel_only, a.force, a.num_gpus, a.workers_per_gpu, a.cv_tsv, a.vae_ckpt) == \
            ("libritts", "i", "o", True, True, 2, 3, "x.tsv", "c")
+    assert a.procs_per_gpu == 1                                                           # extension flag: one process per GPU unless asked
 
 
 def test_scan_and_output_paths(tmp_path):
@@ -161,6 +162,24 @@ def test_driver_mel_only_matches_reference_pipeline(tmp_path):
     stamp = {rel: os.path.getmtime(str(out / rel.replace(".wav", ".pt"))) for rel in clips}
     pd.ShardRunner(args, 0).run(pd.scan_files(str(root)))
     assert stamp == {rel: os.path.getmtime(str(out / rel.replace(".wav", ".pt"))) for rel in clips}
+
+
+@pytest.mark.gpu
+def test_cli_with_two_processes_on_one_gpu(tmp_path, capsys):
+    """The command line end to end (spawned workers, progress queue, exit code) with --procs_per_gpu 2: contiguous shards over
+    num_gpus * procs_per_gpu processes, rank % num_gpus picks the device (process_dataset.py:256-275)."""
+    fe_tables = acb.tables.calm_tables()
+    window, fb = fe_tables[0].numpy(), fe_tables[1].numpy()
+    root, out = tmp_path / "in", tmp_path / "out"
+    clips = {f"s{i % 2}/c{i % 3}/u{i}.wav": o.synth_clip(12000 + 997 * i, 40 + i) for i in range(7)}
+    for rel, x in clips.items():
+        _write_wav(str(root / rel), x)
+    rc = pd.main(["--dataset_name", "librispeech", "--in_dir", str(root), "--out_dir", str(out), "--mel_only", "--num_gpus", "1",
+                  "--procs_per_gpu", "2", "--workers_per_gpu", "2"])
+    assert rc == 0 and "Done: 7/7 files" in capsys.readouterr().out
+    for rel, x in clips.items():
+        mel = torch.load(str(out / rel.replace(".wav", ".pt")))["mel"]
+        assert float(np.max(np.abs(mel.numpy() - o.dataset_mel(x[None], window, fb)))) < 1e-4
 
 
 @pytest.mark.gpu

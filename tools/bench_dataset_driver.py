@@ -21,11 +21,29 @@ import numpy as np
 import torch
 
 
+def _proc(rank, n_procs, files, a, decode_threads, start, done):
+    """One of several driver processes on the same GPU: contiguous shard (process_dataset.py:256-259), warm-up, common start."""
+    sys.path.insert(0, ROOT)
+    import torch as _torch
+    from audio_calm_b200.preprocess import process_dataset as pd
+    from audio_calm_b200.sharding import contiguous_shard
+    _torch.set_num_threads(1)
+    mine = [files[i] for i in contiguous_shard(len(files), rank, n_procs)]
+    warm = types.SimpleNamespace(**{**vars(a), "out_dir": a.out_dir + f"_warm{rank}"})
+    pd.ShardRunner(warm, 0, decode_threads=decode_threads).run(mine[:16])
+    shutil.rmtree(warm.out_dir, ignore_errors=True)
+    runner = pd.ShardRunner(a, 0, decode_threads=decode_threads)
+    start.wait()
+    runner.run(mine)
+    done.put((rank, len(mine), len(runner.errors)))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--files", type=int, default=2000)
     ap.add_argument("--seconds", type=float, default=10.0)
     ap.add_argument("--decode-threads", type=int, default=8)
+    ap.add_argument("--procs", type=int, default=1, help="driver processes sharing the GPU (--procs_per_gpu of the driver)")
     args = ap.parse_args()
     from scipy.io import wavfile
     from audio_calm_b200.preprocess import process_dataset as pd
@@ -46,6 +64,26 @@ def main():
         a = types.SimpleNamespace(dataset_name="librispeech", in_dir=in_dir, out_dir=out_dir, vae_ckpt=None, mel_only=True, cv_tsv=None,
                                   num_gpus=1, workers_per_gpu=args.decode_threads, force=False)
         torch.set_num_threads(1)
+        if args.procs > 1:
+            import multiprocessing as mp
+            ctx = mp.get_context("spawn")
+            start, done = ctx.Barrier(args.procs + 1), ctx.Queue()
+            ps = [ctx.Process(target=_proc, args=(r, args.procs, files, a, args.decode_threads, start, done)) for r in range(args.procs)]
+            for p in ps:
+                p.start()
+            start.wait()
+            t0 = time.perf_counter()
+            res = [done.get() for _ in ps]
+            dt = time.perf_counter() - t0
+            for p in ps:
+                p.join()
+            written = sum(len(fs) for _, _, fs in os.walk(out_dir))
+            print(json.dumps({"tool": "bench_dataset_driver", "files": len(files), "written": written, "errors": sum(r[2] for r in res),
+                              "audio_hours": audio_s / 3600, "seconds": dt, "files_per_s": len(files) / dt,
+                              "audio_hours_per_s": audio_s / 3600 / dt, "procs": args.procs, "decode_threads": args.decode_threads,
+                              "host_cpus": os.cpu_count(), "payload": '{"mel": FloatTensor[80, T4]} per file, torch.save',
+                              "note": "several driver processes on ONE GPU (--procs_per_gpu), contiguous shards, timed from a common start to the last one done"}))
+            return
         runner = pd.ShardRunner(a, 0, decode_threads=args.decode_threads)
         runner.run(files[:32])                              # warm-up: kernels, allocator, thread pools
         shutil.rmtree(out_dir, ignore_errors=True)
