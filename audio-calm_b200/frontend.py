@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -58,6 +58,10 @@ class RaggedBatch:
     offsets: torch.Tensor    # [B] int64 (device)
     lengths: torch.Tensor    # [B] int64 (device)
     lengths_host: np.ndarray  # [B] int64
+    # launch plans derived from the lengths alone, built on first use and kept with the batch (key: n_fft, hop, pad_multiple):
+    # frame counts (host + device) and the per-clip tile prefix sums the kernel walks.  A batch that is forwarded more than once
+    # (peak pass + features, statistics + features, several epochs over cached batches) pays for them once.
+    plans: dict = field(default_factory=dict, repr=False, compare=False)
 
 
 def pack_clips(clips: Sequence[torch.Tensor], device: torch.device) -> RaggedBatch:
@@ -238,14 +242,30 @@ class LogMelFrontend:
         are set to ``fill_value`` (the training collator's ``audio_pad_val = 0.0``, train/train_calm.py:181,213-215).
         Reflection happens at each clip's own ends."""
         self._check_wav(batch.wav)
-        lens = np.ascontiguousarray(batch.lengths_host, dtype=np.int64)
-        B = int(lens.shape[0])
-        if B and int(lens.min()) <= self.n_fft // 2:
-            self.frames_for_length(int(lens.min()))          # raises like the reference's reflect padding
-        frames = 1 + lens // self.hop
-        frames = (frames + pad_multiple - 1) // pad_multiple * pad_multiple
-        cap = int(frame_capacity) if frame_capacity is not None else (int(frames.max()) if B else 0)
-        if B and cap < int(frames.max()):
+        key = (self.n_fft, self.hop, int(pad_multiple))
+        plan = batch.plans.get(key)
+        if plan is None:
+            lens = np.ascontiguousarray(batch.lengths_host, dtype=np.int64)
+            B = int(lens.shape[0])
+            if B and int(lens.min()) <= self.n_fft // 2:
+                self.frames_for_length(int(lens.min()))          # raises like the reference's reflect padding
+            frames = 1 + lens // self.hop
+            frames = (frames + pad_multiple - 1) // pad_multiple * pad_multiple
+            frames_t = torch.from_numpy(frames).to(self.device, non_blocking=True)
+            tile_start_t, n_tiles = None, 0
+            if B:
+                # only the frames that exist are visited: per-clip tile counts differ -> host plan (prefix sums) shipped to the device.
+                # For padded outputs the group that stores a clip's last tile also fills the rest of the row with fill_value.
+                tile_start = np.zeros(B + 1, dtype=np.int32)
+                n_tiles = int(self._lib.acb_plan_tiles(lens.ctypes.data, B, self.n_fft, self.hop, 0, tile_start.ctypes.data))
+                if n_tiles < 0:
+                    _lib.check(n_tiles, "acb_plan_tiles")
+                tile_start_t = torch.from_numpy(tile_start).to(self.device, non_blocking=True)
+            plan = (B, int(frames.max()) if B else 0, int(frames.sum()), frames_t, tile_start_t, n_tiles)
+            batch.plans[key] = plan
+        B, max_frames, sum_frames, frames_t, tile_start_t, n_tiles = plan
+        cap = int(frame_capacity) if frame_capacity is not None else max_frames
+        if B and cap < max_frames:
             raise ValueError("frame_capacity smaller than the longest clip's padded frame count")
         shape = (B, self.n_mels, cap) if layout == "mel_major" else (B, cap, self.n_mels)
         if stats_only:
@@ -256,20 +276,12 @@ class LogMelFrontend:
             out = torch.empty(shape, dtype=out_dtype, device=self.device)
         elif tuple(out.shape) != shape or not out.is_contiguous() or out.device != self.device:
             raise ValueError(f"out must be a contiguous {shape} tensor on {self.device}")
-        frames_t = torch.from_numpy(frames).to(self.device, non_blocking=True)
         if B == 0:
             return out, frames_t
         a = LogmelArgs()
         a.wav = batch.wav.data_ptr()
         a.clip_offset = batch.offsets.data_ptr()
         a.clip_length = batch.lengths.data_ptr()
-        # only the frames that exist are visited: per-clip tile counts differ -> host plan (prefix sums) shipped to the device.
-        # For padded outputs the group that stores a clip's last tile also fills the rest of the row with fill_value.
-        tile_start = np.zeros(B + 1, dtype=np.int32)
-        n_tiles = int(self._lib.acb_plan_tiles(lens.ctypes.data, B, self.n_fft, self.hop, 0, tile_start.ctypes.data))
-        if n_tiles < 0:
-            _lib.check(n_tiles, "acb_plan_tiles")
-        tile_start_t = torch.from_numpy(tile_start).to(self.device, non_blocking=True)
         a.tile_start = tile_start_t.data_ptr()
         a.n_clips = B
         a.n_tiles = n_tiles
@@ -279,8 +291,8 @@ class LogMelFrontend:
         _lib.check(self._lib.acb_logmel_forward(self._handle, ctypes.byref(a), _stream_ptr(self.device)), "acb_logmel_forward")
         self.launches += 2 if moments is not None else 1
         if moments is not None:
-            moments.frames += int(frames.sum())
-        del keep, tile_start_t
+            moments.frames += sum_frames
+        del keep
         return out, frames_t
 
     # ------------------------------------------------------------------ peak / process_audio_chunk

@@ -582,3 +582,23 @@ def test_fuzz_shapes_against_oracle(fe):
             ref = oracle_mel(fe, w, pad=pad)
             assert y[i].shape == ref.shape, (L, pad)
             assert float(np.max(np.abs(y[i] - ref))) < EXPECT, (L, B, pad, layout, use_peak)
+
+def test_ragged_plan_is_cached_with_the_batch(golden):
+    """The launch plan (frame counts, tile prefix sums) depends on the lengths alone and stays with the RaggedBatch: a second forward
+    of the same batch, and forwards with another pad multiple, give the same results as fresh batches."""
+    fe = acb.LogMelFrontend("cuda")
+    clips = [torch.from_numpy(o.synth_clip(n, 70 + i)) for i, n in enumerate((16000, 40001, 24000, 9000))]
+    batch = acb.pack_clips(clips, torch.device("cuda"))
+    y1, f1 = fe.forward_ragged(batch, pad_multiple=4)
+    assert len(batch.plans) == 1
+    y2, f2 = fe.forward_ragged(batch, pad_multiple=4)
+    assert len(batch.plans) == 1 and torch.equal(y1, y2) and torch.equal(f1, f2)
+    y3, f3 = fe.forward_ragged(batch, pad_multiple=1)
+    assert len(batch.plans) == 2
+    fresh = acb.pack_clips(clips, torch.device("cuda"))
+    y4, f4 = fe.forward_ragged(fresh, pad_multiple=1)
+    assert torch.equal(y3, y4) and torch.equal(f3, f4)
+    assert f1.tolist() == [64, 160, 96, 36] and f3.tolist() == [63, 157, 94, 36]
+    acc = acb.MelStatsAccumulator(80, "cuda")
+    fe.forward_ragged(batch, pad_multiple=4, moments=acc, stats_only=True)            # the cached plan also carries the frame total
+    assert acc.frames == 64 + 160 + 96 + 36

@@ -93,7 +93,15 @@ def config4(args, fe, device, rank, world, dist):
     batch = acb.pack_clips(clips, device)
     affine = (acb.MEL_MEAN_DEFAULT, acb.MEL_STD_DEFAULT)
     feats, frames = fe.forward_ragged(batch, out_dtype=torch.bfloat16, affine=affine)
-    ms = timed(lambda: fe.forward_ragged(batch, out_dtype=torch.bfloat16, affine=affine, out=feats), 20)
+    def fresh_batch_step():                                 # a training loop sees every batch once: the tile plan is built per call
+        batch.plans.clear()
+        fe.forward_ragged(batch, out_dtype=torch.bfloat16, affine=affine, out=feats)
+    ms = timed(fresh_batch_step, 20)
+    # the launch alone: captured once in a CUDA graph (plan cached with the batch) and replayed -- no Python between launches
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fe.forward_ragged(batch, out_dtype=torch.bfloat16, affine=affine, out=feats)
+    ms_graph = timed(g.replay, 50)
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -104,7 +112,9 @@ def config4(args, fe, device, rank, world, dist):
     if rank == 0:
         emit(config=4, workload=f"ragged batch of {B} clips/GPU (0.5-20 s) -> [{B}, 80, {feats.shape[2]}] bf16 normalised, zero tail + lens",
              n_gpus=world, ms=ms, audio_hours_per_s=audio_s * world / 3600 / (ms * 1e-3), algorithmic_bytes=alg,
-             achieved_gbs=alg / (ms * 1e-3) / 1e9, roofline_frac=alg / (ms * 1e-3) / 1e9 / peak)
+             achieved_gbs=alg / (ms * 1e-3) / 1e9, roofline_frac=alg / (ms * 1e-3) / 1e9 / peak,
+             kernel_only_ms=ms_graph, kernel_only_roofline_frac=alg / (ms_graph * 1e-3) / 1e9 / peak,
+             valid_frames=int(frames.sum().item()), padded_frames=int(feats.shape[0] * feats.shape[2]))
 
 
 def config5(args, fe, device):
