@@ -1,5 +1,9 @@
 import numpy as np, torch, sys
 sys.path.insert(0,'/root/repo')
+import os
+import audio_calm_b200 as _acb
+if os.environ.get("ACB_LIB"):
+    _acb._lib.LIB_PATH = os.environ["ACB_LIB"]
 from audio_calm_b200 import spectral
 from oracle import spectral_oracle as so
 g=np.load('/root/repo/tests/golden/griffinlim_cases.npz')

@@ -35,6 +35,13 @@ VARIANTS = {
     "tcab3": ["-DACB_DEV", "-DACB_TC_ABLATE=3"],
     "tcab7": ["-DACB_DEV", "-DACB_TC_ABLATE=7"],
     "dev": ["-DACB_DEV"],
+    "gl2": ["-DACB_STFTC_FPC=2", "-DACB_ISTFT_FPC=2"],
+    "gl16": ["-DACB_STFTC_FPC=16", "-DACB_ISTFT_FPC=16"],
+    "gl8": ["-DACB_STFTC_FPC=8", "-DACB_ISTFT_FPC=8"],
+    "gl4": ["-DACB_STFTC_FPC=4", "-DACB_ISTFT_FPC=4"],
+    "gl32": ["-DACB_STFTC_FPC=32", "-DACB_ISTFT_FPC=32"],
+    "gl8_16": ["-DACB_STFTC_FPC=8", "-DACB_ISTFT_FPC=16"],
+    "gl16_8": ["-DACB_STFTC_FPC=16", "-DACB_ISTFT_FPC=8"],
     "b3p16": ["-DACBG_PREP_WARPS=16"],
     "epi16": ["-DACBG_EPI_WARPS=16"],
     "epi12": ["-DACBG_EPI_WARPS=12"],
