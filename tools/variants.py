@@ -35,6 +35,9 @@ VARIANTS = {
     "tcab3": ["-DACB_DEV", "-DACB_TC_ABLATE=3"],
     "tcab7": ["-DACB_DEV", "-DACB_TC_ABLATE=7"],
     "dev": ["-DACB_DEV"],
+    "hint1k": ["-DACBG_WAIT_HINT_NS=1000"],
+    "hint10k": ["-DACBG_WAIT_HINT_NS=10000"],
+    "hint100": ["-DACBG_WAIT_HINT_NS=100"],
     "gl2": ["-DACB_STFTC_FPC=2", "-DACB_ISTFT_FPC=2"],
     "gl16": ["-DACB_STFTC_FPC=16", "-DACB_ISTFT_FPC=16"],
     "gl8": ["-DACB_STFTC_FPC=8", "-DACB_ISTFT_FPC=8"],
