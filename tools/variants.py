@@ -35,6 +35,9 @@ VARIANTS = {
     "tcab3": ["-DACB_DEV", "-DACB_TC_ABLATE=3"],
     "tcab7": ["-DACB_DEV", "-DACB_TC_ABLATE=7"],
     "dev": ["-DACB_DEV"],
+    "p16": ["-DACBG_PREP_WARPS=16"],
+    "band8": ["-DACBG_BAND_COST=8"],
+    "band32": ["-DACBG_BAND_COST=32"],
     "hint1k": ["-DACBG_WAIT_HINT_NS=1000"],
     "hint10k": ["-DACBG_WAIT_HINT_NS=10000"],
     "hint100": ["-DACBG_WAIT_HINT_NS=100"],
