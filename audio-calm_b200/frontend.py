@@ -240,7 +240,8 @@ class LogMelFrontend:
         """Packed variable-length clips -> padded ``[B, n_mels, Tmax]`` (or ``[B, Tmax, n_mels]``) plus
         ``frames[B]`` (int64, valid = reflect-padded frame count per clip).  Frames beyond a clip's own count
         are set to ``fill_value`` (the training collator's ``audio_pad_val = 0.0``, train/train_calm.py:181,213-215).
-        Reflection happens at each clip's own ends."""
+        Reflection happens at each clip's own ends.  The launch plan and ``frames`` depend on the lengths alone and are kept in
+        ``batch.plans``: forwarding a batch again reuses them (the returned ``frames`` tensor is that cached one: treat it as read-only)."""
         self._check_wav(batch.wav)
         key = (self.n_fft, self.hop, int(pad_multiple))
         plan = batch.plans.get(key)
