@@ -602,3 +602,28 @@ def test_ragged_plan_is_cached_with_the_batch(golden):
     acc = acb.MelStatsAccumulator(80, "cuda")
     fe.forward_ragged(batch, pad_multiple=4, moments=acc, stats_only=True)            # the cached plan also carries the frame total
     assert acc.frames == 64 + 160 + 96 + 36
+
+def test_config2_size_independent_properties(fe):
+    """BASELINE config 2 at full size (256 x 30 s), checked through properties that need no oracle run: the batch split in two gives
+    the same bits; the same clips packed as a ragged batch give the same bits; the statistics-only launch, the fused moments and the
+    standalone moments over the stored features agree; a checksum of per-clip checksums is reproduced by a second launch."""
+    x = _device_clips(256, 480000, 4321)
+    y = fe.forward(x, pad_multiple=4)
+    assert tuple(y.shape) == (256, 80, 1876)
+    halves = torch.cat([fe.forward(x[:128], pad_multiple=4), fe.forward(x[128:], pad_multiple=4)])
+    assert torch.equal(halves, y)
+    batch = acb.pack_clips([x[i] for i in range(0, 256, 8)], torch.device("cuda"))      # every 8th clip, packed
+    yr, frames = fe.forward_ragged(batch, pad_multiple=4)
+    assert frames.tolist() == [1876] * 32 and torch.equal(yr, y[0:256:8])
+    fused, only, stored = (acb.MelStatsAccumulator(80, "cuda") for _ in range(3))
+    y2 = fe.forward(x, pad_multiple=4, moments=fused)
+    assert torch.equal(y2, y)
+    fe.forward(x, pad_multiple=4, moments=only, stats_only=True)
+    stored.update(y)
+    a, b, c = fused.finalize(), only.finalize(), stored.finalize()
+    assert a.frames == b.frames == c.frames == 256 * 1876 and a.count == 256 * 1876 * 80
+    assert np.array_equal(a.bin_mean, b.bin_mean) and np.array_equal(a.bin_std, b.bin_std)        # same kernel arithmetic
+    assert float(np.max(np.abs(a.bin_mean - c.bin_mean))) < 1e-6 and float(np.max(np.abs(a.bin_std - c.bin_std))) < 1e-6
+    per_clip = y.double().sum(dim=(1, 2))
+    assert float(per_clip.sum()) == float(fe.forward(x, pad_multiple=4).double().sum(dim=(1, 2)).sum())
+    assert abs(float(y.double().mean()) - c.mel_mean) < 1e-6                                      # the stored-feature statistics are the features' own
