@@ -25,10 +25,10 @@ int fail(int code, const std::string& msg);   // acb_kernels.cu: sets the thread
 #define ACB_STFT_RPC 32      // rows staged per CTA (upper bound)
 #endif
 #ifndef ACB_STFTC_FPC
-#define ACB_STFTC_FPC 8      // frames per CTA of the complex STFT (Griffin-Lim), upper bound
+#define ACB_STFTC_FPC 4      // frames per CTA of the complex STFT (Griffin-Lim), upper bound
 #endif
 #ifndef ACB_ISTFT_FPC
-#define ACB_ISTFT_FPC 8      // frames per CTA of the inverse STFT, upper bound
+#define ACB_ISTFT_FPC 4      // frames per CTA of the inverse STFT, upper bound
 #endif
 #ifndef ACB_STFT_BWD_RPC
 #define ACB_STFT_BWD_RPC 16  // rows per CTA of the backward kernel
@@ -488,7 +488,8 @@ __host__ __device__ inline ChunkSmem chunk_smem(int R, int frames_per_cta, int h
     L.y = off; off += with_spec ? (((frames_per_cta - 1) * hop + N + 3) & ~3) : 0;     // istft: the chunk's overlap-added output
     L.win = off; off += N;
     L.tw = off; off += 2 * N;
-    L.buf = off; off += (kThreads / R) * (2 * 33 * R);
+    const int groups = kThreads / R, pairs = (frames_per_cta + 1) / 2;                  // lane groups beyond the chunk's frame pairs never run a transform
+    L.buf = off; off += (groups < pairs ? groups : pairs) * (2 * 33 * R);
     L.total_bytes = off * 4;
     return L;
 }
@@ -703,10 +704,10 @@ __global__ void __launch_bounds__(256) istft_normalize_kernel(float* __restrict_
     }
 }
 
-// Frames per CTA of the chunked transforms (complex STFT / inverse STFT): 8 when that still gives about eight CTAs per SM, else 4 -- measured
-// on 32 Griffin-Lim iterations (n_fft 1024): 1 x 10 s 2.8 / 1.8 / 1.6 ms, 8 x 10 s 7.3 / 4.6 / 4.1 ms, 64 x 10 s 49 / 30.6 / 31.7 ms at 16 / 8 / 4
-// frames per CTA (16 frames leave one CTA per SM; the FFT of a chunk keeps only some of its warps busy, the staging and the
-// overlap-add all of them).
+// Frames per CTA of the chunked transforms (complex STFT / inverse STFT).  Measured on 32 Griffin-Lim iterations (n_fft 1024): 1 x 20 s
+// 2.8 / 1.8 / 1.6 ms, 8 x 20 s 7.3 / 4.6 / 4.1 ms, 64 x 20 s 49 / 30.6 / 29.3 ms at 16 / 8 / 4 frames per CTA (16 frames leave one CTA per SM;
+// the FFT of a chunk keeps only some of its warps busy, the staging and the overlap-add all of them; with the exchange buffers sized
+// by the chunk's frame pairs, 4 frames are 55 KB per CTA).  The upper bound is halved while the grid would not fill the chip.
 static int chunk_frames(int upper, int n_frames, int64_t rows) {
     int fpc = std::max(2, upper);
     while (fpc > 4 && (int64_t)((n_frames + fpc - 1) / fpc) * rows < 8 * 148) fpc >>= 1;
