@@ -84,7 +84,7 @@ __device__ __forceinline__ void group_fft_stage1(float2 (&pr)[16], float2 (&pi)[
     fft32_packed(pr, pi);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-        const float2 t0 = s_tw[r * k], t1 = s_tw[r * (k + 16)];
+        const float2 t0 = s_tw[k * R + r], t1 = s_tw[(k + 16) * R + r];     // table laid out [k][r]: a group's lanes read consecutive entries
         buf[k + 33 * r] = make_float2(fmaf(pr[k].x, t0.x, -pi[k].x * t0.y), fmaf(pr[k].x, t0.y, pi[k].x * t0.x));
         buf[k + 16 + 33 * r] = make_float2(fmaf(pr[k].y, t1.x, -pi[k].y * t1.y), fmaf(pr[k].y, t1.y, pi[k].y * t1.x));
     }
@@ -94,7 +94,8 @@ __device__ __forceinline__ void group_fft_stage2(float2* buf, int r) {
     constexpr int kPerLane = 32 / R;
 #pragma unroll
     for (int t = 0; t < kPerLane; ++t) {
-        const int k1 = r * kPerLane + t;
+        const int k1 = r + R * t;             // interleaved over the lanes: the group's lanes touch consecutive 8-byte slots (a blocked r * kPerLane + t
+                                              // put the 32 lanes of a warp on 4 of the 16 bank pairs)
         float2 v[R];
 #pragma unroll
         for (int rr = 0; rr < R; ++rr) v[rr] = buf[k1 + 33 * rr];
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restr
         for (int i = tid; i < N; i += kThreads) {
             s_win[i] = window[i];
             float sn, cs;
-            sincospif(2.f * (float)i / (float)N, &sn, &cs);
+            sincospif(2.f * (float)((i % R) * (i / R)) / (float)N, &sn, &cs);      // entry [k = i / R][r = i % R] = W_N^(r k)
             s_tw[i] = make_float2(cs, -sn);
         }
     }
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kThreads) stft_mag_backward_kernel(const float
     for (int i = tid; i < N; i += kThreads) {
         s_win[i] = window[i];
         float sn, cs;
-        sincospif(2.f * (float)i / (float)N, &sn, &cs);
+        sincospif(2.f * (float)((i % R) * (i / R)) / (float)N, &sn, &cs);      // entry [k = i / R][r = i % R] = W_N^(r k)
         s_tw[i] = make_float2(cs, -sn);
     }
     __syncthreads();
@@ -522,7 +523,7 @@ __global__ void __launch_bounds__(kThreads) stft_complex_kernel(const float* __r
         for (int i = tid; i < N; i += kThreads) {
             s_win[i] = window[i];
             float sn, cs;
-            sincospif(2.f * (float)i / (float)N, &sn, &cs);
+            sincospif(2.f * (float)((i % R) * (i / R)) / (float)N, &sn, &cs);      // entry [k = i / R][r = i % R] = W_N^(r k)
             s_tw[i] = make_float2(cs, -sn);
         }
     }
@@ -615,7 +616,7 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
     for (int i = tid; i < N; i += kThreads) {
         s_win[i] = window[i];
         float sn, cs;
-        sincospif(2.f * (float)i / (float)N, &sn, &cs);
+        sincospif(2.f * (float)((i % R) * (i / R)) / (float)N, &sn, &cs);      // entry [k = i / R][r = i % R] = W_N^(r k)
         s_tw[i] = make_float2(cs, -sn);
     }
     __syncthreads();
