@@ -105,6 +105,13 @@ __device__ __forceinline__ void group_fft_stage2(float2* buf, int r) {
     }
 }
 __device__ __forceinline__ int buf_index(int k) { return (k & 31) + 33 * (k >> 5); }
+// sqrt / reciprocal sqrt as ONE special-function instruction each (about 1 ulp / 2 ulp; the correctly rounded sqrtf and the IEEE
+// division are 8-10 instructions apiece, paid twice per bin): the parity tolerance of these kernels is 1e-4 of the magnitudes
+__device__ __forceinline__ float sqrt_fast(float x) {
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // Bank swizzle of the staged rows.  The R lanes of a group read samples base + R j + r (j = 0..31), and the 32 / R groups of a warp work on
 // frames whose bases differ by multiples of the hop (8 R floats for hop = n_fft / 4) -- a multiple of 16, 32 or 64 banks: unswizzled,
@@ -272,8 +279,8 @@ __global__ void __launch_bounds__(kThreads) stft_mag_kernel(const float* __restr
                 const int kc = (N - k) & (N - 1);
                 const float2 z = buf[(k & 31) + 33 * (k >> 5)], zc = buf[(kc & 31) + 33 * (kc >> 5)];
                 const float apc = z.x + zc.x, bmd = z.y - zc.y, amc = z.x - zc.x, bpd = z.y + zc.y;
-                oa[(size_t)k * n_frames] = 0.5f * sqrtf(fmaf(apc, apc, bmd * bmd));
-                if (valid_b) ob[(size_t)k * n_frames] = 0.5f * sqrtf(fmaf(amc, amc, bpd * bpd));
+                oa[(size_t)k * n_frames] = 0.5f * sqrt_fast(fmaf(apc, apc, bmd * bmd));
+                if (valid_b) ob[(size_t)k * n_frames] = 0.5f * sqrt_fast(fmaf(amc, amc, bpd * bpd));
             }
         }
         __syncwarp();
@@ -406,9 +413,9 @@ __global__ void __launch_bounds__(kThreads) stft_mag_backward_kernel(const float
                 const float2 z = buf[buf_index(k)], zc = buf[buf_index(kc)];
                 const float xar = 0.5f * (z.x + zc.x), xai = 0.5f * (z.y - zc.y);          // X_A[k]
                 const float xbr = 0.5f * (z.y + zc.y), xbi = -0.5f * (z.x - zc.x);         // X_B[k]
-                const float ma = sqrtf(fmaf(xar, xar, xai * xai)), mb = sqrtf(fmaf(xbr, xbr, xbi * xbi));
-                const float sa = ma > 0.f ? ga[(size_t)k * n_frames] / ma : 0.f;
-                const float sb = (valid_b && mb > 0.f) ? gb[(size_t)k * n_frames] / mb : 0.f;
+                const float pa = fmaf(xar, xar, xai * xai), pb = fmaf(xbr, xbr, xbi * xbi);   // |X|^2; g / |X| = g * rsqrt(|X|^2)
+                const float sa = pa > 0.f ? ga[(size_t)k * n_frames] * rsqrtf(pa) : 0.f;
+                const float sb = (valid_b && pb > 0.f) ? gb[(size_t)k * n_frames] * rsqrtf(pb) : 0.f;
                 const float har = sa * xar, hai = -sa * xai;                                // h_A = g conj(X_A) / |X_A|
                 const float hbr = sb * xbr, hbi = -sb * xbi;
                 if (k == 0 || 2 * k == N) {
@@ -589,7 +596,7 @@ __global__ void __launch_bounds__(kThreads) stft_complex_kernel(const float* __r
             if (mag != nullptr) {      // one Griffin-Lim phase update: angles = (rebuilt - m * previous) / (|.| + 1e-16); out = angles * magnitude
                 tprev[o[u]] = w;
                 const float ar = fmaf(-momentum, prev[u].x, w.x), ai = fmaf(-momentum, prev[u].y, w.y);
-                const float inv = 1.f / (sqrtf(fmaf(ar, ar, ai * ai)) + 1e-16f);
+                const float inv = __fdividef(1.f, sqrt_fast(fmaf(ar, ar, ai * ai)) + 1e-16f);     // two special-function instructions instead of ~20
                 w = make_float2(ar * inv * m[u], ai * inv * m[u]);
             }
             spec_out[o[u]] = w;
