@@ -629,6 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
         // ================================================ workers ================================================
         const int wtid = tid;                       // 0..255
         uint32_t gs = 0, smp_uses = 0, tile_iter = 0;
+        const int b_begin = p.band_group[warp], b_end = p.band_group[warp + 1];     // this warp's bands of the mel pass (read once: an indexed parameter load)
         const float clamp_min = p.clamp_min, log_scale = p.log_scale, log_floor = p.log_floor;
         const long long cap = p.frame_capacity;
 
@@ -770,7 +771,6 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 const int frame0 = tic * kTileFrames + 4 * lane;
                 const int n_valid = clip_frames - frame0;             // frames of this lane that exist (<= 0: none)
                 const int n_store = p.frames_out - frame0;            // frames of this lane inside the row (the rest of them get fill_value)
-                const int b_begin = p.band_group[warp], b_end = p.band_group[warp + 1];
                 long long out_col = (long long)clip * p.out_clip_stride + (long long)b_begin * cap + frame0;    // element index in out
                 const int esize = p.out_bf16 ? 2 : 4;
                 // four consecutive frames of a band go out as one 16-byte (fp32) / 8-byte (bf16) store when every row keeps them aligned
@@ -778,8 +778,10 @@ __global__ void __launch_bounds__(kThreads, 1) dftgemm_logmel_kernel(const Param
                 float vmax = -3.0e38f, vmin = 3.0e38f, chk = 0.f;
                 const float clamp_eff = clamp_min / post, log_post = post == 1.f ? 0.f : log2f(post) * log_scale;
                 const float4* pow4 = reinterpret_cast<const float4*>(s_pow) + lane;
+                int4 bd_next = s_band[b_begin];               // a band's record is fetched while the previous band is being finished
                 for (int b = b_begin; b < b_end; ++b, out_col += cap) {
-                    const int4 bd = s_band[b];
+                    const int4 bd = bd_next;
+                    bd_next = s_band[min(b + 1, p.n_mels - 1)];
                     const float4* pp = pow4 + bd.x * (kTileFrames / 4);
                     const float* ww = s_melw + bd.z;
                     float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
