@@ -717,8 +717,10 @@ __global__ void __launch_bounds__(256) istft_normalize_kernel(float* __restrict_
 // the FFT of a chunk keeps only some of its warps busy, the staging and the overlap-add all of them; with the exchange buffers sized
 // by the chunk's frame pairs, 4 frames are 55 KB per CTA).  The upper bound is halved while the grid would not fill the chip.
 static int chunk_frames(int upper, int n_frames, int64_t rows) {
+    int dev = 0, sms = 0;   // SM count of the current device (148 on a B200)
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
     int fpc = std::max(2, upper);
-    while (fpc > 4 && (int64_t)((n_frames + fpc - 1) / fpc) * rows < 8 * 148) fpc >>= 1;
+    while (fpc > 4 && (int64_t)((n_frames + fpc - 1) / fpc) * rows < 8 * (int64_t)sms) fpc >>= 1;
     return fpc;
 }
 
