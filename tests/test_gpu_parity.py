@@ -627,3 +627,34 @@ def test_config2_size_independent_properties(fe):
     per_clip = y.double().sum(dim=(1, 2))
     assert float(per_clip.sum()) == float(fe.forward(x, pad_multiple=4).double().sum(dim=(1, 2)).sum())
     assert abs(float(y.double().mean()) - c.mel_mean) < 1e-6                                      # the stored-feature statistics are the features' own
+
+
+def test_config2_domain_properties(fe):
+    """BASELINE config 2 at full size through the properties of the transform itself (no oracle run needed):
+    * amplitude: scaling the waveform by a power of two shifts every un-clamped ln-mel value by 2 ln(a) -- exactly, because a power of
+      two commutes with every rounding of the STFT and the mel sum; clamped values stay at the floor;
+    * time: dropping the first 8 hops of a clip shifts the frames by one tile; frames whose windows do not touch the reflected
+      edges see the same samples in the same tile positions and come out bit-identical;
+    * peak normalisation: the fused gain (clip_peak) agrees with forwarding the waveform process_audio_chunk has scaled
+      (preprocess/core.py:108-110) to the rounding of one multiplication;
+    * pad-to-4: the reflected columns repeat frames T-2-j (process_dataset.py:147-150)."""
+    x = _device_clips(256, 480000, 2468)
+    y = fe.forward(x)
+    floor = float(FLOOR)
+    ys = fe.forward(x * 0.25)
+    live = (y > floor + 3.0) & (ys > floor)                         # well above the clamp before and after the scaling
+    assert float(live.float().mean()) > 0.8
+    shift = np.float32(2.0 * np.log(0.25))
+    assert float(((ys - y)[live] - shift).abs().max()) < 4e-6        # the fp32 roundings of ln(m / 16) against ln(m) + ln(1/16)
+    assert torch.equal(ys[y == floor], y[y == floor])               # silence stays at the floor
+    cut = 8 * 256
+    yc = fe.forward(x[:32, cut:].contiguous())
+    assert tuple(yc.shape) == (32, 80, 1876 - 8)
+    assert torch.equal(yc[:, :, 8:1860], y[:32, :, 16:1868])         # interior frames: same samples, same lanes
+    peak = fe.peak_abs(x)
+    fused = fe.forward(x, peak=peak)
+    scaled = torch.stack([process_audio_chunk(x[i:i + 1])[0] for i in range(0, 256, 37)])
+    assert float((fe.forward(scaled) - fused[0:256:37]).abs().max()) < EXPECT
+    y4 = fe.forward(x[:8, :480000 - 300], pad_multiple=4)           # T = 1875 -> one reflected column
+    assert tuple(y4.shape) == (8, 80, 1876) and torch.equal(y4[:, :, 1875], y4[:, :, 1873])
+    fe.check()
