@@ -681,16 +681,16 @@ __global__ void __launch_bounds__(G * kGroupThreads, G == 4 ? 1 : 2) logmel_fuse
                         s += cv;
                         s2 = fmaf(cv, vB, s2);
                     }
-                    // the 4 pair lanes of a slot are a contiguous, aligned lane group (all 32 lanes take part)
-#pragma unroll
-                    for (int o = 2; o >= 1; o >>= 1) {
-                        s += __shfl_xor_sync(0xffffffffu, s, o);
-                        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                    }
-                    if (pl == 0 && b >= 0) {   // each band has exactly one owner slot per group
-                        two_sum_add(s_mom[b], s);
-                        two_sum_add(s_mom[n_mels + b], s2);
-                    }
+                    // The 4 pair lanes of a slot are a contiguous, aligned lane group (all 32 lanes take part).  Lanes 0, 1 of the group
+                    // end up with the sum, lanes 2, 3 with the sum of squares: in the first step a lane hands over the value its half
+                    // does not keep, so two shuffles reduce both, and ONE compensated add per round -- lane 0 into the band's sum,
+                    // lane 2 into its sum of squares -- updates both accumulators.  Same additions in the same order as reducing the
+                    // two values separately ((v0 + v2) + (v1 + v3)): the moments are bit-identical.
+                    const bool upper = (pl & 2) != 0;
+                    float keep = (upper ? s2 : s) + __shfl_xor_sync(0xffffffffu, upper ? s : s2, 2);
+                    keep += __shfl_xor_sync(0xffffffffu, keep, 1);
+                    if ((pl & 1) == 0 && b >= 0)   // each band has exactly one owner slot per group
+                        two_sum_add(s_mom[(upper ? n_mels : 0) + b], keep);
                 }
                 if (b >= 0) {
                     vA = fmaf(vA, af.x, af.y);
