@@ -182,6 +182,13 @@ struct SmemLayout {
 
 __host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }   // odd: conflict-free both ways
 
+// Kernels without the moment accumulators: every offset is a compile-time constant of the kernel -- the regions whose size depends on
+// the filterbank are sized for kMaxMels (the per-band affine pairs) or placed last (the plan's weights) -- so that no shared-memory
+// address has to be derived from kernel parameters inside the tile loop (at the 128-register cap the compiler re-derived the
+// mbarrier's, the plan records' and the weights' addresses every iteration instead of keeping them: 0.4633 -> 0.4548 ms at config 2).
+// The kernels WITH moments keep the parameter-dependent order: measured with the constant one, 0.545 -> 0.565 ms for the ragged
+// statistics launch and 0.512 -> 0.533 ms for features + moments (the register allocation of the longer mel epilogue changes for the
+// worse; tools/stats_step.py).
 __host__ __device__ inline SmemLayout make_smem_layout(int kGroups, int n_mels, int n_plan_w, bool with_moments = false) {
     SmemLayout L;
     int off = 0;  // in 4-byte words
@@ -189,12 +196,21 @@ __host__ __device__ inline SmemLayout make_smem_layout(int kGroups, int n_mels, 
     L.scratch = off; off += kGroups * kGroupWarps * kScratchFloats;
     L.twiddle = off; off += 5 * 32 * 4;
     L.window = off; off += 32 * 20;                               // first half only (w[n + N/2] = 1 - w[n]), per lane with a 20-float pitch
-    L.plan_w = off; off += (n_plan_w + 3) & ~3;
-    L.affine = off; off += 2 * ((n_mels + 1) & ~1);
-    off = (off + 3) & ~3;
-    L.plan_rec = off; off += kGroupWarps * kMaxRounds * kSlots * 4;       // int4 per (warp, round, slot): the mel phase's per-lane constants
-    L.mbar = off; off += 2 * kGroups;                                     // one 8-byte mbarrier per group ("sample tile landed")
-    L.moments = off; if (with_moments) off += kGroups * 4 * n_mels;       // float2 [kGroups][2][n_mels]
+    if (!with_moments) {
+        L.plan_rec = off; off += kGroupWarps * kMaxRounds * kSlots * 4;   // int4 per (warp, round, slot): the mel phase's per-lane constants
+        L.mbar = off; off += 2 * kGroups;                                 // one 8-byte mbarrier per group ("sample tile landed")
+        off = (off + 3) & ~3;
+        L.affine = off; off += 2 * kMaxMels;                              // float2 per band
+        L.plan_w = off; off += (n_plan_w + 3) & ~3;                       // last: the only region of variable size
+        L.moments = off;
+    } else {
+        L.plan_w = off; off += (n_plan_w + 3) & ~3;
+        L.affine = off; off += 2 * ((n_mels + 1) & ~1);
+        off = (off + 3) & ~3;
+        L.plan_rec = off; off += kGroupWarps * kMaxRounds * kSlots * 4;
+        L.mbar = off; off += 2 * kGroups;
+        L.moments = off; off += kGroups * 4 * n_mels;                     // float2 [kGroups][2][n_mels]
+    }
     L.total_bytes = off * 4;
     return L;
 }
@@ -1816,12 +1832,13 @@ int acb_frontend_create(acb_frontend** out, int device, int n_fft, int hop, int 
     // The attribute is per function, not per handle: several front-ends (different n_mels) may live in one process, so it is
     // always raised to the device's opt-in maximum; the launch passes the handle's own size.
     const int optin = (int)prop.sharedMemPerBlockOptin;
-    fe->groups = make_smem_layout(kMaxGroups, n_mels, fe->n_plan_w, true).total_bytes <= optin ? kMaxGroups : 2;
+    fe->groups = std::max(make_smem_layout(kMaxGroups, n_mels, fe->n_plan_w, true).total_bytes,
+                          make_smem_layout(kMaxGroups, n_mels, fe->n_plan_w, false).total_bytes) <= optin ? kMaxGroups : 2;
     const SmemLayout L = make_smem_layout(fe->groups, n_mels, fe->n_plan_w, false);
     const SmemLayout Lm = make_smem_layout(fe->groups, n_mels, fe->n_plan_w, true);
     fe->smem_bytes = L.total_bytes;
     fe->smem_bytes_moments = Lm.total_bytes;
-    if (e == cudaSuccess && Lm.total_bytes > optin) {
+    if (e == cudaSuccess && std::max(L.total_bytes, Lm.total_bytes) > optin) {
         if (fe->d_blob) cudaFree(fe->d_blob);
         delete fe;
         cudaSetDevice(prev);
