@@ -188,7 +188,7 @@ __host__ __device__ inline int out_row_stride(int n_mels) { return n_mels | 1; }
 // mbarrier's, the plan records' and the weights' addresses every iteration instead of keeping them: 0.4633 -> 0.4548 ms at config 2).
 // The kernels WITH moments keep the parameter-dependent order: measured with the constant one, 0.545 -> 0.565 ms for the ragged
 // statistics launch and 0.512 -> 0.533 ms for features + moments (the register allocation of the longer mel epilogue changes for the
-// worse; tools/stats_step.py).
+// worse; tools/stats_step.py; constant addresses for the plan records and the barrier alone: 0.571 ms).
 __host__ __device__ inline SmemLayout make_smem_layout(int kGroups, int n_mels, int n_plan_w, bool with_moments = false) {
     SmemLayout L;
     int off = 0;  // in 4-byte words
