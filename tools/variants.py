@@ -17,6 +17,9 @@ OUT = os.path.join(ROOT, "tools", "_variants")
 
 VARIANTS = {
     "base": [],
+    "rul3": ["-Xptxas", "--register-usage-level=3"],
+    "rul7": ["-Xptxas", "--register-usage-level=7"],
+    "rul10": ["-Xptxas", "--register-usage-level=10"],
     "sstaged": ["-DACB_STFT_DIRECT=0"],
     "bwd8": ["-DACB_STFT_BWD_RPC=8"],
     "bwd4": ["-DACB_STFT_BWD_RPC=4"],
